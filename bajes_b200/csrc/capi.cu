@@ -1,0 +1,610 @@
+// C ABI of bajes_b200 (see include/bajes_b200.h).  Host-side context management, static table
+// construction (the set-up rows of SURVEY.md section 8a: Detector.store_measurement,
+// detector.py:452-493) and kernel launches.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "roq_relbin.cuh"
+
+using namespace bj;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(BJ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* bj_last_error(void) { return g_last_error.c_str(); }
+extern "C" int bj_abi_version(void) { return BJ_ABI_VERSION; }
+
+extern "C" int bj_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
+                              int* clock_khz) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(BJ_ERR_NO_DEVICE, "no CUDA device visible");
+    }
+    if (device < 0 || device >= n) return fail(BJ_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (name && name_len > 0) {
+        strncpy(name, p.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    if (clock_khz) *clock_khz = khz;
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+enum { KIND_FULLGRID = 0, KIND_ROQ = 1, KIND_RELBIN = 2 };
+
+struct bj_ctx {
+    int kind = KIND_FULLGRID;
+    int device = 0;
+    int sm_count = 0;
+    int sincos = BJ_SINCOS_MUFU;
+    DeviceConfig cfg;
+    // full grid
+    long n_bins = 0;
+    int rec_doubles = 0;
+    double* d_rec = nullptr;
+    double* d_freqs = nullptr;
+    int bins_per_chunk = 0;
+    int n_chunks = 0;
+    // ROQ / relbin static tables
+    RoqDevice roq;
+    RelbinDevice relbin;
+    // per-call workspace (grown on demand)
+    long cap_walkers = 0;
+    double* d_coef = nullptr;
+    double* d_partial = nullptr;
+    double* d_x = nullptr;
+    long cap_x = 0;
+    double* d_logl = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    int launch_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static int check_config(const bj_config* cfg) {
+    if (!cfg) return fail(BJ_ERR_INVALID, "null config");
+    if (cfg->abi_version != BJ_ABI_VERSION)
+        return fail(BJ_ERR_INVALID, "ABI version mismatch: caller %d, library %d", cfg->abi_version, BJ_ABI_VERSION);
+    if (cfg->n_ifo < 1 || cfg->n_ifo > BJ_MAX_IFO)
+        return fail(BJ_ERR_UNSUPPORTED, "n_ifo=%d outside 1..%d", cfg->n_ifo, BJ_MAX_IFO);
+    if (cfg->approx < 0 || cfg->approx > BJ_APPROX_TAYLORF2_55PN_75PNTIDES2020)
+        return fail(BJ_ERR_UNSUPPORTED, "approximant id %d is not a TaylorF2 variant", cfg->approx);
+    if (cfg->sincos < 0 || cfg->sincos > BJ_SINCOS_FP64) return fail(BJ_ERR_INVALID, "bad sincos mode %d", cfg->sincos);
+    if (!(cfg->seglen > 0)) return fail(BJ_ERR_INVALID, "seglen must be positive");
+    return BJ_OK;
+}
+
+static int init_common(bj_ctx* c, const bj_config* cfg) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(BJ_ERR_NO_DEVICE, "no CUDA device visible: bajes_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= n) return fail(BJ_ERR_INVALID, "device %d out of range", cfg->device);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, cfg->device));
+    if (p.major != 10)
+        return fail(BJ_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                    p.major, p.minor);
+    c->device = cfg->device;
+    c->sm_count = p.multiProcessorCount;
+    c->sincos = cfg->sincos;
+    c->cfg.approx = cfg->approx;
+    c->cfg.n_ifo = cfg->n_ifo;
+    c->cfg.marg_phi_ref = cfg->marg_phi_ref;
+    c->cfg.seglen = cfg->seglen;
+    c->cfg.dd_sum = cfg->dd_sum;
+    c->cfg.logZ_noise = cfg->logZ_noise;
+    for (int i = 0; i < BJ_MAX_IFO; ++i) c->cfg.det[i] = cfg->det[i];
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+    return BJ_OK;
+}
+
+template <int NIFO>
+static void build_records(std::vector<double>& rec, long n, const double* freqs, const double* const* data_ri,
+                          const double* const* psd, double seglen) {
+    constexpr int RS = Rec<NIFO>::kDoubles;
+    rec.assign((size_t)n * RS, 0.0);
+    const double four_over_t = 4.0 / seglen;
+    for (long k = 0; k < n; ++k) {
+        const double f = freqs[k];
+        double* r = &rec[(size_t)k * RS];
+        const double u = std::cbrt(f);
+        r[0] = u;
+        r[1] = std::log(f);
+        r[2] = 1.0 / (u * u * u * u * u);
+        r[3] = f;
+        // exp(+i pi f T): exactly +-1 on the FFT grid (waveform.py:392-393)
+        const double kk = f * seglen;
+        const double kr = std::nearbyint(kk);
+        double cs, sn;
+        if (std::fabs(kk - kr) < 1e-6) {
+            cs = (std::fmod(std::fabs(kr), 2.0) == 1.0) ? -1.0 : 1.0;
+            sn = 0.0;
+        } else {
+            cs = std::cos(M_PI * kk);
+            sn = std::sin(M_PI * kk);
+        }
+        const double g = std::pow(f, -7.0 / 6.0);
+        for (int i = 0; i < NIFO; ++i) {
+            const double inv_s = 1.0 / psd[i][k];   // psd = inf outside the ASD table -> weight 0
+            const double dre = data_ri[i][2 * k], dim = data_ri[i][2 * k + 1];
+            // (4/T) conj(d)/S * g * (cs + i sn)
+            const double wr = four_over_t * inv_s * g;
+            const double cre = dre, cim = -dim;
+            r[4 + 2 * i] = wr * (cre * cs - cim * sn);
+            r[5 + 2 * i] = wr * (cre * sn + cim * cs);
+            r[4 + 2 * NIFO + i] = four_over_t * inv_s * g * g;
+        }
+    }
+}
+
+extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
+                         const double* const* data_ri, const double* const* psd) {
+    if (!out) return fail(BJ_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (n_bins <= 0 || !freqs || !data_ri || !psd) return fail(BJ_ERR_INVALID, "empty frequency axis or null tables");
+    for (int64_t k = 0; k < n_bins; ++k)
+        if (!(freqs[k] > 0.0) || !std::isfinite(freqs[k]))
+            return fail(BJ_ERR_INVALID, "freqs[%lld]=%g: in-band frequencies must be positive and finite", (long long)k,
+                        freqs[k]);
+    bj_ctx* c = new bj_ctx();
+    rc = init_common(c, cfg);
+    if (rc) { delete c; return rc; }
+    c->kind = KIND_FULLGRID;
+    c->n_bins = n_bins;
+    std::vector<double> rec;
+    switch (cfg->n_ifo) {
+        case 1: build_records<1>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<1>::kDoubles; break;
+        case 2: build_records<2>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<2>::kDoubles; break;
+        default: build_records<3>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<3>::kDoubles; break;
+    }
+    for (size_t i = 0; i < rec.size(); ++i)
+        if (!std::isfinite(rec[i])) {
+            bj_destroy(c);
+            return fail(BJ_ERR_INVALID, "non-finite static table entry at bin %zu (check data / PSD)", i / c->rec_doubles);
+        }
+    // frequency chunking depends on n_bins ONLY, so the reduction tree (and every output bit) is
+    // independent of how many walkers a call or a rank evaluates
+    long per = (n_bins + 127) / 128;
+    per = ((per + kTileBins - 1) / kTileBins) * kTileBins;
+    if (per < 256) per = 256;
+    c->bins_per_chunk = (int)per;
+    c->n_chunks = (int)((n_bins + per - 1) / per);
+    cudaError_t e = cudaMalloc(&c->d_rec, rec.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_freqs, (size_t)n_bins * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_freqs, freqs, (size_t)n_bins * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        bj_destroy(c);
+        return fail(BJ_ERR_CUDA, "uploading static tables failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return BJ_OK;
+}
+
+extern "C" int bj_destroy(bj_ctx* c) {
+    if (!c) return BJ_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_rec);
+    cudaFree(c->d_freqs);
+    cudaFree(c->d_coef);
+    cudaFree(c->d_partial);
+    cudaFree(c->d_x);
+    cudaFree(c->d_logl);
+    c->roq.release();
+    c->relbin.release();
+    for (int i = 0; i < 4; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return BJ_OK;
+}
+
+static long pad_walkers(long w) { return ((w + 127) / 128) * 128; }
+
+static int ensure_workspace(bj_ctx* c, long n_walkers) {
+    if (n_walkers <= c->cap_walkers) return BJ_OK;
+    long cap = pad_walkers(n_walkers);
+    if (cap < 2 * c->cap_walkers && 2 * c->cap_walkers >= n_walkers) cap = pad_walkers(2 * c->cap_walkers);
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_coef); c->d_coef = nullptr;
+    cudaFree(c->d_partial); c->d_partial = nullptr;
+    cudaFree(c->d_logl); c->d_logl = nullptr;
+    c->cap_walkers = 0;
+    CUDA_TRY(cudaMalloc(&c->d_coef, (size_t)C_NUM * cap * sizeof(double)));
+    size_t part = 0;
+    if (c->kind == KIND_FULLGRID) part = (size_t)c->n_chunks * 3 * c->cfg.n_ifo * cap;
+    if (part) CUDA_TRY(cudaMalloc(&c->d_partial, part * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->d_logl, (size_t)cap * sizeof(double)));
+    c->cap_walkers = cap;
+    return BJ_OK;
+}
+
+static void to_dev_map(const bj_param_map* m, ParamMapDev& d) {
+    for (int i = 0; i < BJ_NUM_PARAMS; ++i) {
+        d.column[i] = m->column[i];
+        d.value[i] = m->value[i];
+    }
+}
+
+static int check_map(const bj_param_map* m, int ndim) {
+    if (!m) return fail(BJ_ERR_INVALID, "null parameter map");
+    for (int i = 0; i < BJ_NUM_PARAMS; ++i) {
+        int col = m->column[i];
+        if (col >= ndim || col < BJ_COL_ABSENT) return fail(BJ_ERR_INVALID, "parameter slot %d maps to column %d (ndim=%d)", i, col, ndim);
+    }
+    auto present = [&](int s) { return m->column[s] != BJ_COL_ABSENT; };
+    if (!present(BJ_P_Q)) return fail(BJ_ERR_INVALID, "parameter 'q' is required");
+    if (!present(BJ_P_MCHIRP) && !present(BJ_P_MTOT)) return fail(BJ_ERR_INVALID, "one of 'mchirp' / 'mtot' is required");
+    if (!present(BJ_P_COS_IOTA) && !present(BJ_P_IOTA)) return fail(BJ_ERR_INVALID, "one of 'cos_iota' / 'iota' is required");
+    const int need[] = {BJ_P_DISTANCE, BJ_P_RA, BJ_P_DEC, BJ_P_PSI, BJ_P_TIME_SHIFT, BJ_P_PHI_REF, BJ_P_T_GPS};
+    for (int s : need)
+        if (!present(s)) return fail(BJ_ERR_INVALID, "required parameter slot %d is absent", s);
+    return BJ_OK;
+}
+
+template <int NIFO, int MODEL, int SC>
+static int launch_fullgrid_t(bj_ctx* c, long n_walkers, cudaStream_t st) {
+    constexpr int RS = Rec<NIFO>::kDoubles;
+    const size_t smem = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
+    auto kern = fullgrid_kernel<NIFO, MODEL, SC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
+    kern<<<grid, kThreads, smem, st>>>(c->d_rec, c->n_bins, c->bins_per_chunk, c->d_coef, c->cap_walkers, n_walkers,
+                                       c->d_partial);
+    CUDA_TRY(cudaGetLastError());
+    c->launch_info[0] = (int)grid.x;
+    c->launch_info[1] = (int)grid.y;
+    c->launch_info[2] = kThreads;
+    c->launch_info[3] = (int)smem;
+    c->launch_info[4] = c->bins_per_chunk;
+    c->launch_info[5] = c->n_chunks;
+    c->launch_info[6] = RS;
+    c->launch_info[7] = MODEL;
+    return BJ_OK;
+}
+
+template <int NIFO, int MODEL>
+static int launch_fullgrid_m(bj_ctx* c, long n_walkers, cudaStream_t st) {
+    switch (c->sincos) {
+        case BJ_SINCOS_MUFU: return launch_fullgrid_t<NIFO, MODEL, BJ_SINCOS_MUFU>(c, n_walkers, st);
+        case BJ_SINCOS_POLY32: return launch_fullgrid_t<NIFO, MODEL, BJ_SINCOS_POLY32>(c, n_walkers, st);
+        default: return launch_fullgrid_t<NIFO, MODEL, BJ_SINCOS_FP64>(c, n_walkers, st);
+    }
+}
+
+template <int NIFO>
+static int launch_fullgrid_n(bj_ctx* c, long n_walkers, cudaStream_t st) {
+    if (c->cfg.approx == BJ_APPROX_TAYLORF2_35PN) return launch_fullgrid_m<NIFO, MODEL_35>(c, n_walkers, st);
+    return launch_fullgrid_m<NIFO, MODEL_GENERIC>(c, n_walkers, st);
+}
+
+static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, const bj_param_map* map,
+                      double* out_logl_dev, double* out_parts_dev, cudaStream_t st) {
+    int rc = check_map(map, ndim);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = ensure_workspace(c, n_walkers);
+    if (rc) return rc;
+    ParamMapDev pm;
+    to_dev_map(map, pm);
+    const int tpb = 128;
+    const unsigned nblk = (unsigned)((n_walkers + tpb - 1) / tpb);
+    CUDA_TRY(cudaEventRecord(c->ev[0], st));
+    prologue_kernel<<<nblk, tpb, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev[1], st));
+    if (c->kind == KIND_FULLGRID) {
+        switch (c->cfg.n_ifo) {
+            case 1: rc = launch_fullgrid_n<1>(c, n_walkers, st); break;
+            case 2: rc = launch_fullgrid_n<2>(c, n_walkers, st); break;
+            default: rc = launch_fullgrid_n<3>(c, n_walkers, st); break;
+        }
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev[2], st));
+        epilogue_kernel<<<nblk, tpb, 0, st>>>(c->cfg, c->d_partial, c->n_chunks, c->d_coef, c->cap_walkers, n_walkers,
+                                              out_logl_dev, out_parts_dev);
+        CUDA_TRY(cudaGetLastError());
+    } else if (c->kind == KIND_ROQ) {
+        rc = launch_roq(c->cfg, c->roq, c->d_coef, c->cap_walkers, n_walkers, out_logl_dev, out_parts_dev, st,
+                        c->launch_info);
+        if (rc) return fail(BJ_ERR_CUDA, "ROQ kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    } else {
+        rc = launch_relbin(c->cfg, c->relbin, c->d_coef, c->cap_walkers, n_walkers, out_logl_dev, out_parts_dev, st,
+                           c->launch_info);
+        if (rc) return fail(BJ_ERR_CUDA, "relative-binning kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[3], st));
+    c->timed = true;
+    return BJ_OK;
+}
+
+extern "C" int bj_loglike_device(bj_ctx* c, const double* x_dev, int64_t n_walkers, int32_t ndim,
+                                 const bj_param_map* map, double* out_logl_dev, double* out_parts_dev, void* stream) {
+    if (!c) return fail(BJ_ERR_INVALID, "null context");
+    if (n_walkers == 0) return BJ_OK;
+    if (n_walkers < 0 || ndim <= 0 || !x_dev || !out_logl_dev) return fail(BJ_ERR_INVALID, "bad batch arguments");
+    return run_device(c, x_dev, (long)n_walkers, ndim, map, out_logl_dev, out_parts_dev, (cudaStream_t)stream);
+}
+
+extern "C" int bj_loglike(bj_ctx* c, const double* x_host, int64_t n_walkers, int32_t ndim, const bj_param_map* map,
+                          double* out_logl_host) {
+    if (!c) return fail(BJ_ERR_INVALID, "null context");
+    if (n_walkers == 0) return BJ_OK;
+    if (n_walkers < 0 || ndim <= 0 || !x_host || !out_logl_host) return fail(BJ_ERR_INVALID, "bad batch arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const long need = (long)n_walkers * ndim;
+    if (need > c->cap_x) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(c->d_x);
+        c->d_x = nullptr;
+        c->cap_x = 0;
+        CUDA_TRY(cudaMalloc(&c->d_x, (size_t)need * sizeof(double)));
+        c->cap_x = need;
+    }
+    int rc = ensure_workspace(c, (long)n_walkers);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->d_x, x_host, (size_t)need * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    rc = run_device(c, c->d_x, (long)n_walkers, ndim, map, c->d_logl, nullptr, c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_logl_host, c->d_logl, (size_t)n_walkers * sizeof(double), cudaMemcpyDeviceToHost,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return BJ_OK;
+}
+
+extern "C" int bj_last_kernel_ms(bj_ctx* c, float* ms3) {
+    if (!c || !ms3) return fail(BJ_ERR_INVALID, "null argument");
+    if (!c->timed) return fail(BJ_ERR_INVALID, "no call has been timed yet");
+    CUDA_TRY(cudaEventSynchronize(c->ev[3]));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms3[i], c->ev[i], c->ev[i + 1]));
+    return BJ_OK;
+}
+
+extern "C" int bj_last_launch_info(bj_ctx* c, int32_t* info8) {
+    if (!c || !info8) return fail(BJ_ERR_INVALID, "null argument");
+    for (int i = 0; i < 8; ++i) info8[i] = c->launch_info[i];
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-point waveform entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int bj_project_waveform(bj_ctx* c, const double* x_host, int32_t ndim, const bj_param_map* map,
+                                   double* out_h_host) {
+    if (!c || !x_host || !out_h_host) return fail(BJ_ERR_INVALID, "null argument");
+    if (c->kind != KIND_FULLGRID) return fail(BJ_ERR_INVALID, "bj_project_waveform needs a full-grid context");
+    int rc = check_map(map, ndim);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = ensure_workspace(c, 1);
+    if (rc) return rc;
+    double* d_x = nullptr;
+    double2* d_h = nullptr;
+    CUDA_TRY(cudaMalloc(&d_x, ndim * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_h, (size_t)c->cfg.n_ifo * c->n_bins * sizeof(double2));
+    if (e != cudaSuccess) { cudaFree(d_x); return fail(BJ_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    ParamMapDev pm;
+    to_dev_map(map, pm);
+    cudaMemcpyAsync(d_x, x_host, ndim * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    prologue_kernel<<<1, 32, 0, c->stream>>>(c->cfg, pm, d_x, ndim, 1, c->d_coef, c->cap_walkers);
+    const unsigned nblk = (unsigned)((c->n_bins + 255) / 256);
+    waveform_kernel<<<nblk, 256, 0, c->stream>>>(c->cfg, c->d_freqs, c->n_bins, c->d_coef, c->cap_walkers, d_h);
+    cudaMemcpyAsync(out_h_host, d_h, (size_t)c->cfg.n_ifo * c->n_bins * sizeof(double2), cudaMemcpyDeviceToHost,
+                    c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_x);
+    cudaFree(d_h);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "waveform kernel failed: %s", cudaGetErrorString(e));
+    return BJ_OK;
+}
+
+extern "C" int bj_polarizations(int device, int approx, double seglen, int centre_shift, int64_t n_freqs,
+                                const double* freqs, const double* x_host, int32_t ndim, const bj_param_map* map,
+                                double* out_hp_host, double* out_hc_host) {
+    if (!freqs || !x_host || !out_hp_host || !out_hc_host || n_freqs <= 0) return fail(BJ_ERR_INVALID, "null / empty argument");
+    if (approx < 0 || approx > BJ_APPROX_TAYLORF2_55PN_75PNTIDES2020)
+        return fail(BJ_ERR_UNSUPPORTED, "approximant id %d is not a TaylorF2 variant", approx);
+    // the polarisations do not depend on the sky position: fill the detector-only slots if absent
+    bj_param_map m = *map;
+    const int sky[] = {BJ_P_RA, BJ_P_DEC, BJ_P_PSI, BJ_P_TIME_SHIFT, BJ_P_T_GPS};
+    for (int s : sky)
+        if (m.column[s] == BJ_COL_ABSENT) { m.column[s] = BJ_COL_CONST; m.value[s] = 0.0; }
+    int rc = check_map(&m, ndim);
+    if (rc) return rc;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(BJ_ERR_NO_DEVICE, "no CUDA device visible: bajes_b200 has no CPU fallback");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.approx = approx;
+    cfg.n_ifo = 0;
+    cfg.seglen = seglen;
+    ParamMapDev pm;
+    to_dev_map(&m, pm);
+    double *d_x = nullptr, *d_f = nullptr, *d_coef = nullptr;
+    double2 *d_hp = nullptr, *d_hc = nullptr;
+    cudaError_t e = cudaMalloc(&d_x, ndim * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_f, (size_t)n_freqs * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_coef, (size_t)C_NUM * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_hp, (size_t)n_freqs * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_hc, (size_t)n_freqs * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMemcpy(d_x, x_host, ndim * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_f, freqs, (size_t)n_freqs * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        prologue_kernel<<<1, 32>>>(cfg, pm, d_x, ndim, 1, d_coef, 1);
+        polarizations_kernel<<<(unsigned)((n_freqs + 255) / 256), 256>>>(seglen, centre_shift, d_f, n_freqs, d_coef, 1,
+                                                                         d_hp, d_hc);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_hp_host, d_hp, (size_t)n_freqs * sizeof(double2), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_hc_host, d_hc, (size_t)n_freqs * sizeof(double2), cudaMemcpyDeviceToHost);
+    cudaFree(d_x); cudaFree(d_f); cudaFree(d_coef); cudaFree(d_hp); cudaFree(d_hc);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "bj_polarizations: %s", cudaGetErrorString(e));
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROQ / relative binning contexts
+// ------------------------------------------------------------------------------------------------
+extern "C" int bj_roq_create(bj_ctx** out, const bj_config* cfg, const bj_roq_tables* tab) {
+    if (!out) return fail(BJ_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (!tab || tab->n_join <= 0 || tab->n_lin <= 0 || tab->n_quad <= 0 || tab->n_coef < 4 || tab->n_knots != tab->n_coef + 4)
+        return fail(BJ_ERR_INVALID, "inconsistent ROQ tables (need a cubic B-spline: n_knots == n_coef + 4)");
+    bj_ctx* c = new bj_ctx();
+    rc = init_common(c, cfg);
+    if (rc) { delete c; return rc; }
+    c->kind = KIND_ROQ;
+    cudaError_t e = c->roq.upload(cfg->n_ifo, tab);
+    if (e != cudaSuccess) {
+        bj_destroy(c);
+        return fail(BJ_ERR_CUDA, "uploading ROQ tables failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return BJ_OK;
+}
+
+extern "C" int bj_relbin_create(bj_ctx** out, const bj_config* cfg, int64_t n_edges, const double* fbin,
+                                const double* const* h0_ri, const double* sdat_ri) {
+    if (!out) return fail(BJ_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (n_edges < 2 || !fbin || !h0_ri || !sdat_ri) return fail(BJ_ERR_INVALID, "bad relative-binning tables");
+    bj_ctx* c = new bj_ctx();
+    rc = init_common(c, cfg);
+    if (rc) { delete c; return rc; }
+    c->kind = KIND_RELBIN;
+    cudaError_t e = c->relbin.upload(cfg->n_ifo, cfg->seglen, n_edges, fbin, h0_ri, sdat_ri);
+    if (e != cudaSuccess) {
+        bj_destroy(c);
+        return fail(BJ_ERR_CUDA, "uploading relative-binning tables failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// issue-rate micro-benchmarks (roofline denominators for the FP64 / MUFU bound kernels)
+// ------------------------------------------------------------------------------------------------
+__global__ void peak_dfma_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, b = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void peak_mufu_kernel(float* out, int iters, float seed) {
+    float a0 = seed + threadIdx.x * 1e-3f, a1 = a0 + .1f, a2 = a0 + .2f, a3 = a0 + .3f, a4 = a0 + .4f, a5 = a0 + .5f,
+          a6 = a0 + .6f, a7 = a0 + .7f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            a0 = __sinf(a0); a1 = __cosf(a1); a2 = __sinf(a2); a3 = __cosf(a3);
+            a4 = __sinf(a4); a5 = __cosf(a5); a6 = __sinf(a6); a7 = __cosf(a7);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int bj_measure_peak(int device, int which, double* out) {
+    if (!out) return fail(BJ_ERR_INVALID, "null out");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(BJ_ERR_NO_DEVICE, "no CUDA device visible");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    const int threads = 256, blocks = p.multiProcessorCount * 8;
+    const int iters = which == 0 ? 4096 : 2048;
+    void* buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        if (which == 0) peak_dfma_kernel<<<blocks, threads>>>((double*)buf, iters, 1.0);
+        else            peak_mufu_kernel<<<blocks, threads>>>((float*)buf, iters, 0.5f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double instr = (double)threads * blocks * (double)iters * (which == 0 ? 64.0 : 32.0);
+        const double rate = instr / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "peak kernel failed: %s", cudaGetErrorString(e));
+    *out = best;
+    return BJ_OK;
+}

@@ -1,0 +1,106 @@
+"""
+Multi-GPU evaluation: the walker batch is sharded across the ranks of a ``torch.distributed`` group
+(one process per GPU, NCCL over NVLink; gloo on CPU for tests).  Walkers are independent
+(``Posterior.log_like`` is a pure function of one point; the reference farms points to workers the same
+way, bajes/pipe/utils/mpi.py:120-159), so the data path has NO collective: each walker's whole reduction
+happens on one GPU and results are bit-identical for any number of ranks.  The only communication is
+the plumbing around it -- broadcast of the [W, ndim] parameter block from the sampler rank and an
+all-gather of the W log-likelihoods (8 MB at W = 2^20: latency-, not bandwidth-bound).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+
+def shard_bounds(n: int, world: int):
+    """Contiguous, balanced slices: rank r owns [lo[r], hi[r])."""
+    base, rem = divmod(n, world)
+    lo = [r * base + min(r, rem) for r in range(world)]
+    hi = [lo[r] + base + (1 if r < rem else 0) for r in range(world)]
+    return lo, hi
+
+
+class ShardedEvaluator:
+    """``evaluate(X)``: rank ``src`` supplies X [W, ndim]; every rank returns the full logL [W].
+
+    ``local_eval(X_slice) -> logL_slice`` is the per-rank worker: on a GPU box it is
+    ``lambda Xs: like.log_like_batch(Xs, names, const)`` (or the device-pointer variant below); the CPU
+    tests pass any pure function.
+    """
+
+    def __init__(self, local_eval: Callable[[np.ndarray], np.ndarray], ndim: int, group=None, device=None, src=0):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.dist = dist
+        self.local_eval = local_eval
+        self.ndim = int(ndim)
+        self.group = group
+        self.src = src
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device if device is not None else torch.device("cpu")
+
+    def evaluate(self, X: Optional[np.ndarray]) -> np.ndarray:
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return np.asarray(self.local_eval(np.ascontiguousarray(X, dtype=np.float64)))
+        # 1. batch size, then the parameter block, from the sampler rank
+        n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if self.rank == self.src:
+            n[0] = len(X)
+        dist.broadcast(n, src=self.src, group=self.group)
+        W = int(n.item())
+        if self.rank == self.src:
+            xt = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(self.device)
+        else:
+            xt = torch.empty((W, self.ndim), dtype=torch.float64, device=self.device)
+        dist.broadcast(xt, src=self.src, group=self.group)
+        # 2. each rank evaluates its contiguous slice (no data-path collective)
+        lo, hi = shard_bounds(W, self.world)
+        mine = xt[lo[self.rank]:hi[self.rank]]
+        out = np.asarray(self.local_eval(mine.cpu().numpy()), dtype=np.float64)
+        # 3. all-gather (padded to equal chunks so one collective suffices)
+        chunk = max(h - l for l, h in zip(lo, hi))
+        send = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
+        send[:len(out)] = torch.as_tensor(out).to(self.device)
+        recv = torch.empty(chunk * self.world, dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        recv = recv.cpu().numpy().reshape(self.world, chunk)
+        return np.concatenate([recv[r, :hi[r] - lo[r]] for r in range(self.world)])
+
+
+class DeviceShardedLikelihood:
+    """Device-resident variant used by bench.py: X stays in HBM, the kernel entry takes device pointers,
+    logL is all-gathered with NCCL.  ``like`` is a ``GWLikelihood`` living on this rank's GPU."""
+
+    def __init__(self, like, names: Sequence[str], const: dict, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.like = like
+        self.pmap = like.param_map(names, const)
+        self.ndim = len(names)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device("cuda", like.device)
+
+    def evaluate_local(self, x_dev, out_dev, parts_dev=None):
+        """x_dev [w, ndim] float64 CUDA tensor (this rank's slice) -> out_dev [w]; asynchronous on the
+        current torch stream."""
+        torch = self.torch
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self.like.engine.loglike_device(x_dev.data_ptr(), x_dev.shape[0], self.ndim, self.pmap, out_dev.data_ptr(),
+                                        parts_dev.data_ptr() if parts_dev is not None else 0, st)
+        return out_dev
+
+    def gather(self, out_dev):
+        """all-gather of equally sized per-rank logL vectors -> [world * w]."""
+        if self.world == 1:
+            return out_dev
+        recv = self.torch.empty(out_dev.numel() * self.world, dtype=out_dev.dtype, device=out_dev.device)
+        self.dist.all_gather_into_tensor(recv, out_dev, group=self.group)
+        return recv

@@ -1,0 +1,369 @@
+"""
+ctypes binding of ``libbajes_b200.so`` (C ABI in ``include/bajes_b200.h``).
+
+This is the binding a bajes maintainer would add: bajes is pure Python, so
+its "FFI" for the likelihood path is ctypes over plain pointers.  There is NO CPU fallback:
+a missing library or a missing B200 raises ``EngineUnavailable`` loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+BJ_ABI_VERSION = 1
+BJ_MAX_IFO = 3
+BJ_COL_CONST = -1
+BJ_COL_ABSENT = -2
+
+PARAM_SLOTS = (
+    "mchirp", "mtot", "q",
+    "s1x", "s1y", "s1z", "s2x", "s2y", "s2z",
+    "s1", "tilt1", "phi_1l", "s2", "tilt2", "phi_2l",
+    "lambda1", "lambda2",
+    "distance", "cos_iota", "iota",
+    "ra", "dec", "psi", "time_shift", "phi_ref", "t_gps",
+)
+BJ_NUM_PARAMS = len(PARAM_SLOTS)
+SLOT_INDEX = {n: i for i, n in enumerate(PARAM_SLOTS)}
+
+# bajes/obs/gw/waveform.py:72-86
+APPROX_IDS = {
+    "TaylorF2_3.5PN": 0,
+    "TaylorF2_5.5PN": 1,
+    "TaylorF2_5.5PN_7.5PNTides": 2,
+    "TaylorF2_5.5PN_3.5PNQM_7.5PNTides": 3,
+    "TaylorF2_5.5PN_7.5PNTides2020": 4,
+}
+SINCOS_MODES = {"mufu": 0, "poly32": 1, "fp64": 2}
+
+LIB_NAME = "libbajes_b200.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
+
+
+class EngineUnavailable(RuntimeError):
+    """The CUDA library or a usable B200 is missing.  There is deliberately no CPU fallback."""
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class bj_param_map(C.Structure):
+    _fields_ = [("column", C.c_int32 * BJ_NUM_PARAMS), ("value", C.c_double * BJ_NUM_PARAMS)]
+
+
+class bj_detector(C.Structure):
+    _fields_ = [("response", C.c_double * 9), ("location", C.c_double * 3),
+                ("gmst_reference", C.c_double), ("reference_time", C.c_double), ("sday", C.c_double)]
+
+
+class bj_config(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("approx", C.c_int32),
+                ("n_ifo", C.c_int32), ("marg_phi_ref", C.c_int32), ("sincos", C.c_int32),
+                ("seglen", C.c_double), ("dd_sum", C.c_double), ("logZ_noise", C.c_double),
+                ("det", bj_detector * BJ_MAX_IFO)]
+
+
+class bj_roq_tables(C.Structure):
+    _fields_ = [("n_join", C.c_int64), ("freqs_join", C.POINTER(C.c_double)),
+                ("n_lin", C.c_int64), ("mask_omega", C.POINTER(C.c_int32)),
+                ("n_quad", C.c_int64), ("mask_psi", C.POINTER(C.c_int32)),
+                ("n_knots", C.c_int64), ("n_coef", C.c_int64),
+                ("knots", C.POINTER(C.POINTER(C.c_double))),
+                ("coef_ri", C.POINTER(C.POINTER(C.c_double))),
+                ("psi_weights", C.POINTER(C.POINTER(C.c_double))),
+                ("tc_min", C.c_double), ("tc_max", C.c_double)]
+
+
+_DP = C.POINTER(C.c_double)
+_DPP = C.POINTER(_DP)
+
+# every symbol include/bajes_b200.h declares: name -> (restype, argtypes)
+EXPORTS = {
+    "bj_last_error": (C.c_char_p, []),
+    "bj_abi_version": (C.c_int, []),
+    "bj_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bj_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(bj_config), C.c_int64, _DP, _DPP, _DPP]),
+    "bj_destroy": (C.c_int, [C.c_void_p]),
+    "bj_loglike": (C.c_int, [C.c_void_p, _DP, C.c_int64, C.c_int32, C.POINTER(bj_param_map), _DP]),
+    "bj_loglike_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(bj_param_map),
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bj_project_waveform": (C.c_int, [C.c_void_p, _DP, C.c_int32, C.POINTER(bj_param_map), _DP]),
+    "bj_polarizations": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int64, _DP, _DP, C.c_int32,
+                                   C.POINTER(bj_param_map), _DP, _DP]),
+    "bj_roq_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(bj_config), C.POINTER(bj_roq_tables)]),
+    "bj_relbin_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(bj_config), C.c_int64, _DP, _DPP, _DP]),
+    "bj_measure_peak": (C.c_int, [C.c_int, C.c_int, _DP]),
+    "bj_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "bj_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+}
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the in-tree library and bind every exported symbol (raises if any is missing)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EngineUnavailable(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  bajes_b200 has no CPU fallback." % p)
+    try:
+        lib = C.CDLL(p)
+    except OSError as exc:  # pragma: no cover
+        raise EngineUnavailable("cannot load %s: %s" % (p, exc)) from exc
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bj_abi_version() != BJ_ABI_VERSION:
+        raise EngineUnavailable("ABI mismatch: library %d, binding %d" % (lib.bj_abi_version(), BJ_ABI_VERSION))
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(lib, rc: int, what: str):
+    if rc == 0:
+        return
+    msg = lib.bj_last_error().decode("utf-8", "replace")
+    if rc == -4:
+        raise EngineUnavailable("%s: %s" % (what, msg))
+    if rc == -3:
+        raise NotImplementedError("%s: %s" % (what, msg))
+    raise EngineError("%s failed (status %d): %s" % (what, rc, msg))
+
+
+def device_info(device: int = 0) -> Dict[str, object]:
+    lib = load_library()
+    name = C.create_string_buffer(128)
+    sm, maj, mnr, khz = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib, lib.bj_device_info(device, name, 128, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(khz)),
+           "bj_device_info")
+    return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value), "clock_khz": khz.value}
+
+
+def measure_peak(which: str, device: int = 0) -> float:
+    """Issue-rate micro-benchmark: 'dfma' or 'mufu' thread-instructions per second."""
+    lib = load_library()
+    out = C.c_double()
+    _check(lib, lib.bj_measure_peak(device, {"dfma": 0, "mufu": 1}[which], C.byref(out)), "bj_measure_peak")
+    return out.value
+
+
+def _as_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_DP)
+
+
+def _ptr_array(arrs: Sequence[np.ndarray]):
+    out = (_DP * len(arrs))()
+    for i, a in enumerate(arrs):
+        out[i] = _ptr(a)
+    return out
+
+
+class ParamMap:
+    """names -> columns of the batch array, plus constants (replaces Prior.this_sample +
+    the dict parsing in Waveform.compute_hphc; bajes/inf/prior.py:262-269, waveform.py:334-377)."""
+
+    UNSUPPORTED_PREFIXES = ("spcal_", "weight", "eos_")
+
+    def __init__(self, names: Sequence[str], const: Optional[Dict[str, float]] = None):
+        const = dict(const or {})
+        self.names = list(names)
+        self.ndim = len(self.names)
+        for n in list(self.names) + list(const):
+            if n.startswith(self.UNSUPPORTED_PREFIXES) and n != "weights":
+                raise NotImplementedError(
+                    "parameter '%s' (calibration envelopes / PSD weights / EOS sampling) is outside the "
+                    "fused GPU likelihood; there is no CPU fallback" % n)
+        self.c = bj_param_map()
+        for i in range(BJ_NUM_PARAMS):
+            self.c.column[i] = BJ_COL_ABSENT
+            self.c.value[i] = 0.0
+        for n, v in const.items():
+            if n in SLOT_INDEX and isinstance(v, (int, float, np.integer, np.floating)):
+                self.c.column[SLOT_INDEX[n]] = BJ_COL_CONST
+                self.c.value[SLOT_INDEX[n]] = float(v)
+        for col, n in enumerate(self.names):
+            if n in SLOT_INDEX:
+                self.c.column[SLOT_INDEX[n]] = col
+        self.ignored = [n for n in self.names if n not in SLOT_INDEX]
+
+    @classmethod
+    def from_dict(cls, params: Dict[str, float]):
+        """Map for a single parameter dict (GWLikelihood.log_like(params))."""
+        names = [n for n in PARAM_SLOTS if n in params]
+        m = cls(names, {})
+        x = np.array([float(params[n]) for n in names], dtype=np.float64)
+        return m, x
+
+    def present(self, name: str) -> bool:
+        return self.c.column[SLOT_INDEX[name]] != BJ_COL_ABSENT
+
+
+def make_config(device, approx, n_ifo, seglen, dets, marg_phi_ref=False, sincos="mufu",
+                dd_sum=0.0, logZ_noise=0.0) -> bj_config:
+    if approx not in APPROX_IDS:
+        raise NotImplementedError(
+            "approximant '%s' is not in the fused GPU path (TaylorF2 family only: %s)" % (approx, list(APPROX_IDS)))
+    cfg = bj_config()
+    cfg.abi_version = BJ_ABI_VERSION
+    cfg.device = int(device)
+    cfg.approx = APPROX_IDS[approx]
+    cfg.n_ifo = int(n_ifo)
+    cfg.marg_phi_ref = 1 if marg_phi_ref else 0
+    cfg.sincos = SINCOS_MODES[sincos]
+    cfg.seglen = float(seglen)
+    cfg.dd_sum = float(dd_sum)
+    cfg.logZ_noise = float(logZ_noise)
+    for i, d in enumerate(dets):
+        resp = np.asarray(d["response"], dtype=np.float64).reshape(9)
+        loc = np.asarray(d["location"], dtype=np.float64).reshape(3)
+        for j in range(9):
+            cfg.det[i].response[j] = resp[j]
+        for j in range(3):
+            cfg.det[i].location[j] = loc[j]
+        cfg.det[i].gmst_reference = float(d["gmst_reference"])
+        cfg.det[i].reference_time = float(d["reference_time"])
+        cfg.det[i].sday = float(d["sday"])
+    return cfg
+
+
+class Engine:
+    """Owns one ``bj_ctx``.  ``kind`` in {'fullgrid', 'roq', 'relbin'}."""
+
+    def __init__(self, handle, n_ifo: int, kind: str, n_bins: int = 0):
+        self._lib = load_library()
+        self._h = handle
+        self.n_ifo = n_ifo
+        self.kind = kind
+        self.n_bins = n_bins
+
+    # -- constructors --------------------------------------------------------------------------
+    @classmethod
+    def fullgrid(cls, cfg: bj_config, freqs, datas, psds) -> "Engine":
+        lib = load_library()
+        freqs = _as_f64(freqs)
+        d_ri = [np.ascontiguousarray(np.asarray(d, dtype=np.complex128)).view(np.float64) for d in datas]
+        p = [_as_f64(x) for x in psds]
+        for a in d_ri:
+            assert a.size == 2 * freqs.size
+        for a in p:
+            assert a.size == freqs.size
+        h = C.c_void_p()
+        _check(lib, lib.bj_create(C.byref(h), C.byref(cfg), freqs.size, _ptr(freqs), _ptr_array(d_ri), _ptr_array(p)),
+               "bj_create")
+        return cls(h, cfg.n_ifo, "fullgrid", freqs.size)
+
+    @classmethod
+    def roq(cls, cfg: bj_config, freqs_join, mask_omega, mask_psi, knots, coefs, psi_weights, tc_min, tc_max):
+        lib = load_library()
+        fj = _as_f64(freqs_join)
+        mo = np.ascontiguousarray(mask_omega, dtype=np.int32)
+        mp = np.ascontiguousarray(mask_psi, dtype=np.int32)
+        kn = [_as_f64(k) for k in knots]
+        cf = [np.ascontiguousarray(np.asarray(c, dtype=np.complex128)).view(np.float64) for c in coefs]
+        ps = [_as_f64(p) for p in psi_weights]
+        n_coef = np.asarray(coefs[0]).shape[0]
+        assert np.asarray(coefs[0]).shape[1] == mo.size
+        t = bj_roq_tables()
+        t.n_join, t.freqs_join = fj.size, _ptr(fj)
+        t.n_lin, t.mask_omega = mo.size, mo.ctypes.data_as(C.POINTER(C.c_int32))
+        t.n_quad, t.mask_psi = mp.size, mp.ctypes.data_as(C.POINTER(C.c_int32))
+        t.n_knots, t.n_coef = kn[0].size, n_coef
+        ka, ca, pa = _ptr_array(kn), _ptr_array(cf), _ptr_array(ps)
+        t.knots, t.coef_ri, t.psi_weights = ka, ca, pa
+        t.tc_min, t.tc_max = float(tc_min), float(tc_max)
+        h = C.c_void_p()
+        _check(lib, lib.bj_roq_create(C.byref(h), C.byref(cfg), C.byref(t)), "bj_roq_create")
+        return cls(h, cfg.n_ifo, "roq")
+
+    @classmethod
+    def relbin(cls, cfg: bj_config, fbin, h0_edges, sdat):
+        lib = load_library()
+        fb = _as_f64(fbin)
+        h0 = [np.ascontiguousarray(np.asarray(h, dtype=np.complex128)).view(np.float64) for h in h0_edges]
+        sd = np.ascontiguousarray(np.asarray(sdat, dtype=np.complex128)).view(np.float64)
+        assert sd.size == 4 * cfg.n_ifo * (fb.size - 1) * 2
+        h = C.c_void_p()
+        _check(lib, lib.bj_relbin_create(C.byref(h), C.byref(cfg), fb.size, _ptr(fb), _ptr_array(h0), _ptr(sd)),
+               "bj_relbin_create")
+        return cls(h, cfg.n_ifo, "relbin")
+
+    # -- calls ----------------------------------------------------------------------------------
+    def loglike(self, x: np.ndarray, pmap: ParamMap) -> np.ndarray:
+        """Host arrays in / out (copies are inside the call)."""
+        x = _as_f64(x)
+        if x.ndim == 1:
+            x = x.reshape(1, -1)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        if x.shape[0] == 0:
+            return out
+        _check(self._lib, self._lib.bj_loglike(self._h, _ptr(x), x.shape[0], x.shape[1], C.byref(pmap.c), _ptr(out)),
+               "bj_loglike")
+        return out
+
+    def loglike_device(self, x_ptr: int, n_walkers: int, ndim: int, pmap: ParamMap, out_ptr: int,
+                       parts_ptr: int = 0, stream: int = 0) -> None:
+        """Device pointers (ints), asynchronous on ``stream`` (a cudaStream_t handle as int)."""
+        _check(self._lib,
+               self._lib.bj_loglike_device(self._h, C.c_void_p(x_ptr), n_walkers, ndim, C.byref(pmap.c),
+                                           C.c_void_p(out_ptr), C.c_void_p(parts_ptr or None),
+                                           C.c_void_p(stream or None)),
+               "bj_loglike_device")
+
+    def project_waveform(self, x: np.ndarray, pmap: ParamMap) -> np.ndarray:
+        x = _as_f64(x).reshape(-1)
+        out = np.empty((self.n_ifo, self.n_bins), dtype=np.complex128)
+        _check(self._lib, self._lib.bj_project_waveform(self._h, _ptr(x), x.size, C.byref(pmap.c),
+                                                        out.view(np.float64).ctypes.data_as(_DP)),
+               "bj_project_waveform")
+        return out
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        _check(self._lib, self._lib.bj_last_kernel_ms(self._h, ms), "bj_last_kernel_ms")
+        return [ms[0], ms[1], ms[2]]
+
+    def last_launch_info(self):
+        info = (C.c_int32 * 8)()
+        _check(self._lib, self._lib.bj_last_launch_info(self._h, info), "bj_last_launch_info")
+        return list(info)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bj_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def polarizations(approx: str, seglen: float, freqs, x: np.ndarray, pmap: ParamMap, centre_shift=True, device=0):
+    lib = load_library()
+    if approx not in APPROX_IDS:
+        raise NotImplementedError("approximant '%s' is not in the fused GPU path" % approx)
+    f = _as_f64(freqs)
+    x = _as_f64(x).reshape(-1)
+    hp = np.empty(f.size, dtype=np.complex128)
+    hc = np.empty(f.size, dtype=np.complex128)
+    _check(lib, lib.bj_polarizations(device, APPROX_IDS[approx], float(seglen), 1 if centre_shift else 0, f.size,
+                                     _ptr(f), _ptr(x), x.size, C.byref(pmap.c),
+                                     hp.view(np.float64).ctypes.data_as(_DP), hc.view(np.float64).ctypes.data_as(_DP)),
+           "bj_polarizations")
+    return hp, hc

@@ -1,0 +1,288 @@
+"""
+Drop-in ``GWLikelihood`` (bajes/pipe/log_like.py:21-183) backed by the fused sm_100a kernels, plus the
+batched entry points the sampler adapters call, and the ``Likelihood`` / ``Posterior`` wrappers of
+bajes/inf/likelihood.py with batched counterparts.
+
+Per-point ``log_like(params)`` keeps the reference contract (dict in, float out, ``-inf`` for
+unphysical points) and is evaluated on the GPU as a batch of one.  There is no CPU code path for
+the likelihood: without the CUDA library / a B200 the constructor raises ``EngineUnavailable``.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import engine as _engine
+from .waveform import Waveform
+
+logger = logging.getLogger(__name__)
+
+
+class Likelihood(object):
+    """Generic likelihood wrapper (bajes/inf/likelihood.py:9-33)."""
+
+    def __init__(self, func=None, args=[], kwargs={}):
+        self.logZ_noise = 0.0
+        self._func = func
+        self._args = args
+        self._kwargs = kwargs
+
+    def log_like(self, x):
+        if self._func is None:
+            raise RuntimeError("Log-likelihood method has been called without specifying the likelihood form. "
+                               "Please implement your Likelihood.")
+        logl = self._func(x, *self._args, **self._kwargs)
+        if np.isnan(logl):
+            raise RuntimeError("Likelihood method returned NaN for the set of parameters: {}.".format(x))
+        return logl
+
+
+class GWLikelihood(Likelihood):
+    """Frequency-domain Gaussian likelihood  Re(d|h) - (h|h)/2  over a detector network."""
+
+    def __init__(self, ifos, datas, dets, noises, freqs, srate, seglen, approx,
+                 nspcal=0, spcal_freqs=None, nweights=0, len_weights=None,
+                 marg_phi_ref=False, marg_time_shift=False, roq=None,
+                 device=0, sincos="mufu", **kwargs):
+        super(GWLikelihood, self).__init__()
+        self.ifos = list(ifos)
+        self.dets = dets
+        self.roq = roq
+        self.nspcal = nspcal
+        self.nweights = nweights
+        self.marg_phi_ref = marg_phi_ref
+        self.marg_time_shift = marg_time_shift
+        self.device = device
+        self.sincos = sincos
+        self.approx = approx
+        self.srate = srate
+        self.seglen = seglen
+
+        if self.roq is not None and self.marg_time_shift:
+            raise AttributeError("Time-shift marginalization has not been implemented with the ROQ approximation.")
+        if self.marg_time_shift:
+            raise NotImplementedError("time-shift marginalisation needs the per-bin <d|h> array + FFT per point and "
+                                      "is not part of the fused GPU likelihood (SURVEY.md section 8e/f N4)")
+        if nspcal or nweights:
+            raise NotImplementedError("spectral calibration envelopes / PSD weights are not in the fused GPU "
+                                      "likelihood yet (SURVEY.md section 8f N3); there is no CPU fallback")
+        if len(self.ifos) > _engine.BJ_MAX_IFO:
+            raise NotImplementedError("more than %d detectors in one fused pass" % _engine.BJ_MAX_IFO)
+
+        # consistency checks of log_like.py:57-96
+        n_freqs = f_min_check = f_max_check = None
+        mask = None
+        for ifo in self.ifos:
+            self.dets[ifo].store_measurement(datas[ifo], noises[ifo], nspcal, spcal_freqs, nweights, len_weights)
+            self.dets[ifo]._owner = self
+            if f_min_check is None:
+                f_min_check = datas[ifo].f_min
+            elif datas[ifo].f_min != f_min_check:
+                raise ValueError("Input f_min of data and model do not match in detector {}.".format(ifo))
+            if f_max_check is None:
+                f_max_check = datas[ifo].f_max
+            elif datas[ifo].f_max != f_max_check:
+                raise ValueError("Input f_max of data and model do not match in detector {}.".format(ifo))
+            if n_freqs is None:
+                n_freqs = len(datas[ifo].freqs)
+            elif len(datas[ifo].freqs) != n_freqs:
+                raise ValueError("Number of data samples does not match in detector {}.".format(ifo))
+            if datas[ifo].seglen != seglen:
+                raise ValueError("Input seglen of data and model do not match in detector {}.".format(ifo))
+            self.logZ_noise += -0.5 * self.dets[ifo]._dd
+            self.Nfr = n_freqs
+            mask = datas[ifo].mask
+
+        freqs = np.asarray(freqs)
+        if self.roq is not None:
+            self.wave = Waveform(self.roq["freqs_join"], srate, seglen, approx, device=device)
+        else:
+            self.wave = Waveform(freqs[mask], srate, seglen, approx, device=device)
+        self._engine = None
+        self._build_engine()
+
+    # ---- engine life cycle ------------------------------------------------------------------------
+    def _config(self):
+        dd_sum = 0.0
+        for ifo in self.ifos:
+            dd_sum += np.real(self.dets[ifo]._dd)
+        return _engine.make_config(self.device, self.approx, len(self.ifos), self.seglen,
+                                   [self.dets[i].constants() for i in self.ifos],
+                                   marg_phi_ref=self.marg_phi_ref, sincos=self.sincos,
+                                   dd_sum=dd_sum, logZ_noise=self.logZ_noise)
+
+    def _build_engine(self):
+        cfg = self._config()
+        if self.roq is None:
+            d0 = self.dets[self.ifos[0]]
+            self._engine = _engine.Engine.fullgrid(cfg, d0.freqs,
+                                                   [self.dets[i].data for i in self.ifos],
+                                                   [self.dets[i].psd for i in self.ifos])
+        else:
+            from .roq import spline_tables
+            knots, coefs, tc_min, tc_max = [], [], None, None
+            for ifo in self.ifos:
+                t, c, lo, hi = spline_tables(self.roq[ifo]["omega_weights_interp"])
+                knots.append(t)
+                coefs.append(c)
+                tc_min = lo if tc_min is None else max(tc_min, lo)
+                tc_max = hi if tc_max is None else min(tc_max, hi)
+            self._engine = _engine.Engine.roq(cfg, self.roq["freqs_join"], self.roq["mask_omega"],
+                                              self.roq["mask_psi"], knots, coefs,
+                                              [self.roq[i]["psi_weights"] for i in self.ifos], tc_min, tc_max)
+
+    @property
+    def engine(self):
+        if self._engine is None:        # after unpickling: re-upload lazily
+            self._build_engine()
+        return self._engine
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_engine"] = None         # device handles never travel through pickle
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        for ifo in self.ifos:
+            self.dets[ifo]._owner = self
+
+    # ---- evaluation -------------------------------------------------------------------------------
+    def param_map(self, names: Sequence[str], const: Optional[Dict[str, float]] = None) -> _engine.ParamMap:
+        return _engine.ParamMap(names, const)
+
+    def log_like_batch(self, X, names: Sequence[str], const: Optional[Dict[str, float]] = None) -> np.ndarray:
+        """``[log_like({**dict(zip(names, x)), **const}) for x in X]`` in one GPU call.
+        X: float64 [W, ndim] host array; returns float64 [W]."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2 or X.shape[1] != len(names):
+            raise ValueError("X must be [n_points, %d]" % len(names))
+        return self.engine.loglike(X, self.param_map(names, const))
+
+    def log_like(self, params):
+        """Reference per-point contract (log_like.py:107-183): dict -> float."""
+        sub = _physical_subset(params)
+        pmap, x = _engine.ParamMap.from_dict(sub)
+        return float(self.engine.loglike(x.reshape(1, -1), pmap)[0])
+
+    def _parts(self, params):
+        """per-detector Re<d|h>, Im<d|h>, <h|h> of one point via the device entry."""
+        import torch
+        sub = _physical_subset(params)
+        pmap, x = _engine.ParamMap.from_dict(sub)
+        dev = torch.device("cuda", self.device)
+        xd = torch.from_numpy(x.reshape(1, -1)).to(dev)
+        out = torch.empty(1, dtype=torch.float64, device=dev)
+        parts = torch.empty((1, len(self.ifos), 3), dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self.engine.loglike_device(xd.data_ptr(), 1, x.size, pmap, out.data_ptr(), parts.data_ptr(), st)
+        torch.cuda.synchronize(dev)
+        return parts.cpu().numpy()[0], float(out.item())
+
+    def inner_products(self, params):
+        """{ifo: (<d|h> complex, <h|h> float)} for one point (Detector.compute_inner_products)."""
+        parts, _ = self._parts(params)
+        return {ifo: (complex(parts[i, 0], parts[i, 1]), float(parts[i, 2])) for i, ifo in enumerate(self.ifos)}
+
+    def project_fdwave(self, params):
+        """{ifo: projected strain on the in-band axis} for one point (Detector.project_fdwave)."""
+        if self.roq is not None:
+            raise NotImplementedError("projected strain on the full axis is not defined for an ROQ likelihood")
+        sub = _physical_subset(params)
+        pmap, x = _engine.ParamMap.from_dict(sub)
+        h = self.engine.project_waveform(x, pmap)
+        return {ifo: h[i] for i, ifo in enumerate(self.ifos)}
+
+
+def _physical_subset(params):
+    """Keep the slots the device prologue understands, in the ORIGINAL parametrisation: when the caller's
+    dict already carries the derived entries compute_hphc adds (mtot from mchirp, iota from cos_iota,
+    cartesian from spherical spins) the primary ones win, as in waveform.py:334-377."""
+    for k in params:
+        if k.startswith(_engine.ParamMap.UNSUPPORTED_PREFIXES) and k != "weights":
+            raise NotImplementedError("parameter '%s' is outside the fused GPU likelihood; no CPU fallback" % k)
+    sub = {k: v for k, v in params.items() if k in _engine.SLOT_INDEX}
+    if "mchirp" in sub:
+        sub.pop("mtot", None)
+    if "cos_iota" in sub:
+        sub.pop("iota", None)
+    if "s1" in sub and "tilt1" in sub and "phi_1l" in sub:
+        for k in ("s1x", "s1y", "s1z"):
+            sub.pop(k, None)
+    if "s2" in sub and "tilt2" in sub and "phi_2l" in sub:
+        for k in ("s2x", "s2y", "s2z"):
+            sub.pop(k, None)
+    return sub
+
+
+class Posterior(object):
+    """bajes/inf/likelihood.py:35-80 plus batched counterparts with identical semantics row by row."""
+
+    def __init__(self, like, prior):
+        self.like = like
+        self.prior = prior
+
+    # -- reference per-point API --------------------------------------------------------------------
+    def prior_transform(self, u):
+        return self.prior.prior_transform(u)
+
+    def _fill(self, x):
+        return self.prior.this_sample({k: v for k, v in zip(self.prior.names, x)})
+
+    def log_like(self, x):
+        return self.like.log_like(self._fill(x))
+
+    def log_prior(self, x):
+        return self.prior.log_prior(x) if self.prior.in_bounds(x) else -np.inf
+
+    def log_post(self, x):
+        if self.prior.in_bounds(x):
+            return self.prior.log_prior(x) + self.like.log_like(self._fill(x))
+        return -np.inf
+
+    def log_likeprior(self, x):
+        if self.prior.in_bounds(x):
+            return self.like.log_like(self._fill(x)), self.prior.log_prior(x)
+        return 0, -np.inf
+
+    # -- batched API ------------------------------------------------------------------------------------
+    def _batch_inputs(self, X):
+        """Columns = sampled parameters (+ prior 'variables' evaluated on the host), constants separate."""
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        names = list(self.prior.names)
+        v_names = list(getattr(self.prior, "v_names", []) or [])
+        if v_names:
+            extra = np.empty((X.shape[0], len(v_names)))
+            for r in range(X.shape[0]):
+                p = {k: v for k, v in zip(names, X[r])}
+                for j, (f, kw) in enumerate(zip(self.prior.v_funcs, self.prior.v_kwargs)):
+                    extra[r, j] = f(**p, **kw)
+            X = np.concatenate([X, extra], axis=1)
+            names = names + v_names
+        const = {k: v for k, v in getattr(self.prior, "const", {}).items()}
+        return X, names, const
+
+    def log_like_batch(self, X):
+        Xf, names, const = self._batch_inputs(X)
+        return self.like.log_like_batch(Xf, names, const)
+
+    def log_post_batch(self, X):
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        inb = np.array([bool(self.prior.in_bounds(x)) for x in X])
+        out = np.full(X.shape[0], -np.inf)
+        if inb.any():
+            lnp = np.array([self.prior.log_prior(x) for x in X[inb]])
+            out[inb] = lnp + self.log_like_batch(X[inb])
+        return out
+
+    def log_likeprior_batch(self, X):
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        inb = np.array([bool(self.prior.in_bounds(x)) for x in X])
+        lnl = np.zeros(X.shape[0])
+        lnp = np.full(X.shape[0], -np.inf)
+        if inb.any():
+            lnp[inb] = np.array([self.prior.log_prior(x) for x in X[inb]])
+            lnl[inb] = self.log_like_batch(X[inb])
+        return lnl, lnp

@@ -1,0 +1,189 @@
+/*
+ * bajes_b200 -- C ABI of the B200-native batched gravitational-wave likelihood.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch
+ * types.  The reference (matteobreschi/bajes v1.1.0) is pure Python and has no FFI; each
+ * entry point below names the Python call it replaces (paths relative to the reference tree).
+ * The ctypes binding a bajes maintainer would add is shown in INTEGRATION.md and shipped as
+ * bajes_b200/engine.py.
+ *
+ * Conventions
+ *   - every function returns BJ_OK (0) or a negative bj_status; bj_last_error() gives the text
+ *     of the last failure on the calling thread.
+ *   - numerical failure of a parameter point is NOT an error: it yields -inf in the output,
+ *     exactly as GWLikelihood.log_like does (bajes/pipe/log_like.py:121-129).
+ *   - a context owns device copies of all static tables; the caller owns X / out buffers.
+ *   - one context per (process, device); calls on a context are serialised on its stream (or on
+ *     the stream passed to the *_device entry points).  No global mutable state.
+ *   - reductions use a fixed tree: results are bit-identical run to run and for any sharding of
+ *     the walker batch across GPUs.
+ */
+#ifndef BAJES_B200_H
+#define BAJES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BJ_ABI_VERSION 1
+#define BJ_MAX_IFO 3            /* detectors fused in one pass of the kernel            */
+
+typedef enum {
+    BJ_OK = 0,
+    BJ_ERR_INVALID = -1,        /* bad argument                                          */
+    BJ_ERR_CUDA = -2,           /* CUDA runtime failure (text in bj_last_error)          */
+    BJ_ERR_UNSUPPORTED = -3,    /* feature outside the fused path (spcal, weights, ...)  */
+    BJ_ERR_NO_DEVICE = -4       /* no CUDA device / not an sm_100 part                   */
+} bj_status;
+
+/* waveform.py:72-86 + taylorf2.py:435-520 (the five TaylorF2 wrappers) */
+typedef enum {
+    BJ_APPROX_TAYLORF2_35PN = 0,               /* 'TaylorF2_3.5PN'                       */
+    BJ_APPROX_TAYLORF2_55PN = 1,               /* 'TaylorF2_5.5PN'                       */
+    BJ_APPROX_TAYLORF2_55PN_75PNTIDES = 2,     /* 'TaylorF2_5.5PN_7.5PNTides'            */
+    BJ_APPROX_TAYLORF2_55PN_35PNQM_75PNTIDES = 3, /* 'TaylorF2_5.5PN_3.5PNQM_7.5PNTides' */
+    BJ_APPROX_TAYLORF2_55PN_75PNTIDES2020 = 4  /* 'TaylorF2_5.5PN_7.5PNTides2020'        */
+} bj_approx;
+
+/* sin/cos evaluation inside the full-grid kernel (phase is always FP64 and reduced exactly) */
+typedef enum {
+    BJ_SINCOS_MUFU = 0,         /* FP32 MUFU.SIN/COS (fastest)                           */
+    BJ_SINCOS_POLY32 = 1,       /* FP32 minimax polynomials after octant reduction       */
+    BJ_SINCOS_FP64 = 2          /* FP64 sincospi (validation)                            */
+} bj_sincos;
+
+/* canonical parameter slots (names as in bajes/pipe/gw_init.py:328-687, waveform.py:276-330) */
+typedef enum {
+    BJ_P_MCHIRP = 0, BJ_P_MTOT, BJ_P_Q,
+    BJ_P_S1X, BJ_P_S1Y, BJ_P_S1Z, BJ_P_S2X, BJ_P_S2Y, BJ_P_S2Z,
+    BJ_P_S1, BJ_P_TILT1, BJ_P_PHI_1L, BJ_P_S2, BJ_P_TILT2, BJ_P_PHI_2L,
+    BJ_P_LAMBDA1, BJ_P_LAMBDA2,
+    BJ_P_DISTANCE, BJ_P_COS_IOTA, BJ_P_IOTA,
+    BJ_P_RA, BJ_P_DEC, BJ_P_PSI, BJ_P_TIME_SHIFT, BJ_P_PHI_REF, BJ_P_T_GPS,
+    BJ_NUM_PARAMS
+} bj_param;
+
+/* How a batch row x[0..ndim) maps onto the slots: column >= 0 reads x[column]; BJ_COL_CONST
+ * uses value[slot]; BJ_COL_ABSENT marks a slot that is not given at all (e.g. 'mtot' when the
+ * sampler works in 'mchirp', cartesian vs spherical spins, 'iota' vs 'cos_iota').
+ * Replaces Prior.this_sample + the dict parsing of Waveform.compute_hphc
+ * (bajes/inf/prior.py:262-269, bajes/obs/gw/waveform.py:334-377). */
+#define BJ_COL_CONST  (-1)
+#define BJ_COL_ABSENT (-2)
+typedef struct {
+    int32_t column[BJ_NUM_PARAMS];
+    double  value[BJ_NUM_PARAMS];
+} bj_param_map;
+
+/* per-detector constants, taken from the constructed Detector (detector.py:196-205) */
+typedef struct {
+    double response[9];         /* row-major 3x3 response tensor   (detector.py:207-211) */
+    double location[3];         /* metres, Earth-fixed             (detector.py:213-224) */
+    double gmst_reference;      /* rad at reference_time           (detector.py:235-242) */
+    double reference_time;      /* GPS s                                                  */
+    double sday;                /* sidereal day in s                                      */
+} bj_detector;
+
+typedef struct {
+    int32_t abi_version;        /* must be BJ_ABI_VERSION                                 */
+    int32_t device;             /* CUDA device ordinal                                    */
+    int32_t approx;             /* bj_approx                                              */
+    int32_t n_ifo;              /* 1..BJ_MAX_IFO                                          */
+    int32_t marg_phi_ref;       /* log_like.py:175-177                                    */
+    int32_t sincos;             /* bj_sincos                                              */
+    double  seglen;             /* s                                                      */
+    double  dd_sum;             /* sum over detectors of Detector._dd (detector.py:493)   */
+    double  logZ_noise;         /* GWLikelihood.logZ_noise (log_like.py:94)               */
+    bj_detector det[BJ_MAX_IFO];
+} bj_config;
+
+typedef struct bj_ctx bj_ctx;
+
+const char* bj_last_error(void);
+int         bj_abi_version(void);
+/* name, SM count, SM clock (kHz) of `device`; BJ_ERR_NO_DEVICE without a GPU */
+int         bj_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major,
+                           int* cc_minor, int* clock_khz);
+
+/* ------------------------------------------------------------------------------------------
+ * Full-grid likelihood.
+ * bj_create replaces GWLikelihood.__init__ + Detector.store_measurement
+ * (pipe/log_like.py:27-105, obs/gw/detector.py:452-493): it uploads, per in-band bin k and
+ * detector i, freqs[k], data_i[k] (complex, interleaved re/im) and psd_i[k] (already multiplied
+ * by the window factor) and builds the fused device tables.
+ * ------------------------------------------------------------------------------------------ */
+int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
+              const double* const* data_ri, const double* const* psd);
+int bj_destroy(bj_ctx* ctx);
+
+/* Batched GWLikelihood.log_like (pipe/log_like.py:107-183) for W points; x is row-major
+ * [W, ndim] float64 in HOST memory; out_logl[W] in HOST memory.  Includes H2D/D2H copies. */
+int bj_loglike(bj_ctx* ctx, const double* x_host, int64_t n_walkers, int32_t ndim,
+               const bj_param_map* map, double* out_logl_host);
+
+/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL = default).
+ * out_parts (optional, may be NULL) receives per-detector [W][n_ifo][3] = Re<d|h>, Im<d|h>, <h|h>
+ * (Detector.compute_inner_products, detector.py:496-544, summed over bins). */
+int bj_loglike_device(bj_ctx* ctx, const double* x_dev, int64_t n_walkers, int32_t ndim,
+                      const bj_param_map* map, double* out_logl_dev, double* out_parts_dev,
+                      void* stream);
+
+/* Projected frequency-domain waveform of ONE parameter point on every detector
+ * (Waveform.compute_hphc + Detector.project_fdwave, waveform.py:270-395, detector.py:394-418).
+ * out_h_host: [n_ifo][n_bins][2] (re, im), FP64 sin/cos.  Used for injections / SNR helpers. */
+int bj_project_waveform(bj_ctx* ctx, const double* x_host, int32_t ndim, const bj_param_map* map,
+                        double* out_h_host);
+
+/* h_plus / h_cross of ONE point on an arbitrary frequency axis, no detector, no data
+ * (Waveform.compute_hphc; `centre_shift` applies exp(i pi f seglen), waveform.py:390-393).
+ * out_hp/out_hc: [n_freqs][2]. */
+int bj_polarizations(int device, int approx, double seglen, int centre_shift, int64_t n_freqs,
+                     const double* freqs, const double* x_host, int32_t ndim,
+                     const bj_param_map* map, double* out_hp_host, double* out_hc_host);
+
+/* ------------------------------------------------------------------------------------------
+ * ROQ likelihood (Detector.compute_inner_products roq branch, detector.py:534-537).
+ * Static inputs come from the host set-up that mirrors pipe/utils/roq.py:817-872 and
+ * pipe/__init__.py:661-716: joined node axis, index masks, psi weights, and the fitted cubic
+ * B-spline of the omega weights (knots t[n_knots], coefficients c[n_coef][n_lin] complex).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int64_t n_join;  const double* freqs_join;
+    int64_t n_lin;   const int32_t* mask_omega;
+    int64_t n_quad;  const int32_t* mask_psi;
+    int64_t n_knots; int64_t n_coef;
+    const double* const* knots;          /* [n_ifo][n_knots]                              */
+    const double* const* coef_ri;        /* [n_ifo][n_coef][n_lin][2]                     */
+    const double* const* psi_weights;    /* [n_ifo][n_quad]                               */
+    double tc_min, tc_max;               /* validity range of the spline (outside: -inf)  */
+} bj_roq_tables;
+
+int bj_roq_create(bj_ctx** out, const bj_config* cfg, const bj_roq_tables* tab);
+/* bj_loglike / bj_loglike_device / bj_destroy work on ROQ contexts too. */
+
+/* ------------------------------------------------------------------------------------------
+ * Relative-binning likelihood (GWBinningLikelihood.log_like, pipe/utils/binning.py:248-306).
+ * Static inputs: bin-edge frequencies fbin[n_edges], fiducial waveform at the edges per
+ * detector h0[n_ifo][n_edges][2], summary data sdat[4][n_ifo][n_bins][2] (A0,A1,B0,B1).
+ * ------------------------------------------------------------------------------------------ */
+int bj_relbin_create(bj_ctx** out, const bj_config* cfg, int64_t n_edges, const double* fbin,
+                     const double* const* h0_ri, const double* sdat_ri);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): issue-rate micro-benchmarks used as roofline denominators.
+ * which: 0 = FP64 FMA (instr/s), 1 = MUFU sin+cos (instr/s).  Result in *out (thread-instr/s).
+ * ------------------------------------------------------------------------------------------ */
+int bj_measure_peak(int device, int which, double* out);
+
+/* timing of the last bj_loglike* call on this context, measured with CUDA events on the
+ * launching stream: ms[0] = prologue, ms[1] = main kernel, ms[2] = epilogue.  Synchronises. */
+int bj_last_kernel_ms(bj_ctx* ctx, float* ms3);
+/* static description of the last launch: grid, block, dynamic smem, bins per chunk, #chunks */
+int bj_last_launch_info(bj_ctx* ctx, int32_t* info8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAJES_B200_H */

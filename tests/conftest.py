@@ -1,0 +1,65 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "needs_reference: needs the read-only reference tree (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    from oracle import shims
+    have_ref = shims.reference_available()
+    skip_ref = pytest.mark.skip(reason="reference tree not present on this machine")
+    for item in items:
+        if "needs_reference" in item.keywords and not have_ref:
+            item.add_marker(skip_ref)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Make sure the in-tree CUDA library exists (compiles in seconds, no GPU needed)."""
+    import __graft_entry__ as g
+    if g._stale():
+        g.build()
+    yield
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: z[k] for k in z.files}
+
+
+def port_network(cfg, gold, with_golden_data=False):
+    """Re-synthesise the injection with the oracle port classes, pinned to the detector constants stored in
+    the golden file (gmst_reference / sday as produced when the reference ran)."""
+    from bajes_b200 import synthetic as syn
+    from oracle import harness
+    cl = harness.port_classes(gmst_reference=float(gold["gmst_reference"][0]), sday=float(gold["sday"][0]))
+    return syn.build_network(cfg, cl)
+
+
+def product_network_from_port(cfg, net):
+    """Product (GPU) objects carrying EXACTLY the data / detector constants of a port network, so both sides
+    of a parity test see identical inputs."""
+    from bajes_b200 import synthetic as syn
+    cl = syn.product_classes()
+    ifos, datas_p, dets_p, noises_p, f = net
+    datas, dets, noises = {}, {}, {}
+    for ifo in ifos:
+        d = cl.Detector(ifo, syn.T_GPS)
+        d.gmst_reference, d.sday = dets_p[ifo].gmst_reference, dets_p[ifo].sday
+        dets[ifo] = d
+        datas[ifo] = cl.make_series(datas_p[ifo].freq_series, f, cfg)
+        fa, asd = cl.design_asd(ifo)
+        noises[ifo] = cl.Noise(fa, asd, f_min=cfg["f_min"], f_max=cfg["f_max"])
+    return ifos, datas, dets, noises, f

@@ -1,0 +1,223 @@
+"""
+GPU parity tests (run with ``-m gpu`` on a B200).  Every call goes through the C ABI
+(``libbajes_b200.so`` via ctypes).  Checked against
+  * the golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+  * the oracle port evaluated live on the host,
+with the tolerance of BASELINE.json: |dlogL| <= 1e-6 |logL| + 1e-4 per point.
+"""
+import numpy as np
+import pytest
+
+from bajes_b200 import GWLikelihood, Waveform, synthetic as syn
+from oracle import harness
+
+from conftest import load_golden, port_network, product_network_from_port
+
+pytestmark = pytest.mark.gpu
+
+TOL_NOTE = "tolerance 1e-6*|logL| + 1e-4 (BASELINE.json north_star)"
+
+
+def _names(gold):
+    return [str(n) for n in gold["names"]]
+
+
+def _check(got, ref, what, frac=1.0):
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin), "%s: finite pattern differs" % what
+    assert np.all(np.isneginf(got[~fin])), "%s: unphysical rows must be -inf" % what
+    err = np.abs(got[fin] - ref[fin])
+    tol = harness.tolerance(ref[fin])
+    worst = float(np.max(err / tol))
+    print("%s: max |dlogL|/tol = %.3g over %d points (logL in [%.1f, %.1f])"
+          % (what, worst, fin.sum(), ref[fin].min(), ref[fin].max()))
+    assert worst <= frac, "%s: %g x tol; %s" % (what, worst, TOL_NOTE)
+    return worst
+
+
+def _like(cfg, gold, net=None, **kw):
+    net = net if net is not None else port_network(cfg, gold)
+    ifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    approx = kw.pop("approx", cfg["approx"])
+    return GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], approx, **kw)
+
+
+# ------------------------------------------------------------------------------------------------------
+# config 1: TaylorF2 3.5PN BBH, H1+L1, 4 s, 20-1024 Hz
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sincos", ["mufu", "poly32", "fp64"])
+@pytest.mark.parametrize("marg", [False, True])
+def test_c1_vs_reference_golden(sincos, marg):
+    cfg = syn.CONFIGS["C1"]
+    gold = load_golden("c1_bbh.npz")
+    like = _like(cfg, gold, marg_phi_ref=marg, sincos=sincos)
+    got = like.log_like_batch(gold["X"], _names(gold), syn.constants(cfg))
+    _check(got, gold["logl_marg%d" % int(marg)], "C1 %s marg=%s" % (sincos, marg))
+
+
+def test_c1_per_detector_inner_products_and_single_point_api():
+    cfg = syn.CONFIGS["C1"]
+    gold = load_golden("c1_bbh.npz")
+    like = _like(cfg, gold, sincos="fp64")
+    names, const = _names(gold), syn.constants(cfg)
+    batch = like.log_like_batch(gold["X"], names, const)
+    for r in range(gold["parts"].shape[0]):
+        p = {k: float(v) for k, v in zip(names, gold["X"][r])}
+        p.update(const)
+        # dict-in / float-out contract of GWLikelihood.log_like, bit-identical to the batched entry
+        assert like.log_like(dict(p)) == batch[r]
+        ip = like.inner_products(p)
+        for i, ifo in enumerate(cfg["ifos"]):
+            dh, hh = ip[ifo]
+            ref = gold["parts"][r, i]
+            scale = np.hypot(ref[0], ref[1]) + np.sqrt(ref[2])
+            assert abs(dh.real - ref[0]) <= 1e-6 * scale + 1e-5
+            assert abs(dh.imag - ref[1]) <= 1e-6 * scale + 1e-5
+            assert abs(hh - ref[2]) <= 1e-10 * ref[2]        # <h|h> is phase-free, pure FP64
+    # unphysical rows: -inf, never an exception (log_like.py:121-129)
+    bad = {k: float(v) for k, v in zip(names, gold["X"][-1])}
+    bad.update(const)
+    assert like.log_like(bad) == -np.inf
+
+
+def test_c1_projected_waveform_matches_oracle():
+    """Waveform.compute_hphc + Detector.project_fdwave per bin (FP64 on the GPU) vs the oracle port."""
+    cfg = syn.CONFIGS["C1"]
+    gold = load_golden("c1_bbh.npz")
+    net = port_network(cfg, gold)
+    like = _like(cfg, gold, net=net)
+    port = harness.port_likelihood(cfg, net=net)
+    names, const = _names(gold), syn.constants(cfg)
+    for r in (0, 5, 70):
+        p = {k: float(v) for k, v in zip(names, gold["X"][r])}
+        p.update(const)
+        ours = like.project_fdwave(dict(p))
+        wave = port.wave.compute_hphc(dict(p))
+        for ifo in cfg["ifos"]:
+            ref = port.dets[ifo].project_fdwave(wave, p)
+            # phases reach ~1e4 rad: agreement is limited by rounding of the phase, ~1e-11 relative
+            assert np.max(np.abs(ours[ifo] - ref)) <= 1e-9 * np.max(np.abs(ref))
+    # the drop-in Waveform object
+    band = gold["band"]
+    w = Waveform(gold["freqs"][band], cfg["srate"], cfg["seglen"], cfg["approx"])
+    p = syn.injection_params(cfg)
+    hphc = w.compute_hphc(dict(p))
+    ref = port.wave.compute_hphc(dict(p))
+    assert np.max(np.abs(hphc.plus - ref.plus)) <= 1e-9 * np.max(np.abs(ref.plus))
+    assert np.max(np.abs(hphc.cross - ref.cross)) <= 1e-9 * np.max(np.abs(ref.cross))
+
+
+# ------------------------------------------------------------------------------------------------------
+# reduced config 2 (16 s, 3 detectors): every approximant of the TaylorF2 family
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("approx,marg,n", [
+    ("TaylorF2_3.5PN", False, 256), ("TaylorF2_3.5PN", True, 64), ("TaylorF2_5.5PN", False, 64),
+    ("TaylorF2_5.5PN_7.5PNTides", False, 64), ("TaylorF2_5.5PN_3.5PNQM_7.5PNTides", False, 64),
+    ("TaylorF2_5.5PN_7.5PNTides2020", False, 64)])
+def test_c2_small_all_approximants(approx, marg, n):
+    cfg = syn.CONFIGS["C2_small"]
+    gold = load_golden("c2_small.npz")
+    like = _like(cfg, gold, approx=approx, marg_phi_ref=marg)
+    got = like.log_like_batch(gold["X"][:n], _names(gold), syn.constants(cfg))
+    _check(got, gold["logl_%s_marg%d" % (approx, int(marg))][:n], "C2_small %s marg=%s" % (approx, marg))
+
+
+# ------------------------------------------------------------------------------------------------------
+# config 2 at full size: 128 s, 521 729 bins, H1/L1/V1
+# ------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2_full():
+    cfg = syn.CONFIGS["C2"]
+    gold = load_golden("c2.npz")
+    net = port_network(cfg, gold)
+    return cfg, gold, net
+
+
+@pytest.mark.parametrize("sincos", ["mufu", "poly32"])
+def test_c2_full_vs_reference_golden(c2_full, sincos):
+    cfg, gold, net = c2_full
+    like = _like(cfg, gold, net=net, sincos=sincos)
+    got = like.log_like_batch(gold["X"], _names(gold), syn.constants(cfg))
+    _check(got, gold["logl_TaylorF2_3.5PN_marg0"], "C2 full %s" % sincos)
+
+
+def test_c2_full_55pn_tides(c2_full):
+    cfg, gold, net = c2_full
+    like = _like(cfg, gold, net=net, approx="TaylorF2_5.5PN_7.5PNTides")
+    ref = gold["logl_TaylorF2_5.5PN_7.5PNTides_marg0"]
+    got = like.log_like_batch(gold["X"][:len(ref)], _names(gold), syn.constants(cfg))
+    _check(got, ref, "C2 full 5.5PN+7.5PN tides")
+
+
+def test_c2_full_size_properties(c2_full):
+    """Size-independent properties at the full 4096-walker batch (the oracle would need ~15 min here)."""
+    cfg, gold, net = c2_full
+    like = _like(cfg, gold, net=net)
+    names, const = _names(gold), syn.constants(cfg)
+    X, _ = syn.draw_walkers(cfg, 4096, 77, "narrow")
+    full = like.log_like_batch(X, names, const)
+    assert np.all(np.isfinite(full))
+    # (a) determinism: run-to-run identical bits
+    assert np.array_equal(full, like.log_like_batch(X, names, const))
+    # (b) sharding invariance: any split of the walker batch gives the same bits per walker
+    parts = np.concatenate([like.log_like_batch(X[:1000], names, const), like.log_like_batch(X[1000:1003], names, const),
+                            like.log_like_batch(X[1003:], names, const)])
+    assert np.array_equal(full, parts)
+    # (c) distance scaling: <d|h> ~ 1/D, <h|h> ~ 1/D^2  =>  logL(D) = a/D - b/D^2
+    i_d = names.index("distance")
+    X2, X3 = X[:64].copy(), X[:64].copy()
+    X2[:, i_d] *= 2.0
+    X3[:, i_d] *= 4.0
+    l1, l2, l3 = full[:64], like.log_like_batch(X2, names, const), like.log_like_batch(X3, names, const)
+    # l1 = a - b, l2 = a/2 - b/4, l3 = a/4 - b/16  =>  l1 - 6 l2 + 8 l3 = 0
+    resid = l1 - 6.0 * l2 + 8.0 * l3
+    assert np.all(np.abs(resid) <= 3 * harness.tolerance(l1) + 1e-9 * np.abs(l1)), np.max(np.abs(resid))
+    # (d) phi_ref shift by pi flips the sign of <d|h>: logL(phi) + logL(phi + pi) = -<h|h>
+    i_p = names.index("phi_ref")
+    Xp = X[:64].copy()
+    Xp[:, i_p] += np.pi
+    lp = like.log_like_batch(Xp, names, const)
+    for r in range(4):
+        p = {k: float(v) for k, v in zip(names, X[r])}
+        p.update(const)
+        hh = sum(v[1] for v in like.inner_products(p).values())
+        assert abs((l1[r] + lp[r]) + hh) <= 2 * harness.tolerance(l1[r]) + 1e-6 * hh
+
+
+def test_zero_noise_injection_peak():
+    """Noise-free injection: logL at the true parameters equals <h|h>/2."""
+    cfg = dict(syn.CONFIGS["C2_small"])
+    cl = syn.product_classes()
+    ifos, datas, dets, noises, f = syn.build_network(cfg, cl, inject=True, noise=False)
+    like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"], sincos="fp64")
+    p = syn.injection_params(cfg)
+    hh = sum(v[1] for v in like.inner_products(dict(p)).values())
+    assert abs(like.log_like(dict(p)) - 0.5 * hh) <= 1e-6 * hh
+
+
+# ------------------------------------------------------------------------------------------------------
+# ROQ (config 3 at reduced size): linear + quadratic weights in JenpyROQ format
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("marg", [False, True])
+def test_roq_vs_reference_golden(marg):
+    from test_oracle_golden import _roq_port
+    gold = load_golden("roq_small.npz")
+    cfg, net, roq = _roq_port(gold)
+    ifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"],
+                        marg_phi_ref=marg, roq=roq)
+    got = like.log_like_batch(gold["X"], _names(gold), syn.constants(cfg))
+    ref = gold["logl_marg%d" % int(marg)]
+    ref = np.where(np.isfinite(ref), ref, -np.inf)     # reference yields nan/-inf outside the tc grid
+    _check(got, ref, "ROQ marg=%s" % marg)
+
+
+def test_engine_reports_launch_and_timing():
+    cfg = syn.CONFIGS["C1"]
+    gold = load_golden("c1_bbh.npz")
+    like = _like(cfg, gold)
+    like.log_like_batch(gold["X"], _names(gold), syn.constants(cfg))
+    ms = like.engine.last_kernel_ms()
+    info = like.engine.last_launch_info()
+    assert all(m >= 0 for m in ms) and ms[1] > 0
+    assert info[2] == 128 and info[0] * info[4] >= int(gold["band"].sum())

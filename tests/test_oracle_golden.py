@@ -1,0 +1,127 @@
+"""
+CPU tests: the oracle port (oracle/bajes_port.py) against the golden vectors that were produced by the
+UNMODIFIED reference (oracle/make_golden.py).  These run everywhere (no GPU, no reference tree).
+"""
+import numpy as np
+import pytest
+
+from bajes_b200 import synthetic as syn
+from oracle import bajes_port as port
+from oracle import harness
+
+from conftest import load_golden, port_network
+
+
+def _names(gold):
+    return [str(n) for n in gold["names"]]
+
+
+def _assert_close(got, ref, what):
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin), "%s: finite pattern differs" % what
+    assert np.all(np.isneginf(got[~fin])), "%s: unphysical rows must be -inf" % what
+    err = np.abs(got[fin] - ref[fin])
+    tol = harness.tolerance(ref[fin])
+    # the port is a restatement in the same arithmetic: demand 1e-3 of the parity tolerance
+    assert np.all(err <= 1e-3 * tol), "%s: max |d|/tol = %g" % (what, np.max(err / tol))
+
+
+@pytest.mark.parametrize("marg", [False, True])
+def test_c1_all_walkers(marg):
+    cfg = syn.CONFIGS["C1"]
+    gold = load_golden("c1_bbh.npz")
+    net = port_network(cfg, gold)
+    # the re-synthesised data must BE the golden data (same seeds, same recipe)
+    for i, ifo in enumerate(cfg["ifos"]):
+        np.testing.assert_allclose(net[1][ifo].freq_series, gold["data"][i], rtol=1e-12, atol=1e-40)
+    like = harness.port_likelihood(cfg, marg_phi_ref=marg, net=net)
+    got = harness.eval_batch(like, gold["X"], _names(gold), syn.constants(cfg))
+    _assert_close(got, gold["logl_marg%d" % int(marg)], "C1 marg=%s" % marg)
+    if not marg:
+        assert abs(like.log_like(syn.injection_params(cfg)) - float(gold["logl_inj"])) < 1e-8
+        assert abs(like.logZ_noise - float(gold["logZ_noise"])) < 1e-9 * abs(float(gold["logZ_noise"]))
+
+
+def test_c1_inner_products_per_detector():
+    cfg = syn.CONFIGS["C1"]
+    gold = load_golden("c1_bbh.npz")
+    like = harness.port_likelihood(cfg, net=port_network(cfg, gold))
+    names, const = _names(gold), syn.constants(cfg)
+    for r in range(gold["parts"].shape[0]):
+        p = {k: float(v) for k, v in zip(names, gold["X"][r])}
+        p.update(const)
+        ip = like.inner_products(p)
+        for i, ifo in enumerate(cfg["ifos"]):
+            dh, hh = ip[ifo]
+            ref = gold["parts"][r, i]
+            assert abs(dh.real - ref[0]) <= 1e-9 * (abs(ref[0]) + 1.0)
+            assert abs(dh.imag - ref[1]) <= 1e-9 * (abs(ref[1]) + 1.0)
+            assert abs(hh - ref[2]) <= 1e-11 * abs(ref[2])
+
+
+@pytest.mark.parametrize("approx,marg,n", [
+    ("TaylorF2_3.5PN", False, 256), ("TaylorF2_3.5PN", True, 64), ("TaylorF2_5.5PN", False, 64),
+    ("TaylorF2_5.5PN_7.5PNTides", False, 64), ("TaylorF2_5.5PN_3.5PNQM_7.5PNTides", False, 64),
+    ("TaylorF2_5.5PN_7.5PNTides2020", False, 64)])
+def test_c2_small_all_approximants(approx, marg, n):
+    cfg = syn.CONFIGS["C2_small"]
+    gold = load_golden("c2_small.npz")
+    net = port_network(cfg, gold)
+    like = harness.port_likelihood(cfg, approx=approx, marg_phi_ref=marg, net=net)
+    np.testing.assert_allclose([np.real(like.dets[i]._dd) for i in cfg["ifos"]], gold["dd"], rtol=1e-12)
+    key = "logl_%s_marg%d" % (approx, int(marg))
+    ref = gold[key]
+    got = harness.eval_batch(like, gold["X"][:n], _names(gold), syn.constants(cfg))
+    _assert_close(got, ref[:n], "C2_small " + key)
+
+
+def test_c2_full_size_spot_check():
+    """Full 128 s / 521 729-bin configuration: 6 points (the port costs ~0.2 s per point)."""
+    cfg = syn.CONFIGS["C2"]
+    gold = load_golden("c2.npz")
+    net = port_network(cfg, gold)
+    like = harness.port_likelihood(cfg, net=net)
+    assert int(gold["n_band"]) == len(like.dets["H1"].freqs) == 521729
+    np.testing.assert_allclose([np.real(like.dets[i]._dd) for i in cfg["ifos"]], gold["dd"], rtol=1e-12)
+    rows = [0, 1, 127, 128, 200, 255]
+    got = harness.eval_batch(like, gold["X"][rows], _names(gold), syn.constants(cfg))
+    _assert_close(got, gold["logl_TaylorF2_3.5PN_marg0"][rows], "C2 full")
+
+
+def _roq_port(gold):
+    cfg = dict(syn.CONFIGS["C2_small"])
+    cfg.update(seglen=float(gold["seglen"]), seed=int(gold["seed"]))
+    net = port_network(cfg, gold)
+    ifos, datas, dets, noises, f = net
+    basis = harness.make_roq_basis(cfg, n_lin=48, n_quad=24, seed=7)
+    roq = {ifo: {} for ifo in ifos}
+    t_lo, t_hi = gold["t_bounds"]
+    for ifo in ifos:
+        mask = datas[ifo].mask
+        ff = f[mask]
+        psd = noises[ifo].interp_psd_pad(ff)
+        fj, m_psi, m_om, psi, omega = port.roq_setup_one_ifo(
+            basis["lin_f"], basis["quad_f"], basis["lin_b"], basis["quad_b"], ff, datas[ifo].freq_series[mask], psd,
+            cfg["seglen"], t_lo, t_hi, int(gold["time_points"]))
+        roq[ifo]["omega_weights_interp"] = omega
+        roq[ifo]["psi_weights"] = psi
+    roq["freqs_join"], roq["mask_psi"], roq["mask_omega"] = fj, m_psi, m_om
+    return cfg, net, roq
+
+
+@pytest.mark.parametrize("marg", [False, True])
+def test_roq_port_vs_reference_golden(marg):
+    gold = load_golden("roq_small.npz")
+    cfg, net, roq = _roq_port(gold)
+    for i, ifo in enumerate(cfg["ifos"]):
+        np.testing.assert_allclose(roq[ifo]["psi_weights"], gold["psi"][i], rtol=1e-10)
+        np.testing.assert_allclose(roq[ifo]["omega_weights_interp"](cfg["seglen"] / 2 + 1e-3), gold["omega_mid"][i],
+                                   rtol=1e-8, atol=1e-12 * np.max(np.abs(gold["omega_mid"][i])))
+    like = harness.port_likelihood(cfg, marg_phi_ref=marg, roq=roq, net=net)
+    with np.errstate(all="ignore"):
+        got = harness.eval_batch(like, gold["X"], _names(gold), syn.constants(cfg))
+    ref = gold["logl_marg%d" % int(marg)]
+    fin = np.isfinite(ref)
+    err = np.abs(got[fin] - ref[fin])
+    assert np.all(err <= 1e-2 * harness.tolerance(ref[fin])), np.max(err / harness.tolerance(ref[fin]))
+    assert not np.any(np.isfinite(got[~fin]))
