@@ -76,9 +76,12 @@ struct bj_ctx {
     DeviceConfig cfg;
     // full grid
     long n_bins = 0;
+    long n_bins_kernel = 0;       // n_bins padded to even for the mixed-precision kernel
     int rec_doubles = 0;
-    double* d_rec = nullptr;
+    double calib[2] = {0.0, 0.0}; // measured phasor bias (eps_a, eps_p)
+    void* d_rec = nullptr;
     double* d_freqs = nullptr;
+    double* d_gram = nullptr;
     int bins_per_chunk = 0;
     int n_chunks = 0;
     // ROQ / relbin static tables
@@ -132,12 +135,68 @@ static int init_common(bj_ctx* c, const bj_config* cfg) {
     c->cfg.seglen = cfg->seglen;
     c->cfg.dd_sum = cfg->dd_sum;
     c->cfg.logZ_noise = cfg->logZ_noise;
+    c->cfg.dh_fix_re = 1.0;
+    c->cfg.dh_fix_im = 0.0;
     for (int i = 0; i < BJ_MAX_IFO; ++i) c->cfg.det[i] = cfg->det[i];
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&c->ev[i]));
     return BJ_OK;
 }
 
+// per-bin quantities shared by both table layouts
+struct BinStatics {
+    double u, L, w5, f, g, cs, sn;
+};
+static BinStatics bin_statics(double f, double seglen) {
+    BinStatics b;
+    b.f = f;
+    b.u = std::cbrt(f);
+    b.L = std::log(f);
+    b.w5 = 1.0 / (b.u * b.u * b.u * b.u * b.u);
+    b.g = std::pow(f, -7.0 / 6.0);
+    // exp(+i pi f T): exactly +-1 on the FFT grid (waveform.py:392-393)
+    const double kk = f * seglen;
+    const double kr = std::nearbyint(kk);
+    if (std::fabs(kk - kr) < 1e-6) {
+        b.cs = (std::fmod(std::fabs(kr), 2.0) == 1.0) ? -1.0 : 1.0;
+        b.sn = 0.0;
+    } else {
+        b.cs = std::cos(M_PI * kk);
+        b.sn = std::sin(M_PI * kk);
+    }
+    return b;
+}
+// (4/T) conj(d)/S * f^(-7/6) * exp(i pi f T)
+static void data_weight(const BinStatics& b, double four_over_t, double dre, double dim, double psd, double& wr,
+                        double& wi) {
+    const double inv_s = 1.0 / psd;          // psd = inf outside the ASD table -> weight 0
+    const double sc = four_over_t * inv_s * b.g;
+    const double cre = dre, cim = -dim;
+    wr = sc * (cre * b.cs - cim * b.sn);
+    wi = sc * (cre * b.sn + cim * b.cs);
+}
+
+// Gram moments of <h|h>: G_i[m][n] = sum_k phi_m phi_n (4/T) f^(-7/3) / S_i   (detector.py:539), long double sums
+static void build_gram(std::vector<double>& gram, int nifo, long n, const double* freqs, const double* const* psd,
+                       double seglen) {
+    std::vector<long double> acc((size_t)nifo * kGram, 0.0L);
+    const double four_over_t = 4.0 / seglen;
+    for (long k = 0; k < n; ++k) {
+        const BinStatics b = bin_statics(freqs[k], seglen);
+        const double u2 = b.u * b.u, u3 = u2 * b.u, u4 = u2 * u2, u5 = u4 * b.u, u6 = u3 * u3, u7 = u6 * b.u;
+        const long double phi[kBasis] = {1.0L, u2, u3, u4, u5, u6, u7, (long double)b.L * u6};
+        for (int i = 0; i < nifo; ++i) {
+            const long double sw = (long double)four_over_t * (1.0 / psd[i][k]) * b.g * b.g;
+            int idx = 0;
+            for (int m = 0; m < kBasis; ++m)
+                for (int q = m; q < kBasis; ++q, ++idx) acc[(size_t)i * kGram + idx] += phi[m] * phi[q] * sw;
+        }
+    }
+    gram.resize(acc.size());
+    for (size_t i = 0; i < acc.size(); ++i) gram[i] = (double)acc[i];
+}
+
+// all-FP64 records (validation mode)
 template <int NIFO>
 static void build_records(std::vector<double>& rec, long n, const double* freqs, const double* const* data_ri,
                           const double* const* psd, double seglen) {
@@ -145,36 +204,64 @@ static void build_records(std::vector<double>& rec, long n, const double* freqs,
     rec.assign((size_t)n * RS, 0.0);
     const double four_over_t = 4.0 / seglen;
     for (long k = 0; k < n; ++k) {
-        const double f = freqs[k];
+        const BinStatics b = bin_statics(freqs[k], seglen);
         double* r = &rec[(size_t)k * RS];
-        const double u = std::cbrt(f);
-        r[0] = u;
-        r[1] = std::log(f);
-        r[2] = 1.0 / (u * u * u * u * u);
-        r[3] = f;
-        // exp(+i pi f T): exactly +-1 on the FFT grid (waveform.py:392-393)
-        const double kk = f * seglen;
-        const double kr = std::nearbyint(kk);
-        double cs, sn;
-        if (std::fabs(kk - kr) < 1e-6) {
-            cs = (std::fmod(std::fabs(kr), 2.0) == 1.0) ? -1.0 : 1.0;
-            sn = 0.0;
-        } else {
-            cs = std::cos(M_PI * kk);
-            sn = std::sin(M_PI * kk);
-        }
-        const double g = std::pow(f, -7.0 / 6.0);
+        r[0] = b.u; r[1] = b.L; r[2] = b.w5; r[3] = b.f;
+        for (int i = 0; i < NIFO; ++i)
+            data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], r[4 + 2 * i], r[5 + 2 * i]);
+    }
+}
+
+// mixed-precision records: FP64 phase statics, FP32 amplitude statics and data weights scaled by 2^-e
+template <int NIFO>
+static int build_records_mixed(std::vector<unsigned char>& rec, long n, long n_padded, const double* freqs,
+                               const double* const* data_ri, const double* const* psd, double seglen, int* exp_out) {
+    constexpr int RB = RecM<NIFO>::kBytes;
+    rec.assign((size_t)n_padded * RB, 0);
+    const double four_over_t = 4.0 / seglen;
+    double mx = 0.0;
+    for (long k = 0; k < n; ++k) {
+        const BinStatics b = bin_statics(freqs[k], seglen);
         for (int i = 0; i < NIFO; ++i) {
-            const double inv_s = 1.0 / psd[i][k];   // psd = inf outside the ASD table -> weight 0
-            const double dre = data_ri[i][2 * k], dim = data_ri[i][2 * k + 1];
-            // (4/T) conj(d)/S * g * (cs + i sn)
-            const double wr = four_over_t * inv_s * g;
-            const double cre = dre, cim = -dim;
-            r[4 + 2 * i] = wr * (cre * cs - cim * sn);
-            r[5 + 2 * i] = wr * (cre * sn + cim * cs);
-            r[4 + 2 * NIFO + i] = four_over_t * inv_s * g * g;
+            double wr, wi;
+            data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            if (!std::isfinite(wr) || !std::isfinite(wi)) return -1;
+            mx = std::fmax(mx, std::fmax(std::fabs(wr), std::fabs(wi)));
         }
     }
+    int e = 0;
+    if (mx > 0.0) std::frexp(mx, &e);       // mx = m 2^e, m in [0.5, 1)  ->  scaled weights below 1
+    const double sc = std::ldexp(1.0, -e);
+    for (long k = 0; k < n_padded; ++k) {
+        const long ks = k < n ? k : n - 1;   // padding record: statics of the last bin, zero weights
+        const BinStatics b = bin_statics(freqs[ks], seglen);
+        unsigned char* r = &rec[(size_t)k * RB];
+        double hd[4] = {b.u, b.L, b.w5, b.f};
+        memcpy(r, hd, 32);
+        float hf[4] = {(float)b.u, (float)b.L, 0.0f, 0.0f};
+        memcpy(r + 32, hf, 16);
+        for (int i = 0; i < NIFO; ++i) {
+            double wr = 0.0, wi = 0.0;
+            if (k < n) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            const float fr = (float)(wr * sc), fi = (float)(wi * sc);
+            float d4[4] = {fr, fi, fi, -fr};
+            memcpy(r + 48 + 16 * i, d4, 16);
+        }
+    }
+    *exp_out = e;
+    return 0;
+}
+
+template <int SC>
+static int calibrate(double* eps2) {
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 2 * sizeof(double)));
+    cudaMemset(d, 0, 2 * sizeof(double));
+    calibrate_kernel<SC><<<256, 256>>>(d);
+    cudaError_t e = cudaMemcpy(eps2, d, 2 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "phasor calibration failed: %s", cudaGetErrorString(e));
+    return BJ_OK;
 }
 
 extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
@@ -193,26 +280,68 @@ extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, con
     if (rc) { delete c; return rc; }
     c->kind = KIND_FULLGRID;
     c->n_bins = n_bins;
-    std::vector<double> rec;
-    switch (cfg->n_ifo) {
-        case 1: build_records<1>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<1>::kDoubles; break;
-        case 2: build_records<2>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<2>::kDoubles; break;
-        default: build_records<3>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<3>::kDoubles; break;
-    }
-    for (size_t i = 0; i < rec.size(); ++i)
-        if (!std::isfinite(rec[i])) {
+    std::vector<double> gram;
+    build_gram(gram, cfg->n_ifo, n_bins, freqs, psd, cfg->seglen);
+    for (size_t i = 0; i < gram.size(); ++i)
+        if (!std::isfinite(gram[i])) {
             bj_destroy(c);
-            return fail(BJ_ERR_INVALID, "non-finite static table entry at bin %zu (check data / PSD)", i / c->rec_doubles);
+            return fail(BJ_ERR_INVALID, "non-finite <h|h> moment (check the PSD)");
         }
+    const void* rec_ptr = nullptr;
+    size_t rec_bytes = 0;
+    std::vector<double> rec;
+    std::vector<unsigned char> recm;
+    if (cfg->sincos == BJ_SINCOS_FP64) {
+        c->n_bins_kernel = n_bins;
+        switch (cfg->n_ifo) {
+            case 1: build_records<1>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<1>::kDoubles; break;
+            case 2: build_records<2>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<2>::kDoubles; break;
+            default: build_records<3>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<3>::kDoubles; break;
+        }
+        for (size_t i = 0; i < rec.size(); ++i)
+            if (!std::isfinite(rec[i])) {
+                bj_destroy(c);
+                return fail(BJ_ERR_INVALID, "non-finite static table entry at bin %zu (check data / PSD)", i / c->rec_doubles);
+            }
+        rec_ptr = rec.data();
+        rec_bytes = rec.size() * sizeof(double);
+    } else {
+        c->n_bins_kernel = n_bins + (n_bins & 1);      // the mixed kernel consumes bins in pairs
+        int e2 = 0, bad = 0;
+        switch (cfg->n_ifo) {
+            case 1: bad = build_records_mixed<1>(recm, n_bins, c->n_bins_kernel, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<1>::kDoubles; break;
+            case 2: bad = build_records_mixed<2>(recm, n_bins, c->n_bins_kernel, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<2>::kDoubles; break;
+            default: bad = build_records_mixed<3>(recm, n_bins, c->n_bins_kernel, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<3>::kDoubles; break;
+        }
+        if (bad) {
+            bj_destroy(c);
+            return fail(BJ_ERR_INVALID, "non-finite static table entry (check data / PSD)");
+        }
+        double eps[2] = {0.0, 0.0};
+        rc = cfg->sincos == BJ_SINCOS_MUFU ? calibrate<BJ_SINCOS_MUFU>(eps) : calibrate<BJ_SINCOS_POLY32>(eps);
+        if (rc) { bj_destroy(c); return rc; }
+        // computed phasor = true phasor * (1 + eps_a - i eps_p): divide it out, and undo the 2^-e table scale
+        const double ar = 1.0 + eps[0], ai = -eps[1];
+        const double den = ar * ar + ai * ai;
+        const double sc = std::ldexp(1.0, e2);
+        c->cfg.dh_fix_re = sc * ar / den;
+        c->cfg.dh_fix_im = -sc * ai / den;
+        c->calib[0] = eps[0];
+        c->calib[1] = eps[1];
+        rec_ptr = recm.data();
+        rec_bytes = recm.size();
+    }
     // frequency chunking depends on n_bins ONLY, so the reduction tree (and every output bit) is
     // independent of how many walkers a call or a rank evaluates
-    long per = (n_bins + 127) / 128;
+    long per = (c->n_bins_kernel + 127) / 128;
     per = ((per + kTileBins - 1) / kTileBins) * kTileBins;
     if (per < 256) per = 256;
     c->bins_per_chunk = (int)per;
-    c->n_chunks = (int)((n_bins + per - 1) / per);
-    cudaError_t e = cudaMalloc(&c->d_rec, rec.size() * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice);
+    c->n_chunks = (int)((c->n_bins_kernel + per - 1) / per);
+    cudaError_t e = cudaMalloc(&c->d_rec, rec_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, rec_ptr, rec_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_gram, gram.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_gram, gram.data(), gram.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_freqs, (size_t)n_bins * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(c->d_freqs, freqs, (size_t)n_bins * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -228,6 +357,7 @@ extern "C" int bj_destroy(bj_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_rec);
     cudaFree(c->d_freqs);
+    cudaFree(c->d_gram);
     cudaFree(c->d_coef);
     cudaFree(c->d_partial);
     cudaFree(c->d_x);
@@ -254,7 +384,7 @@ static int ensure_workspace(bj_ctx* c, long n_walkers) {
     c->cap_walkers = 0;
     CUDA_TRY(cudaMalloc(&c->d_coef, (size_t)C_NUM * cap * sizeof(double)));
     size_t part = 0;
-    if (c->kind == KIND_FULLGRID) part = (size_t)c->n_chunks * 3 * c->cfg.n_ifo * cap;
+    if (c->kind == KIND_FULLGRID) part = (size_t)c->n_chunks * 2 * c->cfg.n_ifo * cap;
     if (part) CUDA_TRY(cudaMalloc(&c->d_partial, part * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->d_logl, (size_t)cap * sizeof(double)));
     c->cap_walkers = cap;
@@ -284,37 +414,51 @@ static int check_map(const bj_param_map* m, int ndim) {
     return BJ_OK;
 }
 
-template <int NIFO, int MODEL, int SC>
-static int launch_fullgrid_t(bj_ctx* c, long n_walkers, cudaStream_t st) {
-    constexpr int RS = Rec<NIFO>::kDoubles;
-    const size_t smem = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
-    auto kern = fullgrid_kernel<NIFO, MODEL, SC>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
-    kern<<<grid, kThreads, smem, st>>>(c->d_rec, c->n_bins, c->bins_per_chunk, c->d_coef, c->cap_walkers, n_walkers,
-                                       c->d_partial);
-    CUDA_TRY(cudaGetLastError());
+static void note_launch(bj_ctx* c, dim3 grid, size_t smem, int rec8, int model) {
     c->launch_info[0] = (int)grid.x;
     c->launch_info[1] = (int)grid.y;
     c->launch_info[2] = kThreads;
     c->launch_info[3] = (int)smem;
     c->launch_info[4] = c->bins_per_chunk;
     c->launch_info[5] = c->n_chunks;
-    c->launch_info[6] = RS;
-    c->launch_info[7] = MODEL;
+    c->launch_info[6] = rec8;
+    c->launch_info[7] = model;
+}
+
+template <int NIFO, int MODEL>
+static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st) {
+    constexpr int RS = Rec<NIFO>::kDoubles;
+    const size_t smem = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
+    auto kern = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
+    kern<<<grid, kThreads, smem, st>>>((const double*)c->d_rec, c->n_bins_kernel, c->bins_per_chunk, c->d_coef,
+                                       c->cap_walkers, n_walkers, c->d_partial);
+    CUDA_TRY(cudaGetLastError());
+    note_launch(c, grid, smem, RS, MODEL);
+    return BJ_OK;
+}
+
+template <int NIFO, int MODEL, int SC>
+static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st) {
+    constexpr int RB = RecM<NIFO>::kBytes;
+    const size_t smem = (size_t)kStages * kTileBins * RB + kStages * sizeof(uint64_t);
+    auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
+    kern<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->n_bins_kernel, c->bins_per_chunk, c->d_coef,
+                                       c->cap_walkers, n_walkers, c->d_partial);
+    CUDA_TRY(cudaGetLastError());
+    note_launch(c, grid, smem, RB / 8, MODEL);
     return BJ_OK;
 }
 
 template <int NIFO, int MODEL>
 static int launch_fullgrid_m(bj_ctx* c, long n_walkers, cudaStream_t st) {
     switch (c->sincos) {
-        case BJ_SINCOS_MUFU: return launch_fullgrid_t<NIFO, MODEL, BJ_SINCOS_MUFU>(c, n_walkers, st);
-        case BJ_SINCOS_POLY32: return launch_fullgrid_t<NIFO, MODEL, BJ_SINCOS_POLY32>(c, n_walkers, st);
-        default: return launch_fullgrid_t<NIFO, MODEL, BJ_SINCOS_FP64>(c, n_walkers, st);
+        case BJ_SINCOS_MUFU: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_MUFU>(c, n_walkers, st);
+        case BJ_SINCOS_POLY32: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_POLY32>(c, n_walkers, st);
+        default: return launch_fullgrid_fp64<NIFO, MODEL>(c, n_walkers, st);
     }
 }
 
@@ -347,8 +491,8 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
         }
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[2], st));
-        epilogue_kernel<<<nblk, tpb, 0, st>>>(c->cfg, c->d_partial, c->n_chunks, c->d_coef, c->cap_walkers, n_walkers,
-                                              out_logl_dev, out_parts_dev);
+        epilogue_kernel<<<nblk, tpb, 0, st>>>(c->cfg, c->d_partial, c->n_chunks, c->d_gram, c->d_coef, c->cap_walkers,
+                                              n_walkers, out_logl_dev, out_parts_dev);
         CUDA_TRY(cudaGetLastError());
     } else if (c->kind == KIND_ROQ) {
         rc = launch_roq(c->cfg, c->roq, c->d_coef, c->cap_walkers, n_walkers, out_logl_dev, out_parts_dev, st,

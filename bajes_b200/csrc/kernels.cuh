@@ -15,15 +15,19 @@
 namespace bj {
 
 // ----------------------------------------------------------------------------------------------
-// per-bin record layout (doubles):  [u, L, w5, f, (dr_i, di_i) x NIFO, s_i x NIFO, pad]
+// per-bin record layout (doubles):  [u, L, w5, f, (dr_i, di_i) x NIFO]
 //   u = f^(1/3), L = ln f, w5 = f^(-5/3)
 //   dr + i di = (4/T) conj(d_i)/S_i * f^(-7/6) * exp(+i pi f T)      (centre shift folded in)
-//   s         = (4/T)/S_i * f^(-7/3)
+// <h|h> needs no per-bin work at all: |h|^2 = amp^2 |C_i|^2 f^(-7/3) Q^2 and Q is a polynomial in
+// (u, L) with per-walker coefficients, so <h|h>_i = sum_{m<=n} g_m g_n G_i[m][n] with the Gram moments
+// G_i[m][n] = sum_k phi_m phi_n (4/T) f^(-7/3) / S_i tabulated once at set-up (kGram entries per detector).
 // ----------------------------------------------------------------------------------------------
 template <int NIFO> struct Rec {
-    static constexpr int kDoubles = ((4 + 3 * NIFO) + 1) & ~1;   // even => 16-byte aligned records
+    static constexpr int kDoubles = 4 + 2 * NIFO;                 // even => 16-byte aligned records
     static constexpr int kBytes = kDoubles * 8;
 };
+constexpr int kBasis = 8;                         // phi = {1, u^2, u^3, u^4, u^5, u^6, u^7, L u^6}
+constexpr int kGram = kBasis * (kBasis + 1) / 2;  // upper triangle, row-major
 
 constexpr int kThreads = 128;        // walkers per CTA
 constexpr int kTileBins = 64;        // bins per smem stage
@@ -63,37 +67,135 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// ---- sin/cos of a 32-bit binary angle (turns * 2^32, two's complement) ------------------------
+// ---- packed FP32x2 helpers (Blackwell FFMA2 / FMUL2) -----------------------------------------------
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// ---- Q e^{-i theta} from a 32-bit binary angle (turns * 2^32, two's complement) ---------------------
+// Returns cq = Q cos(theta), sq = Q sin(theta) as doubles.
+//   POLY32 : theta = pi z + pi n with z = sext31(b) 2^-31 in [-1/2, 1/2); sin(pi z)/z and cos(pi z) are
+//            degree-5 minimax polynomials in z^2 evaluated TOGETHER with packed FP32x2 FMAs; the (-1)^n
+//            sign and the amplitude Q ride on one packed multiply (scripts/fit_sincospi.py: max abs error
+//            1.9e-7, rms 4e-8, norm bias 2e-8).  No quadrant selects, no predicates.
+//   MUFU   : MUFU.SIN / MUFU.COS (fastest per evaluation but biased: fails the parity tolerance on some configs)
+//   FP64   : sincospi in double (validation)
 template <int SC>
-__device__ __forceinline__ void sincos_turns32(int32_t b, double& s, double& c) {
-    if constexpr (SC == BJ_SINCOS_MUFU) {
-        const float x = __int2float_rn(b) * 1.4629180792671596e-9f;   // 2 pi / 2^32  -> [-pi, pi]
+__device__ __forceinline__ void scaled_phasor(int32_t b, double Q, float Qf, double& cq, double& sq) {
+    if constexpr (SC == BJ_SINCOS_POLY32) {
+        int32_t rem;
+        asm("bfe.s32 %0, %1, 0, 31;" : "=r"(rem) : "r"(b));            // SGXT: nearest-half-turn remainder
+        const uint32_t flip = (uint32_t)(b ^ (b + b)) & 0x80000000u;    // parity of the half turn
+        const float qs = __uint_as_float(__float_as_uint(Qf) ^ flip);
+        const float z = __int2float_rn(rem) * 4.656612873077393e-10f;   // 2^-31
+        const float z2 = z * z;
+        const float zq = z * qs;
+        const unsigned long long zz = pack2(z2, z2);
+        // FP32-aware minimax coefficients (scripts/fit_sincospi.py); lanes = (sin(pi z)/z, cos(pi z))
+        unsigned long long p = pack2(-6.772854831e-03f, -2.412191778e-02f);
+        p = fma2(p, zz, pack2(8.189047128e-02f, 2.347589880e-01f));
+        p = fma2(p, zz, pack2(-5.992177725e-01f, -1.335172534e+00f));
+        p = fma2(p, zz, pack2(2.550160408e+00f, 4.058705807e+00f));
+        p = fma2(p, zz, pack2(-5.167712688e+00f, -4.934802055e+00f));
+        p = fma2(p, zz, pack2(-8.747612412e-08f, 1.000000000e+00f));  // sine: low word of pi ; cosine: 1
+        p = mul2(p, pack2(zq, qs));
+        float sf, cf;
+        unpack2(p, sf, cf);
+        sf = fmaf(zq, 3.141592741e+00f, sf);                            // + high word of pi
+        sq = (double)sf;
+        cq = (double)cf;
+    } else if constexpr (SC == BJ_SINCOS_MUFU) {
+        const float x = __int2float_rn(b) * 1.4629180792671596e-9f;     // 2 pi / 2^32  -> [-pi, pi]
         float sf, cf;
         __sincosf(x, &sf, &cf);
-        s = (double)sf;
-        c = (double)cf;
-    } else if constexpr (SC == BJ_SINCOS_POLY32) {
-        // nearest quarter turn q, remainder in [-pi/4, pi/4]
-        const int32_t q = (b + (1 << 29)) >> 30;
-        const int32_t r = b - (q << 30);
-        const float x = __int2float_rn(r) * 1.4629180792671596e-9f;
-        const float x2 = x * x;
-        float ps = fmaf(-1.9515295891e-4f, x2, 8.3321608736e-3f);
-        ps = fmaf(ps, x2, -1.6666654611e-1f);
-        const float sf = fmaf(x * x2, ps, x);
-        float pc = fmaf(2.443315711809948e-5f, x2, -1.388731625493765e-3f);
-        pc = fmaf(pc, x2, 4.166664568298827e-2f);
-        const float cf = fmaf(x2 * x2, pc, fmaf(-0.5f, x2, 1.0f));
-        const float s0 = (q & 1) ? cf : sf;
-        const float c0 = (q & 1) ? sf : cf;
-        // q mod 4: 0 (c,s)  1 (-s,c)  2 (-c,-s)  3 (s,-c)
-        const bool neg_s = (q & 2) != 0;
-        const bool neg_c = ((q + 1) & 2) != 0;
-        s = (double)(neg_s ? -s0 : s0);
-        c = (double)(neg_c ? -c0 : c0);
+        sq = (double)(sf * Qf);
+        cq = (double)(cf * Qf);
     } else {
-        const double r = (double)b * 2.3283064365386963e-10;   // 2^-32 -> turns in [-0.5, 0.5)
+        const double r = (double)b * 2.3283064365386963e-10;            // 2^-32 -> turns in [-0.5, 0.5)
+        double s, c;
         sincospi(2.0 * r, &s, &c);
+        sq = Q * s;
+        cq = Q * c;
+    }
+}
+
+// Same phasors, returned as FP32 (cq, sq) for the mixed-precision kernel (no FP64 conversion at all).
+template <int SC>
+__device__ __forceinline__ void scaled_phasor_f32(int32_t b, float Qf, float& cq, float& sq) {
+    if constexpr (SC == BJ_SINCOS_POLY32) {
+        int32_t rem;
+        asm("bfe.s32 %0, %1, 0, 31;" : "=r"(rem) : "r"(b));            // SGXT: nearest-half-turn remainder
+        const uint32_t flip = (uint32_t)(b ^ (b + b)) & 0x80000000u;    // parity of the half turn
+        const float qs = __uint_as_float(__float_as_uint(Qf) ^ flip);
+        const float z = __int2float_rn(rem) * 4.656612873077393e-10f;   // 2^-31
+        const float z2 = z * z;
+        const float zq = z * qs;
+        const unsigned long long zz = pack2(z2, z2);
+        // FP32-aware minimax coefficients (scripts/fit_sincospi.py); lanes = (sin(pi z)/z, cos(pi z))
+        unsigned long long p = pack2(-6.772854831e-03f, -2.412191778e-02f);
+        p = fma2(p, zz, pack2(8.189047128e-02f, 2.347589880e-01f));
+        p = fma2(p, zz, pack2(-5.992177725e-01f, -1.335172534e+00f));
+        p = fma2(p, zz, pack2(2.550160408e+00f, 4.058705807e+00f));
+        p = fma2(p, zz, pack2(-5.167712688e+00f, -4.934802055e+00f));
+        p = fma2(p, zz, pack2(-8.747612412e-08f, 1.000000000e+00f));  // sine: low word of pi ; cosine: 1
+        p = mul2(p, pack2(zq, qs));
+        float sf, cf;
+        unpack2(p, sf, cf);
+        sf = fmaf(zq, 3.141592741e+00f, sf);                            // + high word of pi
+        sq = sf;
+        cq = cf;
+    } else {
+        const float x = __int2float_rn(b) * 1.4629180792671596e-9f;
+        float sf, cf;
+        __sincosf(x, &sf, &cf);
+        sq = sf * Qf;
+        cq = cf * Qf;
+    }
+}
+
+// ---- calibration of the FP32 phasor bias -------------------------------------------------------------
+// The hardware / polynomial phasor e^ = c^ - i s^ equals the true one times (1 + eps_a - i eps_p) on average
+// over the circle (MUFU: eps_a = -7.34e-8 in EVERY octant; scripts/sincos_error.cu).  A constant factor on
+// every term is a constant factor on <d|h>: it is measured once here and divided out in the epilogue, which
+// leaves only zero-mean rounding noise.  out[0] += c^ c + s^ s - 1, out[1] += s^ c - c^ s over 2^22 angles.
+template <int SC>
+__global__ void calibrate_kernel(double* out) {
+    double ea = 0.0, ep = 0.0;
+    const int n = 1 << 22;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        // golden-ratio sequence: equidistributed over the circle AND in the low bits (a fixed low-bit pattern
+        // would bias the int->float rounding of the remainder and with it the measured phase)
+        const int32_t b = (int32_t)((uint32_t)i * 2654435769u + 0x7F4A7C15u);
+        float cq, sq;
+        scaled_phasor_f32<SC>(b, 1.0f, cq, sq);
+        double s, c;
+        sincospi(2.0 * ((double)b * 2.3283064365386963e-10), &s, &c);
+        ea += (double)cq * c + (double)sq * s - 1.0;
+        ep += (double)sq * c - (double)cq * s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ea += __shfl_xor_sync(0xffffffffu, ea, o);
+        ep += __shfl_xor_sync(0xffffffffu, ep, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], ea / n);
+        atomicAdd(&out[1], ep / n);
     }
 }
 
@@ -109,47 +211,136 @@ __global__ void prologue_kernel(DeviceConfig cfg, ParamMapDev pm, const double* 
 }
 
 // ---- the fused full-grid kernel -----------------------------------------------------------------
+// One CTA = kThreads walkers (one per thread, coefficients in registers) x one frequency chunk.
+// Per bin and walker: phase (FP64 Horner, + magic constant so that the low word of the double IS the binary
+// angle), amplitude series, and per detector one FP64 FMA for the time-delay ramp, one scaled phasor, and a
+// 4-DFMA complex multiply-accumulate with the static data record.  NB bins are processed in lockstep so the
+// scheduler always has independent DFMA chains to interleave.
+template <int NIFO, int MODEL>
+struct WalkerRegs {
+    static constexpr int NA = (MODEL == MODEL_35) ? 8 : 16;
+    static constexpr int NBQ = (MODEL == MODEL_35) ? 2 : 7;
+    double a[NA], a10, a12, bq[NBQ], c8, k0m, q[6], q6l, tau[NIFO];
+};
+
+template <int NIFO, int MODEL, int SC, int NB>
+__device__ __forceinline__ void process_bins(const double* __restrict__ rec, const WalkerRegs<NIFO, MODEL>& w,
+                                             double (&zr)[NIFO], double (&zi)[NIFO]) {
+    constexpr int RS = Rec<NIFO>::kDoubles;
+    double u[NB], L[NB], w5[NB], f[NB], u2[NB], ph[NB], Q[NB];
+    float Qf[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const double2* r = reinterpret_cast<const double2*>(rec + j * RS);
+        const double2 h0 = r[0], h1 = r[1];
+        u[j] = h0.x; L[j] = h0.y; w5[j] = h1.x; f[j] = h1.y;
+        u2[j] = u[j] * u[j];
+    }
+    // ---- phase in turns (+ magic) ----
+    if constexpr (MODEL == MODEL_35) {
+        double p[NB], bl[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) p[j] = fma(w.a12, u2[j], w.a10);       // tidal pair enters at u^7 * u^3
+#pragma unroll
+        for (int j = 0; j < NB; ++j) p[j] = fma(p[j], u2[j] * u[j], w.a[7]);
+#pragma unroll
+        for (int k = 6; k >= 2; --k) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) p[j] = fma(p[j], u[j], w.a[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            p[j] = fma(p[j], u2[j], w.a[0]);
+            bl[j] = fma(w.bq[1], u[j], w.bq[0]);
+            ph[j] = fma(w5[j], p[j], fma(L[j], bl[j], w.k0m));
+        }
+    } else {
+        double p[NB], bl[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { p[j] = w.a[15]; bl[j] = w.bq[6]; }
+#pragma unroll
+        for (int k = 14; k >= 0; --k) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) p[j] = fma(p[j], u[j], w.a[k]);
+        }
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) bl[j] = fma(bl[j], u[j], w.bq[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            bl[j] = fma(L[j], w.c8 * (u2[j] * u[j]), bl[j]);
+            ph[j] = fma(w5[j], p[j], fma(L[j], bl[j], w.k0m));
+        }
+    }
+    // ---- amplitude series ----
+    {
+        double qq[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) qq[j] = fma(w.q6l, L[j], w.q[4]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) qq[j] = fma(w.q[5], u[j], qq[j]);
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) qq[j] = fma(qq[j], u[j], w.q[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            Q[j] = fma(u2[j], qq[j], 1.0);
+            Qf[j] = (float)Q[j];
+        }
+    }
+    // ---- per detector ----
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const double tt = fma(f[j], w.tau[i], ph[j]);
+            double cq, sq;
+            scaled_phasor<SC>(__double2loint(tt), Q[j], Qf[j], cq, sq);
+            const double2 d = *reinterpret_cast<const double2*>(rec + j * RS + 4 + 2 * i);
+            // (dr + i di) * Q (c - i s)
+            zr[i] = fma(d.x, cq, zr[i]);
+            zr[i] = fma(d.y, sq, zr[i]);
+            zi[i] = fma(d.y, cq, zi[i]);
+            zi[i] = fma(-d.x, sq, zi[i]);
+        }
+    }
+}
+
 template <int NIFO, int MODEL, int SC>
-__global__ void __launch_bounds__(kThreads) fullgrid_kernel(const double* __restrict__ rec, long n_bins,
-                                                              int bins_per_chunk, const double* __restrict__ coef,
-                                                              long stride, long n_walkers,
-                                                              double* __restrict__ partial) {
+__global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __restrict__ rec, long n_bins,
+                                                                 int bins_per_chunk, const double* __restrict__ coef,
+                                                                 long stride, long n_walkers,
+                                                                 double* __restrict__ partial) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileBins * RS * 8);
 
-    const long w = (long)blockIdx.y * kThreads + threadIdx.x;
-    const long wl = w < n_walkers ? w : n_walkers - 1;
+    const long wi = (long)blockIdx.y * kThreads + threadIdx.x;
+    const long wl = wi < n_walkers ? wi : n_walkers - 1;
 
-    // coefficients -> registers
-    constexpr int NA = (MODEL == MODEL_35) ? 8 : 16;
-    double a[NA];
-    double a10 = 0.0, a12 = 0.0;
+    WalkerRegs<NIFO, MODEL> w;
 #pragma unroll
-    for (int j = 0; j < NA; ++j) a[j] = coef[(C_A0 + j) * stride + wl];
-    if constexpr (MODEL == MODEL_35) {
-        a10 = coef[(C_A0 + 10) * stride + wl];
-        a12 = coef[(C_A0 + 12) * stride + wl];
-    }
-    constexpr int NB = (MODEL == MODEL_35) ? 2 : 7;
-    double bq[NB];
+    for (int j = 0; j < WalkerRegs<NIFO, MODEL>::NA; ++j) w.a[j] = coef[(C_A0 + j) * stride + wl];
+    w.a10 = coef[(C_A0 + 10) * stride + wl];
+    w.a12 = coef[(C_A0 + 12) * stride + wl];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) bq[j] = coef[(C_B0 + j) * stride + wl];
-    double c8 = 0.0;
-    if constexpr (MODEL != MODEL_35) c8 = coef[C_C8 * stride + wl];
-    const double k0m = coef[C_K0 * stride + wl] + kMagic;
-    double q[6];
+    for (int j = 0; j < WalkerRegs<NIFO, MODEL>::NBQ; ++j) w.bq[j] = coef[(C_B0 + j) * stride + wl];
+    w.c8 = coef[C_C8 * stride + wl];
+    w.k0m = coef[C_K0 * stride + wl] + kMagic;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) q[j] = coef[(C_Q2 + j) * stride + wl];
-    const double q6l = coef[C_Q6L * stride + wl];
-    double tau[NIFO];
+    for (int j = 0; j < 6; ++j) w.q[j] = coef[(C_Q2 + j) * stride + wl];
+    w.q6l = coef[C_Q6L * stride + wl];
 #pragma unroll
-    for (int i = 0; i < NIFO; ++i) tau[i] = coef[(C_TAU0 + i) * stride + wl];
+    for (int i = 0; i < NIFO; ++i) w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
 
-    double zr[NIFO], zi[NIFO], hh[NIFO];
+    double zr[NIFO], zi[NIFO];
 #pragma unroll
-    for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; hh[i] = 0.0; }
+    for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; }
 
     const long bin0 = (long)blockIdx.x * bins_per_chunk;
     long remaining = n_bins - bin0;
@@ -179,66 +370,256 @@ __global__ void __launch_bounds__(kThreads) fullgrid_kernel(const double* __rest
         mbar_wait(&full[slot], (uint32_t)((t / kStages) & 1));
         const double* tile = stages + (size_t)slot * kTileBins * RS;
         const int nb = min(kTileBins, nb_total - t * kTileBins);
-#pragma unroll 2
-        for (int b = 0; b < nb; ++b) {
-            const double2* r = reinterpret_cast<const double2*>(tile + b * RS);
-            const double2 h0 = r[0];   // u, L
-            const double2 h1 = r[1];   // w5, f
-            const double u = h0.x, L = h0.y, w5 = h1.x, f = h1.y;
-            const double u2 = u * u;
+        int b = 0;
+#pragma unroll 1
+        for (; b + 2 <= nb; b += 2) process_bins<NIFO, MODEL, SC, 2>(tile + b * RS, w, zr, zi);
+        if (b < nb) process_bins<NIFO, MODEL, SC, 1>(tile + b * RS, w, zr, zi);
+        __syncthreads();
+        if (threadIdx.x == 0 && t + kStages < n_tiles) {
+            fence_proxy_async();
+            issue(t + kStages, slot);
+        }
+    }
 
-            // ---- phase in turns (+ magic) ------------------------------------------------------
-            double ph;
-            if constexpr (MODEL == MODEL_35) {
-                const double u3 = u2 * u;
-                double p = fma(a12, u2, a10);          // tidal pair enters at u^7 * u^3
-                p = fma(p, u3, a[7]);
-                p = fma(p, u, a[6]);
-                p = fma(p, u, a[5]);
-                p = fma(p, u, a[4]);
-                p = fma(p, u, a[3]);
-                p = fma(p, u, a[2]);
-                p = fma(p, u2, a[0]);
-                const double bl = fma(bq[1], u, bq[0]);
-                ph = fma(w5, p, fma(L, bl, k0m));
-            } else {
-                double p = a[15];
+    if (wi < n_walkers) {
+        double* out = partial + (size_t)blockIdx.x * (2 * NIFO) * stride + wi;
 #pragma unroll
-                for (int j = 14; j >= 0; --j) p = fma(p, u, a[j]);
-                double bl = bq[6];
-#pragma unroll
-                for (int j = 5; j >= 0; --j) bl = fma(bl, u, bq[j]);
-                const double u3 = u2 * u;
-                bl = fma(L, c8 * u3, bl);
-                ph = fma(w5, p, fma(L, bl, k0m));
-            }
+        for (int i = 0; i < NIFO; ++i) {
+            out[(2 * i + 0) * stride] = zr[i];
+            out[(2 * i + 1) * stride] = zi[i];
+        }
+    }
+}
 
-            // ---- amplitude series ----------------------------------------------------------------
-            double qq = fma(q6l, L, q[4]);
-            qq = fma(q[5], u, qq);
-            qq = fma(qq, u, q[3]);
-            qq = fma(qq, u, q[2]);
-            qq = fma(qq, u, q[1]);
-            qq = fma(qq, u, q[0]);
-            const double Q = fma(u2, qq, 1.0);
-            const double Q2 = Q * Q;
+// ---- the production kernel: FP64 phase, FP32 amplitude / phasor / multiply-accumulate ---------------
+// Cost model measured on B200 (scripts/ubench.cu): what limits this kernel is operand-read bandwidth, not a
+// math pipe -- a DFMA with three distinct register pairs issues every 3 cycles, F2F.F64.F32 runs at XU rate,
+// FP32 and FP64 FMAs do not overlap for free.  Hence: everything that does not NEED 53 bits is FP32:
+//   * phase in turns: FP64 Horner + magic constant (exact binary angle in the low word)      [must be FP64]
+//   * amplitude series Q: FP32 Horner, two bins per packed FFMA2
+//   * phasor: calibrated MUFU or packed polynomial, scaled by Q in FP32
+//   * <d|h> terms: FP32 records (dr, di, di, -dr), two packed FFMA2 per detector into an FP32 block
+//     accumulator that is flushed into the FP64 accumulators every kBlockBins bins (rounding noise of the
+//     short FP32 partial sums is below the phasor noise; analysis in DESIGN.md section 5)
+// Record (bytes): [u, L, w5, f : f64 x4][uf, Lf : f32 x2, pad 8][(dr, di, di, -dr) : f32 x4] x NIFO
+template <int NIFO> struct RecM {
+    static constexpr int kBytes = 48 + 16 * NIFO;
+    static constexpr int kDoubles = kBytes / 8;
+};
+#ifndef BJ_BLOCK_BINS
+#define BJ_BLOCK_BINS 8
+#endif
+constexpr int kBlockBins = BJ_BLOCK_BINS;   // FP32 partial sums are flushed to FP64 every kBlockBins bins
 
-            // ---- per detector ----------------------------------------------------------------------
+template <int NIFO, int MODEL>
+struct WalkerRegsM {
+    static constexpr int NA = (MODEL == MODEL_35) ? 8 : 16;
+    static constexpr int NBQ = (MODEL == MODEL_35) ? 2 : 7;
+    double a[NA], a10, a12, bq[NBQ], c8, k0m, tau[NIFO];
+    float q[6], q6l;
+};
+
+// amplitude series Q(u, L) in FP64 with the exact per-walker coefficients
+__device__ __forceinline__ double amp_series_f64(double u, double L, const double* __restrict__ coef, long stride,
+                                                 long w) {
+    double t = fma(coef[C_Q6L * stride + w], L, coef[(C_Q2 + 4) * stride + w]);
+    t = fma(coef[(C_Q2 + 5) * stride + w], u, t);
+    t = fma(t, u, coef[(C_Q2 + 3) * stride + w]);
+    t = fma(t, u, coef[(C_Q2 + 2) * stride + w]);
+    t = fma(t, u, coef[(C_Q2 + 1) * stride + w]);
+    t = fma(t, u, coef[(C_Q2 + 0) * stride + w]);
+    return fma(u * u, t, 1.0);
+}
+
+template <int NIFO, int MODEL, int SC>
+__device__ __forceinline__ void process_pair_mixed(const unsigned char* __restrict__ rec,
+                                                   const WalkerRegsM<NIFO, MODEL>& w,
+                                                   unsigned long long (&acc)[NIFO]) {
+    constexpr int RB = RecM<NIFO>::kBytes;
+    double u[2], L[2], w5[2], f[2], u2[2], ph[2];
+    float uf[2], Lf[2];
 #pragma unroll
-            for (int i = 0; i < NIFO; ++i) {
-                const double tt = fma(f, tau[i], ph);
-                double s, c;
-                sincos_turns32<SC>(__double2loint(tt), s, c);
-                const double dr = tile[b * RS + 4 + 2 * i];
-                const double di = tile[b * RS + 5 + 2 * i];
-                const double sw = tile[b * RS + 4 + 2 * NIFO + i];
-                // (dr + i di) * (c - i s)
-                const double pr = fma(dr, c, di * s);
-                const double pi_ = fma(di, c, -(dr * s));
-                zr[i] = fma(Q, pr, zr[i]);
-                zi[i] = fma(Q, pi_, zi[i]);
-                hh[i] = fma(Q2, sw, hh[i]);
-            }
+    for (int j = 0; j < 2; ++j) {
+        const double2* r = reinterpret_cast<const double2*>(rec + j * RB);
+        const double2 h0 = r[0], h1 = r[1];
+        const float2 h2 = *reinterpret_cast<const float2*>(rec + j * RB + 32);
+        u[j] = h0.x; L[j] = h0.y; w5[j] = h1.x; f[j] = h1.y;
+        uf[j] = h2.x; Lf[j] = h2.y;
+        u2[j] = u[j] * u[j];
+    }
+    // ---- phase in turns (+ magic), FP64 ----
+    if constexpr (MODEL == MODEL_35) {
+        double p[2], bl[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) p[j] = fma(w.a12, u2[j], w.a10);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) p[j] = fma(p[j], u2[j] * u[j], w.a[7]);
+#pragma unroll
+        for (int k = 6; k >= 2; --k) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) p[j] = fma(p[j], u[j], w.a[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            p[j] = fma(p[j], u2[j], w.a[0]);
+            bl[j] = fma(w.bq[1], u[j], w.bq[0]);
+            ph[j] = fma(w5[j], p[j], fma(L[j], bl[j], w.k0m));
+        }
+    } else {
+        double p[2], bl[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { p[j] = w.a[15]; bl[j] = w.bq[6]; }
+#pragma unroll
+        for (int k = 14; k >= 0; --k) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) p[j] = fma(p[j], u[j], w.a[k]);
+        }
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bl[j] = fma(bl[j], u[j], w.bq[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            bl[j] = fma(L[j], w.c8 * (u2[j] * u[j]), bl[j]);
+            ph[j] = fma(w5[j], p[j], fma(L[j], bl[j], w.k0m));
+        }
+    }
+    // ---- amplitude series, FP32, both bins in one packed Horner ----
+    float Qf[2];
+    {
+        const unsigned long long up = pack2(uf[0], uf[1]);
+        const unsigned long long lp = pack2(Lf[0], Lf[1]);
+        unsigned long long t = fma2(pack2(w.q6l, w.q6l), lp, pack2(w.q[4], w.q[4]));
+        t = fma2(pack2(w.q[5], w.q[5]), up, t);
+        t = fma2(t, up, pack2(w.q[3], w.q[3]));
+        t = fma2(t, up, pack2(w.q[2], w.q[2]));
+        t = fma2(t, up, pack2(w.q[1], w.q[1]));
+        t = fma2(t, up, pack2(w.q[0], w.q[0]));
+        t = fma2(mul2(up, up), t, pack2(1.0f, 1.0f));
+        unpack2(t, Qf[0], Qf[1]);
+    }
+    // ---- per detector: ramp, phasor, packed complex MAC ----
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double tt = fma(f[j], w.tau[i], ph[j]);
+            float cq, sq;
+            scaled_phasor_f32<SC>(__double2loint(tt), Qf[j], cq, sq);
+            const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(rec + j * RB + 48 + 16 * i);
+            // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
+            acc[i] = fma2(d.x, pack2(cq, cq), acc[i]);
+            acc[i] = fma2(d.y, pack2(sq, sq), acc[i]);
+        }
+    }
+}
+
+template <int NIFO, int MODEL, int SC>
+__global__ void __launch_bounds__(kThreads, 4) fullgrid_mixed_kernel(const unsigned char* __restrict__ rec,
+                                                                       long n_bins, int bins_per_chunk,
+                                                                       const double* __restrict__ coef, long stride,
+                                                                       long n_walkers, double* __restrict__ partial) {
+    constexpr int RB = RecM<NIFO>::kBytes;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* stages = smem_raw;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileBins * RB);
+
+    const long wi = (long)blockIdx.y * kThreads + threadIdx.x;
+    const long wl = wi < n_walkers ? wi : n_walkers - 1;
+
+    WalkerRegsM<NIFO, MODEL> w;
+#pragma unroll
+    for (int j = 0; j < WalkerRegsM<NIFO, MODEL>::NA; ++j) w.a[j] = coef[(C_A0 + j) * stride + wl];
+    w.a10 = coef[(C_A0 + 10) * stride + wl];
+    w.a12 = coef[(C_A0 + 12) * stride + wl];
+#pragma unroll
+    for (int j = 0; j < WalkerRegsM<NIFO, MODEL>::NBQ; ++j) w.bq[j] = coef[(C_B0 + j) * stride + wl];
+    w.c8 = coef[C_C8 * stride + wl];
+    w.k0m = coef[C_K0 * stride + wl] + kMagic;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) w.q[j] = (float)coef[(C_Q2 + j) * stride + wl];
+    w.q6l = (float)coef[C_Q6L * stride + wl];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
+
+    double zr[NIFO], zi[NIFO];
+    unsigned long long acc[NIFO];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; acc[i] = 0ull; }
+
+    // n_bins is even by construction (the table is padded with one zero-weight record if needed)
+    const long bin0 = (long)blockIdx.x * bins_per_chunk;
+    long remaining = n_bins - bin0;
+    const int nb_total = remaining < bins_per_chunk ? (int)remaining : bins_per_chunk;
+    const int n_tiles = (nb_total + kTileBins - 1) / kTileBins;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int slot) {
+        const int nb = min(kTileBins, nb_total - tile * kTileBins);
+        const uint32_t bytes = (uint32_t)nb * RB;
+        mbar_expect_tx(&full[slot], bytes);
+        tma_bulk_g2s(stages + (size_t)slot * kTileBins * RB, rec + (bin0 + (long)tile * kTileBins) * RB, bytes,
+                     &full[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages && s < n_tiles; ++s) issue(s, s);
+    }
+
+    // The FP32 amplitude series carries a SYSTEMATIC relative error of a few 1e-8 (its per-walker coefficients
+    // are rounded once, for all bins), and a systematic factor on every term is a factor on <d|h> ~ 1e4.  It
+    // varies smoothly with frequency, so once per tile the exact FP64 series is evaluated at the tile's first bin
+    // and the ratio rides on the flush of the FP32 block sums (the flush add becomes an FMA: free).
+    double corr = 1.0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            float re, im;
+            unpack2(acc[i], re, im);
+            zr[i] = fma((double)re, corr, zr[i]);
+            zi[i] = fma((double)im, corr, zi[i]);
+            acc[i] = 0ull;
+        }
+    };
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int slot = t % kStages;
+        mbar_wait(&full[slot], (uint32_t)((t / kStages) & 1));
+        const unsigned char* tile = stages + (size_t)slot * kTileBins * RB;
+        const int nb = min(kTileBins, nb_total - t * kTileBins);
+        {
+            // exact series vs the series with float-rounded coefficients, BOTH in FP64 arithmetic at the tile's
+            // first bin: the ratio is the smooth systematic factor (no rounding noise enters)
+            const double2 h0 = *reinterpret_cast<const double2*>(tile);
+            const double q_exact = amp_series_f64(h0.x, h0.y, coef, stride, wl);
+            double t = fma((double)w.q6l, h0.y, (double)w.q[4]);
+            t = fma((double)w.q[5], h0.x, t);
+            t = fma(t, h0.x, (double)w.q[3]);
+            t = fma(t, h0.x, (double)w.q[2]);
+            t = fma(t, h0.x, (double)w.q[1]);
+            t = fma(t, h0.x, (double)w.q[0]);
+            const double q_rounded = fma(h0.x * h0.x, t, 1.0);
+            corr = q_exact / q_rounded;
+        }
+        const int n_blocks = nb / kBlockBins;
+#pragma unroll 1
+        for (int blk = 0; blk < n_blocks; ++blk) {
+            const unsigned char* base = tile + (size_t)blk * kBlockBins * RB;
+#pragma unroll 1
+            for (int b = 0; b < kBlockBins; b += 2) process_pair_mixed<NIFO, MODEL, SC>(base + b * RB, w, acc);
+            flush();
+        }
+        {
+            const int done = n_blocks * kBlockBins;
+#pragma unroll 1
+            for (int b = done; b + 2 <= nb; b += 2) process_pair_mixed<NIFO, MODEL, SC>(tile + (size_t)b * RB, w, acc);
+            if (done < nb) flush();
         }
         __syncthreads();
         if (threadIdx.x == 0 && t + kStages < n_tiles) {
@@ -247,13 +628,12 @@ __global__ void __launch_bounds__(kThreads) fullgrid_kernel(const double* __rest
         }
     }
 
-    if (w < n_walkers) {
-        double* out = partial + (size_t)blockIdx.x * (3 * NIFO) * stride + w;
+    if (wi < n_walkers) {
+        double* out = partial + (size_t)blockIdx.x * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
-            out[(3 * i + 0) * stride] = zr[i];
-            out[(3 * i + 1) * stride] = zi[i];
-            out[(3 * i + 2) * stride] = hh[i];
+            out[(2 * i + 0) * stride] = zr[i];
+            out[(2 * i + 1) * stride] = zi[i];
         }
     }
 }
@@ -273,29 +653,45 @@ __device__ inline double log_bessel_i0(double x) {
     return x + log(sum) - 0.5 * log(kTwoPi * x);
 }
 
-// ---- epilogue: fixed-order reduction over chunks + logL ---------------------------------------------
+// ---- epilogue: fixed-order reduction over chunks, <h|h> from the Gram moments, logL -------------------
 // sums[W][n_ifo][3] (optional) receives Re<d|h>, Im<d|h>, <h|h> per detector.
 __global__ void epilogue_kernel(DeviceConfig cfg, const double* __restrict__ partial, int n_chunks,
-                                const double* __restrict__ coef, long stride, long n_walkers,
-                                double* __restrict__ logl, double* __restrict__ sums) {
+                                const double* __restrict__ gram, const double* __restrict__ coef, long stride,
+                                long n_walkers, double* __restrict__ logl, double* __restrict__ sums) {
     const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_walkers) return;
     const int nifo = cfg.n_ifo;
     const double amp = coef[C_AMP * stride + w];
     const bool valid = coef[C_VALID * stride + w] != 0.0;
+    // amplitude-series coefficients in the basis phi = {1, u^2, ..., u^7, L u^6}
+    double g[kBasis];
+    g[0] = 1.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) g[1 + j] = coef[(C_Q2 + j) * stride + w];
+    g[7] = coef[C_Q6L * stride + w];
     double dh_re = 0.0, dh_im = 0.0, hh_tot = 0.0;
     for (int i = 0; i < nifo; ++i) {
-        double zr = 0.0, zi = 0.0, h = 0.0;
+        double zr = 0.0, zi = 0.0;
         for (int ch = 0; ch < n_chunks; ++ch) {
-            const double* p = partial + ((size_t)ch * (3 * nifo) + 3 * i) * stride + w;
+            const double* p = partial + ((size_t)ch * (2 * nifo) + 2 * i) * stride + w;
             zr += p[0];
             zi += p[stride];
-            h += p[2 * stride];
+        }
+        double h = 0.0;
+        const double* G = gram + i * kGram;
+        int idx = 0;
+        for (int m = 0; m < kBasis; ++m) {
+            double row = 0.0;
+            for (int n = m; n < kBasis; ++n, ++idx) row = fma((n == m ? 1.0 : 2.0) * g[n], G[idx], row);
+            h = fma(g[m], row, h);
         }
         const double cr = coef[(C_CR0 + i) * stride + w];
         const double ci = coef[(C_CI0 + i) * stride + w];
-        const double re = amp * (cr * zr - ci * zi);
-        const double im = amp * (cr * zi + ci * zr);
+        // undo the (power-of-two) table scale and the calibrated phasor bias: z -> z * (kr + i ki)
+        const double xr = zr * cfg.dh_fix_re - zi * cfg.dh_fix_im;
+        const double xi = zr * cfg.dh_fix_im + zi * cfg.dh_fix_re;
+        const double re = amp * (cr * xr - ci * xi);
+        const double im = amp * (cr * xi + ci * xr);
         const double hi = amp * amp * (cr * cr + ci * ci) * h;
         if (sums) {
             sums[(w * nifo + i) * 3 + 0] = re;

@@ -51,6 +51,7 @@ struct DeviceConfig {
     double seglen;
     double dd_sum;
     double logZ_noise;
+    double dh_fix_re, dh_fix_im;   // <d|h> correction: table scale / calibrated phasor bias (1 + 0i in fp64 mode)
     bj_detector det[BJ_MAX_IFO];
 };
 

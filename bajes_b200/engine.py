@@ -40,7 +40,7 @@ APPROX_IDS = {
 SINCOS_MODES = {"mufu": 0, "poly32": 1, "fp64": 2}
 
 LIB_NAME = "libbajes_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
+LIB_PATH = os.environ.get("BAJES_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", LIB_NAME)
 
 
 class EngineUnavailable(RuntimeError):
