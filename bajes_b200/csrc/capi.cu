@@ -491,8 +491,9 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
         }
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[2], st));
-        epilogue_kernel<<<nblk, tpb, 0, st>>>(c->cfg, c->d_partial, c->n_chunks, c->d_gram, c->d_coef, c->cap_walkers,
-                                              n_walkers, out_logl_dev, out_parts_dev);
+        epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers), kEpiWalkers * kEpiSlices, 0, st>>>(
+            c->cfg, c->d_partial, c->n_chunks, c->d_gram, c->d_coef, c->cap_walkers, n_walkers, out_logl_dev,
+            out_parts_dev);
         CUDA_TRY(cudaGetLastError());
     } else if (c->kind == KIND_ROQ) {
         rc = launch_roq(c->cfg, c->roq, c->d_coef, c->cap_walkers, n_walkers, out_logl_dev, out_parts_dev, st,

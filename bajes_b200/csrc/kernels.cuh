@@ -655,11 +655,25 @@ __device__ inline double log_bessel_i0(double x) {
 
 // ---- epilogue: fixed-order reduction over chunks, <h|h> from the Gram moments, logL -------------------
 // sums[W][n_ifo][3] (optional) receives Re<d|h>, Im<d|h>, <h|h> per detector.
-__global__ void epilogue_kernel(DeviceConfig cfg, const double* __restrict__ partial, int n_chunks,
-                                const double* __restrict__ gram, const double* __restrict__ coef, long stride,
-                                long n_walkers, double* __restrict__ logl, double* __restrict__ sums) {
-    const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_walkers) return;
+constexpr int kEpiWalkers = 32;   // walkers per epilogue CTA
+constexpr int kEpiSlices = 8;     // chunk slices summed in parallel, then combined in fixed order
+__global__ void __launch_bounds__(kEpiWalkers * kEpiSlices)
+epilogue_kernel(DeviceConfig cfg, const double* __restrict__ partial, int n_chunks,
+                const double* __restrict__ gram, const double* __restrict__ coef, long stride,
+                long n_walkers, double* __restrict__ logl, double* __restrict__ sums) {
+    __shared__ double red[kEpiSlices][2 * BJ_MAX_IFO][kEpiWalkers];
+    const int lane_w = threadIdx.x % kEpiWalkers, slice = threadIdx.x / kEpiWalkers;
+    const long w = (long)blockIdx.x * kEpiWalkers + lane_w;
+    const long wc = w < n_walkers ? w : n_walkers - 1;
+    // stage 1: slice s adds chunks s, s + kEpiSlices, ... in ascending order (fixed tree: bits do not depend on W)
+    for (int j = 0; j < 2 * cfg.n_ifo; ++j) {
+        double acc = 0.0;
+        for (int ch = slice; ch < n_chunks; ch += kEpiSlices)
+            acc += partial[((size_t)ch * (2 * cfg.n_ifo) + j) * stride + wc];
+        red[slice][j][lane_w] = acc;
+    }
+    __syncthreads();
+    if (slice != 0 || w >= n_walkers) return;
     const int nifo = cfg.n_ifo;
     const double amp = coef[C_AMP * stride + w];
     const bool valid = coef[C_VALID * stride + w] != 0.0;
@@ -672,10 +686,10 @@ __global__ void epilogue_kernel(DeviceConfig cfg, const double* __restrict__ par
     double dh_re = 0.0, dh_im = 0.0, hh_tot = 0.0;
     for (int i = 0; i < nifo; ++i) {
         double zr = 0.0, zi = 0.0;
-        for (int ch = 0; ch < n_chunks; ++ch) {
-            const double* p = partial + ((size_t)ch * (2 * nifo) + 2 * i) * stride + w;
-            zr += p[0];
-            zi += p[stride];
+#pragma unroll
+        for (int sl = 0; sl < kEpiSlices; ++sl) {
+            zr += red[sl][2 * i][lane_w];
+            zi += red[sl][2 * i + 1][lane_w];
         }
         double h = 0.0;
         const double* G = gram + i * kGram;

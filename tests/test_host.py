@@ -208,3 +208,22 @@ def test_walker_draws_are_seeded_and_shaped():
     assert np.array_equal(a, b) and a.shape == (100, 13) and names == syn.WALKER_NAMES
     w, _ = syn.draw_walkers(cfg, 100, 5, "wide")
     assert np.all(w[:, names.index("q")] >= 1.0)
+
+
+# ---- relative-binning set-up (host NumPy) vs the oracle port ----------------------------------------------
+def test_relbin_setup_matches_port():
+    from bajes_b200.binning import compute_sdat, setup_bins
+    cfg = syn.CONFIGS["C4_small"]
+    f = syn.frequency_axis(cfg)
+    fb = f[(f >= cfg["f_min"]) & (f <= cfg["f_max"])]
+    n1, fbin1, ind1 = setup_bins(fb, cfg["f_min"], cfg["f_max"])
+    n2, fbin2, ind2 = port.relbin_setup_bins(fb, cfg["f_min"], cfg["f_max"])
+    assert n1 == n2 and np.array_equal(ind1, ind2) and np.array_equal(fbin1, fbin2)
+    assert 40 <= n1 <= 80                       # the reference defaults chi=1, eps=0.5 give ~60 bins
+    rng = np.random.default_rng(1)
+    psds = [np.abs(rng.normal(size=len(fb))) + 1.0 for _ in range(2)]
+    datas = [rng.normal(size=len(fb)) + 1j * rng.normal(size=len(fb)) for _ in range(2)]
+    h0s = [rng.normal(size=len(fb)) + 1j * rng.normal(size=len(fb)) for _ in range(2)]
+    a = compute_sdat(fb, fbin1, ind1, psds, datas, h0s)
+    b = port.relbin_summary_data(fb, fbin2, ind2, psds, datas, h0s)
+    np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12 * np.max(np.abs(b)))
