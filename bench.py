@@ -197,7 +197,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload(cfg, args, n),
+            "config": workload(cfg, args, args.walkers or cfg["n_walkers"]),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d walkers x %d bins x %d detectors per step, oracle/bajes_port.py over a "
                                        "%d-process pool" % (n, nb, len(cfg["ifos"]), cores)},

@@ -53,6 +53,8 @@ def port_classes(gmst_reference=None, sday=None):
 
 
 def reference_likelihood(cfg, approx=None, marg_phi_ref=False, roq=None, net=None):
+    from oracle import shims
+    shims.import_reference()
     from bajes.pipe.log_like import GWLikelihood
     cl = reference_classes()
     ifos, datas, dets, noises, f = net if net is not None else syn.build_network(cfg, cl)
