@@ -238,7 +238,13 @@ static int build_records_mixed(std::vector<unsigned char>& rec, long n, long n_p
         unsigned char* r = &rec[(size_t)k * RB];
         double hd[4] = {b.u, b.L, b.w5, b.f};
         memcpy(r, hd, 32);
-        float hf[4] = {(float)b.u, (float)b.L, 0.0f, 0.0f};
+        // pair slot: even record (uf_even, uf_odd), odd record (Lf_even, Lf_odd)
+        const long ke = k & ~1L, ko = ke + 1;
+        const BinStatics be = bin_statics(freqs[ke < n ? ke : n - 1], seglen);
+        const BinStatics bo = bin_statics(freqs[ko < n ? ko : n - 1], seglen);
+        float hf[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if ((k & 1) == 0) { hf[0] = (float)be.u; hf[1] = (float)bo.u; }
+        else              { hf[0] = (float)be.L; hf[1] = (float)bo.L; }
         memcpy(r + 32, hf, 16);
         for (int i = 0; i < NIFO; ++i) {
             double wr = 0.0, wi = 0.0;

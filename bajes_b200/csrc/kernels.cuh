@@ -401,14 +401,23 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
 //   * <d|h> terms: FP32 records (dr, di, di, -dr), two packed FFMA2 per detector into an FP32 block
 //     accumulator that is flushed into the FP64 accumulators every kBlockBins bins (rounding noise of the
 //     short FP32 partial sums is below the phasor noise; analysis in DESIGN.md section 5)
-// Record (bytes): [u, L, w5, f : f64 x4][uf, Lf : f32 x2, pad 8][(dr, di, di, -dr) : f32 x4] x NIFO
+// Record (bytes): [u, L, w5, f : f64 x4][pair slot : f32 x2, pad 8][(dr, di, di, -dr) : f32 x4] x NIFO
+// Bins are consumed in (even, odd) pairs; the pair slot of the even record holds (uf_even, uf_odd) and that of
+// the odd record (Lf_even, Lf_odd), so each LDS.64 delivers a ready-packed FFMA2 operand.
 template <int NIFO> struct RecM {
     static constexpr int kBytes = 48 + 16 * NIFO;
     static constexpr int kDoubles = kBytes / 8;
 };
+#ifndef BJ_PAIR_UNROLL
+#define BJ_PAIR_UNROLL 4
+#endif
+#ifndef BJ_MIN_CTAS
+#define BJ_MIN_CTAS 3
+#endif
 #ifndef BJ_BLOCK_BINS
 #define BJ_BLOCK_BINS 8
 #endif
+constexpr int kPairUnroll = BJ_PAIR_UNROLL;
 constexpr int kBlockBins = BJ_BLOCK_BINS;   // FP32 partial sums are flushed to FP64 every kBlockBins bins
 
 template <int NIFO, int MODEL>
@@ -437,16 +446,15 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
                                                    unsigned long long (&acc)[NIFO]) {
     constexpr int RB = RecM<NIFO>::kBytes;
     double u[2], L[2], w5[2], f[2], u2[2], ph[2];
-    float uf[2], Lf[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const double2* r = reinterpret_cast<const double2*>(rec + j * RB);
         const double2 h0 = r[0], h1 = r[1];
-        const float2 h2 = *reinterpret_cast<const float2*>(rec + j * RB + 32);
         u[j] = h0.x; L[j] = h0.y; w5[j] = h1.x; f[j] = h1.y;
-        uf[j] = h2.x; Lf[j] = h2.y;
         u2[j] = u[j] * u[j];
     }
+    const unsigned long long up = *reinterpret_cast<const unsigned long long*>(rec + 32);        // (uf0, uf1)
+    const unsigned long long lp = *reinterpret_cast<const unsigned long long*>(rec + RB + 32);   // (Lf0, Lf1)
     // ---- phase in turns (+ magic), FP64 ----
     if constexpr (MODEL == MODEL_35) {
         double p[2], bl[2];
@@ -488,8 +496,6 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
     // ---- amplitude series, FP32, both bins in one packed Horner ----
     float Qf[2];
     {
-        const unsigned long long up = pack2(uf[0], uf[1]);
-        const unsigned long long lp = pack2(Lf[0], Lf[1]);
         unsigned long long t = fma2(pack2(w.q6l, w.q6l), lp, pack2(w.q[4], w.q[4]));
         t = fma2(pack2(w.q[5], w.q[5]), up, t);
         t = fma2(t, up, pack2(w.q[3], w.q[3]));
@@ -516,7 +522,7 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
 }
 
 template <int NIFO, int MODEL, int SC>
-__global__ void __launch_bounds__(kThreads, 4) fullgrid_mixed_kernel(const unsigned char* __restrict__ rec,
+__global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(const unsigned char* __restrict__ rec,
                                                                        long n_bins, int bins_per_chunk,
                                                                        const double* __restrict__ coef, long stride,
                                                                        long n_walkers, double* __restrict__ partial) {
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_mixed_kernel(const unsig
 #pragma unroll 1
         for (int blk = 0; blk < n_blocks; ++blk) {
             const unsigned char* base = tile + (size_t)blk * kBlockBins * RB;
-#pragma unroll 1
+#pragma unroll kPairUnroll
             for (int b = 0; b < kBlockBins; b += 2) process_pair_mixed<NIFO, MODEL, SC>(base + b * RB, w, acc);
             flush();
         }
