@@ -137,6 +137,8 @@ static int init_common(bj_ctx* c, const bj_config* cfg) {
     c->cfg.logZ_noise = cfg->logZ_noise;
     c->cfg.dh_fix_re = 1.0;
     c->cfg.dh_fix_im = 0.0;
+    c->cfg.f_lo = 0.0;
+    c->cfg.f_hi = 0.0;
     for (int i = 0; i < BJ_MAX_IFO; ++i) c->cfg.det[i] = cfg->det[i];
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&c->ev[i]));
@@ -286,6 +288,12 @@ extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, con
     if (rc) { delete c; return rc; }
     c->kind = KIND_FULLGRID;
     c->n_bins = n_bins;
+    c->cfg.f_lo = freqs[0];
+    c->cfg.f_hi = freqs[0];
+    for (int64_t k = 0; k < n_bins; ++k) {
+        c->cfg.f_lo = std::fmin(c->cfg.f_lo, freqs[k]);
+        c->cfg.f_hi = std::fmax(c->cfg.f_hi, freqs[k]);
+    }
     std::vector<double> gram;
     build_gram(gram, cfg->n_ifo, n_bins, freqs, psd, cfg->seglen);
     for (size_t i = 0; i < gram.size(); ++i)
@@ -449,11 +457,16 @@ template <int NIFO, int MODEL, int SC>
 static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st) {
     constexpr int RB = RecM<NIFO>::kBytes;
     const size_t smem = (size_t)kStages * kTileBins * RB + kStages * sizeof(uint64_t);
-    auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC>;
+    auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC, false>;
+    auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
     kern<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->n_bins_kernel, c->bins_per_chunk, c->d_coef,
                                        c->cap_walkers, n_walkers, c->d_partial);
+    // wide-phase fix-up: every CTA returns immediately unless the prologue flagged one of its walkers
+    fixup<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->n_bins_kernel, c->bins_per_chunk, c->d_coef,
+                                        c->cap_walkers, n_walkers, c->d_partial);
     CUDA_TRY(cudaGetLastError());
     note_launch(c, grid, smem, RB / 8, MODEL);
     return BJ_OK;

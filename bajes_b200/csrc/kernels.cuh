@@ -33,7 +33,6 @@ constexpr int kThreads = 128;        // walkers per CTA
 constexpr int kTileBins = 64;        // bins per smem stage
 constexpr int kStages = 4;
 constexpr double kMagic = 1572864.0; // 1.5 * 2^20: ulp(t + kMagic) == 2^-32 turns for |t| < 2^19
-constexpr double kMaxTurns = 450000.0;
 
 enum : int { MODEL_35 = 0, MODEL_GENERIC = 1 };
 
@@ -132,6 +131,12 @@ __device__ __forceinline__ void scaled_phasor(int32_t b, double Q, float Qf, dou
         sq = Q * s;
         cq = Q * c;
     }
+}
+
+// binary angle of an arbitrary turn count (no range limit): exact reduction t - rint(t), then round to 2^-32
+__device__ __forceinline__ int32_t robust_angle(double turns) {
+    const double r = turns - rint(turns);
+    return (int32_t)__double2ll_rn(r * 4294967296.0);      // r = +-0.5 wraps to the same angle
 }
 
 // Same phasors, returned as FP32 (cq, sq) for the mixed-precision kernel (no FP64 conversion at all).
@@ -299,7 +304,16 @@ __device__ __forceinline__ void process_bins(const double* __restrict__ rec, con
         for (int j = 0; j < NB; ++j) {
             const double tt = fma(f[j], w.tau[i], ph[j]);
             double cq, sq;
-            scaled_phasor<SC>(__double2loint(tt), Q[j], Qf[j], cq, sq);
+            if constexpr (SC == BJ_SINCOS_FP64) {
+                // validation mode: no binary-angle trick at all (k0m carries no magic constant here)
+                const double r = tt - rint(tt);
+                double sn, cs;
+                sincospi(2.0 * r, &sn, &cs);
+                sq = Q[j] * sn;
+                cq = Q[j] * cs;
+            } else {
+                scaled_phasor<SC>(__double2loint(tt), Q[j], Qf[j], cq, sq);
+            }
             const double2 d = *reinterpret_cast<const double2*>(rec + j * RS + 4 + 2 * i);
             // (dr + i di) * Q (c - i s)
             zr[i] = fma(d.x, cq, zr[i]);
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
 #pragma unroll
     for (int j = 0; j < WalkerRegs<NIFO, MODEL>::NBQ; ++j) w.bq[j] = coef[(C_B0 + j) * stride + wl];
     w.c8 = coef[C_C8 * stride + wl];
-    w.k0m = coef[C_K0 * stride + wl] + kMagic;
+    w.k0m = coef[C_K0 * stride + wl] + (SC == BJ_SINCOS_FP64 ? 0.0 : kMagic);
 #pragma unroll
     for (int j = 0; j < 6; ++j) w.q[j] = coef[(C_Q2 + j) * stride + wl];
     w.q6l = coef[C_Q6L * stride + wl];
@@ -440,7 +454,7 @@ __device__ __forceinline__ double amp_series_f64(double u, double L, const doubl
     return fma(u * u, t, 1.0);
 }
 
-template <int NIFO, int MODEL, int SC>
+template <int NIFO, int MODEL, int SC, bool ROBUST>
 __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restrict__ rec,
                                                    const WalkerRegsM<NIFO, MODEL>& w,
                                                    unsigned long long (&acc)[NIFO]) {
@@ -512,7 +526,7 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
         for (int j = 0; j < 2; ++j) {
             const double tt = fma(f[j], w.tau[i], ph[j]);
             float cq, sq;
-            scaled_phasor_f32<SC>(__double2loint(tt), Qf[j], cq, sq);
+            scaled_phasor_f32<SC>(ROBUST ? robust_angle(tt) : __double2loint(tt), Qf[j], cq, sq);
             const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(rec + j * RB + 48 + 16 * i);
             // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
             acc[i] = fma2(d.x, pack2(cq, cq), acc[i]);
@@ -521,7 +535,11 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
     }
 }
 
-template <int NIFO, int MODEL, int SC>
+// ROBUST = false: the production kernel.  ROBUST = true: the fix-up pass, launched right after it over the same grid;
+// a CTA exits at once unless the prologue flagged one of its walkers as "wide phase" (|turns| may exceed 2^19, the
+// range of the binary-angle trick), otherwise it recomputes the tile with the exact reduction t - rint(t) and
+// overwrites the tile's partial sums.
+template <int NIFO, int MODEL, int SC, bool ROBUST>
 __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(const unsigned char* __restrict__ rec,
                                                                        long n_bins, int bins_per_chunk,
                                                                        const double* __restrict__ coef, long stride,
@@ -533,6 +551,9 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 
     const long wi = (long)blockIdx.y * kThreads + threadIdx.x;
     const long wl = wi < n_walkers ? wi : n_walkers - 1;
+    if constexpr (ROBUST) {
+        if (!__syncthreads_or(coef[C_VALID * stride + wl] == 2.0)) return;
+    }
 
     WalkerRegsM<NIFO, MODEL> w;
 #pragma unroll
@@ -542,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 #pragma unroll
     for (int j = 0; j < WalkerRegsM<NIFO, MODEL>::NBQ; ++j) w.bq[j] = coef[(C_B0 + j) * stride + wl];
     w.c8 = coef[C_C8 * stride + wl];
-    w.k0m = coef[C_K0 * stride + wl] + kMagic;
+    w.k0m = coef[C_K0 * stride + wl] + (ROBUST ? 0.0 : kMagic);
 #pragma unroll
     for (int j = 0; j < 6; ++j) w.q[j] = (float)coef[(C_Q2 + j) * stride + wl];
     w.q6l = (float)coef[C_Q6L * stride + wl];
@@ -617,14 +638,14 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 #pragma unroll 1
         for (int blk = 0; blk < n_blocks; ++blk) {
             const unsigned char* base = tile + (size_t)blk * kBlockBins * RB;
-#pragma unroll kPairUnroll
-            for (int b = 0; b < kBlockBins; b += 2) process_pair_mixed<NIFO, MODEL, SC>(base + b * RB, w, acc);
+#pragma unroll (ROBUST ? 1 : kPairUnroll)
+            for (int b = 0; b < kBlockBins; b += 2) process_pair_mixed<NIFO, MODEL, SC, ROBUST>(base + b * RB, w, acc);
             flush();
         }
         {
             const int done = n_blocks * kBlockBins;
 #pragma unroll 1
-            for (int b = done; b + 2 <= nb; b += 2) process_pair_mixed<NIFO, MODEL, SC>(tile + (size_t)b * RB, w, acc);
+            for (int b = done; b + 2 <= nb; b += 2) process_pair_mixed<NIFO, MODEL, SC, ROBUST>(tile + (size_t)b * RB, w, acc);
             if (done < nb) flush();
         }
         __syncthreads();

@@ -37,7 +37,7 @@ enum : int {
     C_AMP = 35,
     C_CR0 = 36,      // Re C_i   [BJ_MAX_IFO]
     C_CI0 = 39,      // Im C_i   [BJ_MAX_IFO]
-    C_VALID = 42,    // 1.0 = evaluate, 0.0 = return -inf  (log_like.py:121-129)
+    C_VALID = 42,    // 0 = return -inf (log_like.py:121-129), 1 = evaluate, 2 = evaluate with the wide-phase path
     C_FP0 = 43,      // F+_i     [BJ_MAX_IFO]   (diagnostics / polarisation dump)
     C_FC0 = 46,      // Fx_i
     C_COSI = 49,
@@ -52,6 +52,7 @@ struct DeviceConfig {
     double dd_sum;
     double logZ_noise;
     double dh_fix_re, dh_fix_im;   // <d|h> correction: table scale / calibrated phasor bias (1 + 0i in fp64 mode)
+    double f_lo, f_hi;             // in-band frequency range (0, 0 when the context has no full grid)
     bj_detector det[BJ_MAX_IFO];
 };
 
@@ -403,7 +404,31 @@ __device__ inline void walker_coefficients(const DeviceConfig& cfg, const ParamM
     ok = ok && isfinite(hp_scale) && (hp_scale != 0.0) && isfinite(out[C_AMP] * cosi);
     // quirk (taylorf2.py:252): the 5.5PN phase takes (pi M f gt)^(1/3) WITHOUT abs -> NaN for M < 0
     if (order55 && !(mtot > 0.0)) ok = false;
-    out[C_VALID] = ok ? 1.0 : 0.0;
+    // The fast kernel reads the binary angle from the low word of (turns + 1.5 * 2^20), exact while |turns| < 2^19.
+    // Every term of the phase is monotone in f, so its magnitude is bounded by the larger of the two band ends.
+    double wide = 0.0;
+    if (ok && cfg.f_hi > 0.0) {
+        double bound = 0.0;
+        const double fe[2] = {cfg.f_lo, cfg.f_hi};
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+            const double u = cbrt(fe[e]), L = fabs(log(fe[e]));
+            const double w5 = 1.0 / (u * u * u * u * u);
+            double up = 1.0, sa = 0.0, sb = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) {
+                sa += fabs(out[C_A0 + j]) * up;
+                if (j < 7) sb += fabs(out[C_B0 + j]) * up;
+                up *= u;
+            }
+            bound = fmax(bound, w5 * sa + L * sb + L * L * fabs(out[C_C8]) * u * u * u);
+        }
+        double tmax = 0.0;
+        for (int i = 0; i < cfg.n_ifo; ++i) tmax = fmax(tmax, fabs(out[C_TAU0 + i]));
+        bound += fabs(out[C_K0]) + cfg.f_hi * tmax;
+        if (!(bound < 500000.0)) wide = 1.0;
+    }
+    out[C_VALID] = ok ? 1.0 + wide : 0.0;
 }
 
 }  // namespace bj

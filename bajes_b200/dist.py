@@ -50,9 +50,11 @@ class ShardedEvaluator:
         # 1. batch size, then the parameter block, from the sampler rank
         n = torch.zeros(1, dtype=torch.int64, device=self.device)
         if self.rank == self.src:
-            n[0] = len(X)
+            n[0] = -1 if X is None else len(X)
         dist.broadcast(n, src=self.src, group=self.group)
         W = int(n.item())
+        if W < 0:                       # shutdown signal for the worker loop
+            return None
         if self.rank == self.src:
             xt = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(self.device)
         else:
@@ -70,6 +72,38 @@ class ShardedEvaluator:
         dist.all_gather_into_tensor(recv, send, group=self.group)
         recv = recv.cpu().numpy().reshape(self.world, chunk)
         return np.concatenate([recv[r, :hi[r] - lo[r]] for r in range(self.world)])
+
+
+    def serve(self):
+        """Worker loop of the non-sampler ranks (the role of MPIPool.wait, bajes/pipe/utils/mpi.py:91-117):
+        take part in every evaluate() of the sampler rank until it calls shutdown()."""
+        assert self.rank != self.src
+        n_calls = 0
+        while self.evaluate(None) is not None:
+            n_calls += 1
+        return n_calls
+
+    def shutdown(self):
+        """Sampler rank: release the workers."""
+        if self.world > 1 and self.rank == self.src:
+            self.evaluate(None)
+
+
+class ShardedLikelihood:
+    """Likelihood facade for the sampler rank: ``log_like_batch`` shards the batch over all ranks."""
+
+    def __init__(self, like, evaluator):
+        self.like = like
+        self.evaluator = evaluator
+        for attr in ("ifos", "dets", "logZ_noise"):
+            if hasattr(like, attr):
+                setattr(self, attr, getattr(like, attr))
+
+    def log_like_batch(self, X, names, const=None):
+        return self.evaluator.evaluate(np.ascontiguousarray(X, dtype=np.float64))
+
+    def log_like(self, params):
+        return self.like.log_like(params)
 
 
 class DeviceShardedLikelihood:

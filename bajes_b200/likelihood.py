@@ -268,21 +268,33 @@ class Posterior(object):
         Xf, names, const = self._batch_inputs(X)
         return self.like.log_like_batch(Xf, names, const)
 
+    def _prior_batch(self, X):
+        """(in-bounds mask, log-prior of the in-bounds rows); uses the prior's vectorised methods when it has them
+        (a bajes ``Prior`` is evaluated row by row, as bajes itself does)."""
+        if hasattr(self.prior, "in_bounds_batch"):
+            inb = np.asarray(self.prior.in_bounds_batch(X), dtype=bool)
+        else:
+            inb = np.array([bool(self.prior.in_bounds(x)) for x in X])
+        if hasattr(self.prior, "log_prior_batch"):
+            lnp = np.asarray(self.prior.log_prior_batch(X[inb]), dtype=float)
+        else:
+            lnp = np.array([self.prior.log_prior(x) for x in X[inb]], dtype=float)
+        return inb, lnp
+
     def log_post_batch(self, X):
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
-        inb = np.array([bool(self.prior.in_bounds(x)) for x in X])
+        inb, lnp = self._prior_batch(X)
         out = np.full(X.shape[0], -np.inf)
         if inb.any():
-            lnp = np.array([self.prior.log_prior(x) for x in X[inb]])
             out[inb] = lnp + self.log_like_batch(X[inb])
         return out
 
     def log_likeprior_batch(self, X):
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
-        inb = np.array([bool(self.prior.in_bounds(x)) for x in X])
+        inb, lnp_in = self._prior_batch(X)
         lnl = np.zeros(X.shape[0])
         lnp = np.full(X.shape[0], -np.inf)
         if inb.any():
-            lnp[inb] = np.array([self.prior.log_prior(x) for x in X[inb]])
+            lnp[inb] = lnp_in
             lnl[inb] = self.log_like_batch(X[inb])
         return lnl, lnp

@@ -39,17 +39,22 @@ class BatchedPool(multiprocessing.pool.Pool):
         name = getattr(func, "__name__", "")
         batched = _BATCHED.get(name)
         if owner is not None and batched is not None and hasattr(owner, batched):
-            pts = [np.asarray(p, dtype=np.float64) for p in iterable]
-            if len(pts) == 0:
+            if isinstance(iterable, np.ndarray) and iterable.ndim == 2:
+                X = np.ascontiguousarray(iterable, dtype=np.float64)
+            else:
+                pts = [np.asarray(p, dtype=np.float64) for p in iterable]
+                if len(pts) == 0:
+                    return []
+                X = np.stack(pts)
+            if len(X) == 0:
                 return []
-            X = np.stack(pts)
             self.n_batched_calls += 1
-            self.n_points += len(pts)
+            self.n_points += len(X)
             res = getattr(owner, batched)(X)
             if name == "log_likeprior":
                 lnl, lnp = res
-                return [(float(a), float(b)) for a, b in zip(lnl, lnp)]
-            return [float(v) for v in res]
+                return list(zip(lnl.tolist(), lnp.tolist()))
+            return np.asarray(res).tolist()
         return [func(x) for x in iterable]
 
     def imap(self, func, iterable, chunksize=1):

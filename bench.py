@@ -386,7 +386,7 @@ def main():
             "config": workload(cfg, args, W), "evals_per_s": value / nb,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Xmine.nbytes),
                     "d2h_bytes_per_step": int(W * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": 3 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
             "sincos": args.sincos, "wall_s_timed_region": t_wall}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -85,43 +85,11 @@ def tolerance(ref):
     return 1e-6 * np.abs(np.where(np.isfinite(ref), ref, 0.0)) + 1e-4
 
 
-# ---- synthetic ROQ bases (format-only: smooth random interpolants in the JenpyROQ layout) -------------
-def make_roq_basis(cfg, n_lin=48, n_quad=24, seed=7):
-    """Deterministic stand-in for a JenpyROQ basis on the in-band axis of ``cfg``:
-    returns dict(lin_f, quad_f, lin_b [N, n_lin] complex, quad_b [N, n_quad] real).  Node frequencies
-    are a subset of the axis (so the joined axis is on-grid); the interpolants are smooth bumps with a
-    slowly varying complex phase -- enough to exercise every code path."""
-    rng = np.random.default_rng(seed)
-    f = syn.frequency_axis(cfg)
-    fb = f[(f >= cfg["f_min"]) & (f <= cfg["f_max"])]
-    n = len(fb)
-    il = np.unique(np.round(np.geomspace(1, n - 2, n_lin)).astype(int))
-    iq = np.unique(np.round(np.geomspace(2, n - 3, n_quad)).astype(int))
-    x = np.linspace(0.0, 1.0, n)
-
-    def bumps(idx, cplx):
-        cols = []
-        for i in idx:
-            width = 0.01 + 0.05 * rng.random()
-            b = np.exp(-0.5 * ((x - x[i]) / width) ** 2)
-            if cplx:
-                b = b * np.exp(1j * (rng.normal() + 6.0 * rng.random() * (x - x[i])))
-            cols.append(b / np.sqrt(n))
-        return np.stack(cols, axis=1)
-
-    return dict(lin_f=fb[il], quad_f=fb[iq], lin_b=bumps(il, True), quad_b=np.real(bumps(iq, False)))
+# ---- synthetic ROQ bases: generator lives in bajes_b200/synthetic.py (shared with the benchmarks) -----------
+make_roq_basis = syn.make_roq_basis
 
 
-def write_jenpyroq(path, basis, cfg):
-    """JenpyROQ directory layout read by roq.py:834-853."""
-    os.makedirs(os.path.join(path, "ROQ_data/linear"), exist_ok=True)
-    os.makedirs(os.path.join(path, "ROQ_data/quadratic"), exist_ok=True)
-    np.save(os.path.join(path, "ROQ_data/linear/empirical_frequencies_linear.npy"), basis["lin_f"])
-    np.save(os.path.join(path, "ROQ_data/quadratic/empirical_frequencies_quadratic.npy"), basis["quad_f"])
-    np.save(os.path.join(path, "ROQ_data/linear/basis_interpolant_linear.npy"), basis["lin_b"])
-    np.save(os.path.join(path, "ROQ_data/quadratic/basis_interpolant_quadratic.npy"), basis["quad_b"])
-    with open(os.path.join(path, "ROQ_data/ROQ_metadata.txt"), "w") as fh:
-        fh.write("# fmin fmax seglen\n%.17g %.17g %.17g\n" % (cfg["f_min"], cfg["f_max"], cfg["seglen"]))
+write_jenpyroq = syn.write_jenpyroq
 
 
 class FakePrior:
