@@ -30,7 +30,10 @@ class ShardedEvaluator:
     tests pass any pure function.
     """
 
-    def __init__(self, local_eval: Callable[[np.ndarray], np.ndarray], ndim: int, group=None, device=None, src=0):
+    def __init__(self, local_eval: Callable[[np.ndarray], np.ndarray], ndim: int, group=None, device=None, src=0,
+                 local_eval_device=None):
+        """``local_eval_device(x_dev [w, ndim], out_dev [w])`` (optional, CUDA): evaluates a device-resident slice in
+        place on the current stream -- the shard then never leaves HBM between the broadcast and the all-gather."""
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -42,6 +45,7 @@ class ShardedEvaluator:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else torch.device("cpu")
+        self.local_eval_device = local_eval_device
 
     def evaluate(self, X: Optional[np.ndarray]) -> np.ndarray:
         torch, dist = self.torch, self.dist
@@ -63,11 +67,14 @@ class ShardedEvaluator:
         # 2. each rank evaluates its contiguous slice (no data-path collective)
         lo, hi = shard_bounds(W, self.world)
         mine = xt[lo[self.rank]:hi[self.rank]]
-        out = np.asarray(self.local_eval(mine.cpu().numpy()), dtype=np.float64)
         # 3. all-gather (padded to equal chunks so one collective suffices)
         chunk = max(h - l for l, h in zip(lo, hi))
         send = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
-        send[:len(out)] = torch.as_tensor(out).to(self.device)
+        if self.local_eval_device is not None and mine.shape[0] > 0:
+            self.local_eval_device(mine.contiguous(), send[:mine.shape[0]])
+        else:
+            out = np.asarray(self.local_eval(mine.cpu().numpy()), dtype=np.float64)
+            send[:len(out)] = torch.as_tensor(out).to(self.device)
         recv = torch.empty(chunk * self.world, dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         recv = recv.cpu().numpy().reshape(self.world, chunk)

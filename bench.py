@@ -275,6 +275,8 @@ def main():
     t_wall0 = time.perf_counter()
     for a, b in ev:
         flush.zero_()                              # L2 flush, outside the timed events
+        if world > 1:
+            dist.barrier()                         # align the ranks (untimed) so the all-gather does not absorb skew
         a.record()
         step_device()
         b.record()
@@ -284,11 +286,19 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([float(np.mean(step_ms)), float(np.mean(kern_ms))], dtype=torch.float64, device=dev)
+    per_rank_all = per_rank.clone().unsqueeze(0)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        per_rank_all = torch.empty((world, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(per_rank_all, per_rank)
+    per_rank_all = per_rank_all.cpu().numpy().round(4).tolist()
     total_s = float(total_ms.item()) * 1e-3
 
-    # ---- end-to-end through the host-pointer C ABI (H2D + kernels + D2H inside the timed region) -------------
+    # ---- end-to-end through the public API, host buffers in / out inside the timed region ----------------------
+    #   N = 1: the host-pointer C-ABI entry bj_loglike (pinned X -> H2D -> prologue/kernel/epilogue -> D2H logL)
+    #   N > 1: ShardedEvaluator.evaluate on the sampler rank (host X -> device, NCCL broadcast, every rank evaluates
+    #          its slice, NCCL all-gather, device -> host), the other ranks in serve()
     pmap = like.param_map(names, const)
     import ctypes as C
     lib = engine.load_library()
@@ -298,19 +308,41 @@ def main():
                             C.byref(pmap.c), C.cast(out_pin.data_ptr(), C.POINTER(C.c_double)))
         assert rc == 0, lib.bj_last_error()
 
-    for _ in range(3):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    torch.cuda.synchronize(dev)
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if world == 1:
+        for _ in range(3):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        assert np.array_equal(out_pin.numpy(), out_dev.cpu().numpy()), "host and device entry points disagree"
+        h2d, d2h = int(Xmine.nbytes), int(W * 8)
+    else:
+        from bajes_b200.dist import ShardedEvaluator
+
+        def eval_dev(xs, outs):
+            like.engine.loglike_device(xs.data_ptr(), xs.shape[0], len(names), pmap, outs.data_ptr(), 0,
+                                       torch.cuda.current_stream(dev).cuda_stream)
+
+        she = ShardedEvaluator(lambda Xs: like.log_like_batch(Xs, names, const), ndim=len(names), device=dev,
+                               local_eval_device=eval_dev)
+        e2e_s = 0.0
+        if rank == 0:
+            for _ in range(3):
+                got = she.evaluate(Xall)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                got = she.evaluate(Xall)
+            e2e_s = time.perf_counter() - t0
+            she.shutdown()
+            assert np.array_equal(got[:W], out_dev.cpu().numpy()), "sharded and local results disagree"
+        else:
+            she.serve()
+        h2d, d2h = int(Xall.nbytes), int(W * world * 8)
     clk = clocks.stop() if rank == 0 else None
-    e2e_s = float(e2e_s.item())
-    assert np.array_equal(out_pin.numpy(), out_dev.cpu().numpy()), "host and device entry points disagree"
 
     if rank != 0:
         if world > 1:
@@ -384,10 +416,13 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload(cfg, args, W), "evals_per_s": value / nb,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Xmine.nbytes),
-                    "d2h_bytes_per_step": int(W * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "path": "bj_loglike (host pointers)" if world == 1 else
+                            "ShardedEvaluator.evaluate: host X -> NCCL broadcast -> per-rank slices -> NCCL all-gather -> host"},
             "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "sincos": args.sincos, "wall_s_timed_region": t_wall}
+            "sincos": args.sincos, "wall_s_timed_region": t_wall,
+            "per_rank_ms": {"step_and_fused_kernel": per_rank_all}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

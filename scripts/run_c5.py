@@ -63,7 +63,14 @@ def main():
     bounds[names.index("lambda2"), 0] = max(0.0, bounds[names.index("lambda2"), 0])
     prior = BoxPrior(names, bounds, const)
 
-    ev = ShardedEvaluator(lambda Xs: like.log_like_batch(Xs, names, const), ndim=len(names), device=dev)
+    pmap = like.param_map(names, const)
+
+    def eval_device(x_dev, out_dev):
+        like.engine.loglike_device(x_dev.data_ptr(), x_dev.shape[0], len(names), pmap, out_dev.data_ptr(), 0,
+                                   torch.cuda.current_stream(dev).cuda_stream)
+
+    ev = ShardedEvaluator(lambda Xs: like.log_like_batch(Xs, names, const), ndim=len(names), device=dev,
+                          local_eval_device=eval_device if world > 1 else None)
     if rank != 0:
         ev.serve()
         dist.destroy_process_group()
