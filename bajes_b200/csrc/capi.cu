@@ -84,6 +84,15 @@ struct bj_ctx {
     double* d_gram = nullptr;
     int bins_per_chunk = 0;
     int n_chunks = 0;
+    // cells / chunks / extras (calibration envelopes, PSD weights)
+    ExtrasDims dims;
+    int n_cells = 1;
+    ChunkDesc* d_chunks = nullptr;
+    int* d_cell_band = nullptr;
+    int* d_cell_seg = nullptr;
+    double* d_dd_band = nullptr;
+    double* d_spcal_freqs = nullptr;
+    double* d_coef_ex = nullptr;
     // ROQ / relbin static tables
     RoqDevice roq;
     RelbinDevice relbin;
@@ -139,6 +148,7 @@ static int init_common(bj_ctx* c, const bj_config* cfg) {
     c->cfg.dh_fix_im = 0.0;
     c->cfg.f_lo = 0.0;
     c->cfg.f_hi = 0.0;
+    memset(&c->dims, 0, sizeof(c->dims));
     for (int i = 0; i < BJ_MAX_IFO; ++i) c->cfg.det[i] = cfg->det[i];
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&c->ev[i]));
@@ -178,37 +188,137 @@ static void data_weight(const BinStatics& b, double four_over_t, double dre, dou
     wi = sc * (cre * b.sn + cim * b.cs);
 }
 
-// Gram moments of <h|h>: G_i[m][n] = sum_k phi_m phi_n (4/T) f^(-7/3) / S_i   (detector.py:539), long double sums
-static void build_gram(std::vector<double>& gram, int nifo, long n, const double* freqs, const double* const* psd,
+// ------------------------------------------------------------------------------------------------
+// table layout: cells (runs of bins with constant PSD-weight band and calibration segment), padded to an even
+// number of records, cut into chunks
+// ------------------------------------------------------------------------------------------------
+struct Layout {
+    std::vector<long> slot_bin;      // table slot -> in-band bin whose statics it carries
+    std::vector<char> slot_real;     // 0 for zero-weight padding slots
+    std::vector<double> slot_t;      // calibration interpolation fraction in [0, 1]
+    std::vector<int> slot_cell;
+    std::vector<int> cell_band, cell_seg;
+    std::vector<ChunkDesc> chunks;
+    int per = 0;
+};
+
+static int build_layout(Layout& L, long n, const double* freqs, const bj_extras* ex) {
+    const int nsp = ex ? ex->nspcal : 0, nw = ex ? ex->nweights : 0;
+    std::vector<int> band(n, 0), seg(n, 0);
+    std::vector<double> tt(n, 0.0);
+    if (nw > 0) {
+        long k = 0;
+        for (int b = 0; b < nw; ++b)
+            for (int64_t m = 0; m < ex->len_weights[b] && k < n; ++m) band[k++] = b;
+        if (k != n) return -1;
+    }
+    if (nsp > 0) {
+        const double* nf = ex->spcal_freqs;
+        for (long k = 0; k < n; ++k) {
+            const double f = freqs[k];
+            if (f <= nf[0]) { seg[k] = 0; tt[k] = 0.0; }                       // np.interp clamps (detector.py:519)
+            else if (f >= nf[nsp - 1]) { seg[k] = nsp - 2; tt[k] = 1.0; }
+            else {
+                int j = 0;
+                while (j + 2 < nsp && f >= nf[j + 1]) ++j;
+                seg[k] = j;
+                tt[k] = (f - nf[j]) / (nf[j + 1] - nf[j]);
+            }
+        }
+    }
+    long k = 0;
+    while (k < n) {
+        const int cell = (int)L.cell_band.size();
+        L.cell_band.push_back(band[k]);
+        L.cell_seg.push_back(seg[k]);
+        long k1 = k;
+        while (k1 < n && band[k1] == band[k] && seg[k1] == seg[k]) {
+            L.slot_bin.push_back(k1); L.slot_real.push_back(1); L.slot_t.push_back(tt[k1]); L.slot_cell.push_back(cell);
+            ++k1;
+        }
+        if ((k1 - k) & 1) {                        // pad the cell to an even number of records
+            L.slot_bin.push_back(k1 - 1); L.slot_real.push_back(0); L.slot_t.push_back(tt[k1 - 1]); L.slot_cell.push_back(cell);
+        }
+        k = k1;
+    }
+    // chunk size depends on the table ONLY, so the reduction tree (and every output bit) is independent of how many
+    // walkers a call or a rank evaluates
+    const long total = (long)L.slot_bin.size();
+    long per = (total + 127) / 128;
+    per = ((per + kTileBins - 1) / kTileBins) * kTileBins;
+    if (per < 256) per = 256;
+    L.per = (int)per;
+    long s0 = 0;
+    while (s0 < total) {
+        const int cell = L.slot_cell[s0];
+        long s1 = s0;
+        while (s1 < total && L.slot_cell[s1] == cell) ++s1;
+        for (long a = s0; a < s1; a += per) {
+            ChunkDesc cd;
+            cd.start = (int)a;
+            cd.len = (int)std::min(per, s1 - a);
+            cd.band = L.cell_band[cell];
+            cd.seg = L.cell_seg[cell];
+            L.chunks.push_back(cd);
+        }
+        s0 = s1;
+    }
+    return 0;
+}
+
+// Gram moments of <h|h> per detector, cell and t-weight: sum_k phi_m phi_n (4/T) f^(-7/3) / S_i * {(1-t)^2, t(1-t), t^2}
+// (detector.py:539; without calibration only the first set, with weight 1); and (4/T) sum |d|^2/S per weight band
+static void build_gram(std::vector<double>& gram, std::vector<double>& dd_band, const Layout& L, int nifo, int nsp,
+                       int nw, const double* freqs, const double* const* data_ri, const double* const* psd,
                        double seglen) {
-    std::vector<long double> acc((size_t)nifo * kGram, 0.0L);
+    const int ncell = (int)L.cell_band.size();
+    std::vector<long double> acc((size_t)nifo * ncell * 3 * kGram, 0.0L);
+    std::vector<long double> dd((size_t)nifo * (nw > 0 ? nw : 1), 0.0L);
     const double four_over_t = 4.0 / seglen;
-    for (long k = 0; k < n; ++k) {
+    for (size_t sidx = 0; sidx < L.slot_bin.size(); ++sidx) {
+        if (!L.slot_real[sidx]) continue;
+        const long k = L.slot_bin[sidx];
+        const int cell = L.slot_cell[sidx];
         const BinStatics b = bin_statics(freqs[k], seglen);
         const double u2 = b.u * b.u, u3 = u2 * b.u, u4 = u2 * u2, u5 = u4 * b.u, u6 = u3 * u3, u7 = u6 * b.u;
         const long double phi[kBasis] = {1.0L, u2, u3, u4, u5, u6, u7, (long double)b.L * u6};
+        const long double t = L.slot_t[sidx];
+        const long double tw[3] = {nsp > 0 ? (1 - t) * (1 - t) : 1.0L, nsp > 0 ? t * (1 - t) : 0.0L, nsp > 0 ? t * t : 0.0L};
         for (int i = 0; i < nifo; ++i) {
             const long double sw = (long double)four_over_t * (1.0 / psd[i][k]) * b.g * b.g;
-            int idx = 0;
-            for (int m = 0; m < kBasis; ++m)
-                for (int q = m; q < kBasis; ++q, ++idx) acc[(size_t)i * kGram + idx] += phi[m] * phi[q] * sw;
+            for (int st = 0; st < 3; ++st) {
+                if (tw[st] == 0.0L) continue;
+                long double* a = &acc[(((size_t)i * ncell + cell) * 3 + st) * kGram];
+                int idx = 0;
+                for (int m = 0; m < kBasis; ++m)
+                    for (int q = m; q < kBasis; ++q, ++idx) a[idx] += phi[m] * phi[q] * sw * tw[st];
+            }
+            if (nw > 0) {
+                const long double re = data_ri[i][2 * k], im = data_ri[i][2 * k + 1];
+                dd[(size_t)i * nw + L.cell_band[cell]] += (long double)four_over_t * (re * re + im * im) / psd[i][k];
+            }
         }
     }
     gram.resize(acc.size());
     for (size_t i = 0; i < acc.size(); ++i) gram[i] = (double)acc[i];
+    dd_band.resize(dd.size());
+    for (size_t i = 0; i < dd.size(); ++i) dd_band[i] = (double)dd[i];
 }
 
 // all-FP64 records (validation mode)
 template <int NIFO>
-static void build_records(std::vector<double>& rec, long n, const double* freqs, const double* const* data_ri,
-                          const double* const* psd, double seglen) {
+static void build_records(std::vector<double>& rec, const Layout& L, const double* freqs,
+                          const double* const* data_ri, const double* const* psd, double seglen) {
     constexpr int RS = Rec<NIFO>::kDoubles;
-    rec.assign((size_t)n * RS, 0.0);
+    const size_t n = L.slot_bin.size();
+    rec.assign(n * RS, 0.0);
     const double four_over_t = 4.0 / seglen;
-    for (long k = 0; k < n; ++k) {
+    for (size_t sidx = 0; sidx < n; ++sidx) {
+        const long k = L.slot_bin[sidx];
         const BinStatics b = bin_statics(freqs[k], seglen);
-        double* r = &rec[(size_t)k * RS];
+        double* r = &rec[sidx * RS];
         r[0] = b.u; r[1] = b.L; r[2] = b.w5; r[3] = b.f;
+        if (!L.slot_real[sidx]) continue;
         for (int i = 0; i < NIFO; ++i)
             data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], r[4 + 2 * i], r[5 + 2 * i]);
     }
@@ -216,13 +326,16 @@ static void build_records(std::vector<double>& rec, long n, const double* freqs,
 
 // mixed-precision records: FP64 phase statics, FP32 amplitude statics and data weights scaled by 2^-e
 template <int NIFO>
-static int build_records_mixed(std::vector<unsigned char>& rec, long n, long n_padded, const double* freqs,
+static int build_records_mixed(std::vector<unsigned char>& rec, const Layout& L, const double* freqs,
                                const double* const* data_ri, const double* const* psd, double seglen, int* exp_out) {
     constexpr int RB = RecM<NIFO>::kBytes;
-    rec.assign((size_t)n_padded * RB, 0);
+    const size_t n = L.slot_bin.size();
+    rec.assign(n * RB, 0);
     const double four_over_t = 4.0 / seglen;
     double mx = 0.0;
-    for (long k = 0; k < n; ++k) {
+    for (size_t sidx = 0; sidx < n; ++sidx) {
+        if (!L.slot_real[sidx]) continue;
+        const long k = L.slot_bin[sidx];
         const BinStatics b = bin_statics(freqs[k], seglen);
         for (int i = 0; i < NIFO; ++i) {
             double wr, wi;
@@ -234,23 +347,28 @@ static int build_records_mixed(std::vector<unsigned char>& rec, long n, long n_p
     int e = 0;
     if (mx > 0.0) std::frexp(mx, &e);       // mx = m 2^e, m in [0.5, 1)  ->  scaled weights below 1
     const double sc = std::ldexp(1.0, -e);
-    for (long k = 0; k < n_padded; ++k) {
-        const long ks = k < n ? k : n - 1;   // padding record: statics of the last bin, zero weights
-        const BinStatics b = bin_statics(freqs[ks], seglen);
-        unsigned char* r = &rec[(size_t)k * RB];
+    for (size_t sidx = 0; sidx < n; ++sidx) {
+        const long k = L.slot_bin[sidx];
+        const BinStatics b = bin_statics(freqs[k], seglen);
+        unsigned char* r = &rec[sidx * RB];
         double hd[4] = {b.u, b.L, b.w5, b.f};
         memcpy(r, hd, 32);
-        // pair slot: even record (uf_even, uf_odd), odd record (Lf_even, Lf_odd)
-        const long ke = k & ~1L, ko = ke + 1;
-        const BinStatics be = bin_statics(freqs[ke < n ? ke : n - 1], seglen);
-        const BinStatics bo = bin_statics(freqs[ko < n ? ko : n - 1], seglen);
+        // pair slots (records are consumed in (even, odd) pairs; cells and chunks start on even records):
+        //   even record: (uf_even, uf_odd) and (t_even, t_odd)      odd record: (Lf_even, Lf_odd)
+        const size_t se = sidx & ~(size_t)1, so = se + 1;
+        const BinStatics be = bin_statics(freqs[L.slot_bin[se]], seglen);
+        const BinStatics bo = bin_statics(freqs[L.slot_bin[so < n ? so : se]], seglen);
         float hf[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if ((k & 1) == 0) { hf[0] = (float)be.u; hf[1] = (float)bo.u; }
-        else              { hf[0] = (float)be.L; hf[1] = (float)bo.L; }
+        if ((sidx & 1) == 0) {
+            hf[0] = (float)be.u; hf[1] = (float)bo.u;
+            hf[2] = (float)L.slot_t[se]; hf[3] = (float)L.slot_t[so < n ? so : se];
+        } else {
+            hf[0] = (float)be.L; hf[1] = (float)bo.L;
+        }
         memcpy(r + 32, hf, 16);
         for (int i = 0; i < NIFO; ++i) {
             double wr = 0.0, wi = 0.0;
-            if (k < n) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            if (L.slot_real[sidx]) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
             const float fr = (float)(wr * sc), fi = (float)(wi * sc);
             float d4[4] = {fr, fi, fi, -fr};
             memcpy(r + 48 + 16 * i, d4, 16);
@@ -272,30 +390,64 @@ static int calibrate(double* eps2) {
     return BJ_OK;
 }
 
-extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
-                         const double* const* data_ri, const double* const* psd) {
+template <typename T>
+static cudaError_t upload(T** dst, const std::vector<T>& src) {
+    if (src.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dst, src.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
+                            const double* const* data_ri, const double* const* psd, const bj_extras* ex) {
     if (!out) return fail(BJ_ERR_INVALID, "null out pointer");
     *out = nullptr;
     int rc = check_config(cfg);
     if (rc) return rc;
     if (n_bins <= 0 || !freqs || !data_ri || !psd) return fail(BJ_ERR_INVALID, "empty frequency axis or null tables");
-    for (int64_t k = 0; k < n_bins; ++k)
+    for (int64_t k = 0; k < n_bins; ++k) {
         if (!(freqs[k] > 0.0) || !std::isfinite(freqs[k]))
             return fail(BJ_ERR_INVALID, "freqs[%lld]=%g: in-band frequencies must be positive and finite", (long long)k,
                         freqs[k]);
+        if (k > 0 && !(freqs[k] > freqs[k - 1])) return fail(BJ_ERR_INVALID, "in-band frequencies must be ascending");
+    }
+    const int nsp = ex ? ex->nspcal : 0, nw = ex ? ex->nweights : 0;
+    if (nsp < 0 || nsp == 1 || nsp > BJ_MAX_SPCAL) return fail(BJ_ERR_INVALID, "nspcal=%d outside {0, 2..%d}", nsp, BJ_MAX_SPCAL);
+    if (nw < 0 || nw > BJ_MAX_WEIGHTS) return fail(BJ_ERR_INVALID, "nweights=%d outside 0..%d", nw, BJ_MAX_WEIGHTS);
+    if (nsp > 0) {
+        if (!ex->spcal_freqs) return fail(BJ_ERR_INVALID, "null spcal_freqs");
+        for (int j = 1; j < nsp; ++j)
+            if (!(ex->spcal_freqs[j] > ex->spcal_freqs[j - 1])) return fail(BJ_ERR_INVALID, "spcal_freqs must be ascending");
+    }
+    if (nw > 0) {
+        if (!ex->len_weights) return fail(BJ_ERR_INVALID, "null len_weights");
+        int64_t tot = 0;
+        for (int b = 0; b < nw; ++b) {
+            if (ex->len_weights[b] < 0) return fail(BJ_ERR_INVALID, "negative len_weights[%d]", b);
+            tot += ex->len_weights[b];
+        }
+        if (tot != n_bins) return fail(BJ_ERR_INVALID, "sum(len_weights)=%lld differs from n_bins=%lld", (long long)tot, (long long)n_bins);
+    }
     bj_ctx* c = new bj_ctx();
     rc = init_common(c, cfg);
     if (rc) { delete c; return rc; }
     c->kind = KIND_FULLGRID;
     c->n_bins = n_bins;
+    c->dims.nspcal = nsp;
+    c->dims.nweights = nw;
+    for (int b = 0; b < nw; ++b) c->dims.len_weights[b] = (int)ex->len_weights[b];
     c->cfg.f_lo = freqs[0];
-    c->cfg.f_hi = freqs[0];
-    for (int64_t k = 0; k < n_bins; ++k) {
-        c->cfg.f_lo = std::fmin(c->cfg.f_lo, freqs[k]);
-        c->cfg.f_hi = std::fmax(c->cfg.f_hi, freqs[k]);
-    }
-    std::vector<double> gram;
-    build_gram(gram, cfg->n_ifo, n_bins, freqs, psd, cfg->seglen);
+    c->cfg.f_hi = freqs[n_bins - 1];
+
+    Layout L;
+    if (build_layout(L, n_bins, freqs, ex)) { bj_destroy(c); return fail(BJ_ERR_INVALID, "len_weights do not cover the band"); }
+    c->n_cells = (int)L.cell_band.size();
+    c->n_chunks = (int)L.chunks.size();
+    c->bins_per_chunk = L.per;
+    c->n_bins_kernel = (long)L.slot_bin.size();
+
+    std::vector<double> gram, dd_band;
+    build_gram(gram, dd_band, L, cfg->n_ifo, nsp, nw, freqs, data_ri, psd, cfg->seglen);
     for (size_t i = 0; i < gram.size(); ++i)
         if (!std::isfinite(gram[i])) {
             bj_destroy(c);
@@ -306,26 +458,24 @@ extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, con
     std::vector<double> rec;
     std::vector<unsigned char> recm;
     if (cfg->sincos == BJ_SINCOS_FP64) {
-        c->n_bins_kernel = n_bins;
         switch (cfg->n_ifo) {
-            case 1: build_records<1>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<1>::kDoubles; break;
-            case 2: build_records<2>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<2>::kDoubles; break;
-            default: build_records<3>(rec, n_bins, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<3>::kDoubles; break;
+            case 1: build_records<1>(rec, L, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<1>::kDoubles; break;
+            case 2: build_records<2>(rec, L, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<2>::kDoubles; break;
+            default: build_records<3>(rec, L, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<3>::kDoubles; break;
         }
         for (size_t i = 0; i < rec.size(); ++i)
             if (!std::isfinite(rec[i])) {
                 bj_destroy(c);
-                return fail(BJ_ERR_INVALID, "non-finite static table entry at bin %zu (check data / PSD)", i / c->rec_doubles);
+                return fail(BJ_ERR_INVALID, "non-finite static table entry at record %zu (check data / PSD)", i / c->rec_doubles);
             }
         rec_ptr = rec.data();
         rec_bytes = rec.size() * sizeof(double);
     } else {
-        c->n_bins_kernel = n_bins + (n_bins & 1);      // the mixed kernel consumes bins in pairs
         int e2 = 0, bad = 0;
         switch (cfg->n_ifo) {
-            case 1: bad = build_records_mixed<1>(recm, n_bins, c->n_bins_kernel, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<1>::kDoubles; break;
-            case 2: bad = build_records_mixed<2>(recm, n_bins, c->n_bins_kernel, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<2>::kDoubles; break;
-            default: bad = build_records_mixed<3>(recm, n_bins, c->n_bins_kernel, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<3>::kDoubles; break;
+            case 1: bad = build_records_mixed<1>(recm, L, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<1>::kDoubles; break;
+            case 2: bad = build_records_mixed<2>(recm, L, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<2>::kDoubles; break;
+            default: bad = build_records_mixed<3>(recm, L, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<3>::kDoubles; break;
         }
         if (bad) {
             bj_destroy(c);
@@ -345,17 +495,17 @@ extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, con
         rec_ptr = recm.data();
         rec_bytes = recm.size();
     }
-    // frequency chunking depends on n_bins ONLY, so the reduction tree (and every output bit) is
-    // independent of how many walkers a call or a rank evaluates
-    long per = (c->n_bins_kernel + 127) / 128;
-    per = ((per + kTileBins - 1) / kTileBins) * kTileBins;
-    if (per < 256) per = 256;
-    c->bins_per_chunk = (int)per;
-    c->n_chunks = (int)((c->n_bins_kernel + per - 1) / per);
     cudaError_t e = cudaMalloc(&c->d_rec, rec_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, rec_ptr, rec_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_gram, gram.size() * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemcpy(c->d_gram, gram.data(), gram.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = upload(&c->d_gram, gram);
+    if (e == cudaSuccess) e = upload(&c->d_dd_band, dd_band);
+    if (e == cudaSuccess) e = upload(&c->d_chunks, L.chunks);
+    if (e == cudaSuccess) e = upload(&c->d_cell_band, L.cell_band);
+    if (e == cudaSuccess) e = upload(&c->d_cell_seg, L.cell_seg);
+    if (e == cudaSuccess && nsp > 0) {
+        std::vector<double> nf(ex->spcal_freqs, ex->spcal_freqs + nsp);
+        e = upload(&c->d_spcal_freqs, nf);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&c->d_freqs, (size_t)n_bins * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(c->d_freqs, freqs, (size_t)n_bins * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -366,12 +516,23 @@ extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, con
     return BJ_OK;
 }
 
+extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
+                         const double* const* data_ri, const double* const* psd) {
+    return bj_create_ex(out, cfg, n_bins, freqs, data_ri, psd, nullptr);
+}
+
 extern "C" int bj_destroy(bj_ctx* c) {
     if (!c) return BJ_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_rec);
     cudaFree(c->d_freqs);
     cudaFree(c->d_gram);
+    cudaFree(c->d_chunks);
+    cudaFree(c->d_cell_band);
+    cudaFree(c->d_cell_seg);
+    cudaFree(c->d_dd_band);
+    cudaFree(c->d_spcal_freqs);
+    cudaFree(c->d_coef_ex);
     cudaFree(c->d_coef);
     cudaFree(c->d_partial);
     cudaFree(c->d_x);
@@ -395,8 +556,11 @@ static int ensure_workspace(bj_ctx* c, long n_walkers) {
     cudaFree(c->d_coef); c->d_coef = nullptr;
     cudaFree(c->d_partial); c->d_partial = nullptr;
     cudaFree(c->d_logl); c->d_logl = nullptr;
+    cudaFree(c->d_coef_ex); c->d_coef_ex = nullptr;
     c->cap_walkers = 0;
     CUDA_TRY(cudaMalloc(&c->d_coef, (size_t)C_NUM * cap * sizeof(double)));
+    if (c->dims.nspcal > 0 || c->dims.nweights > 0)
+        CUDA_TRY(cudaMalloc(&c->d_coef_ex, (size_t)ex_num_slots(c->dims, c->cfg.n_ifo) * cap * sizeof(double)));
     size_t part = 0;
     if (c->kind == KIND_FULLGRID) part = (size_t)c->n_chunks * 2 * c->cfg.n_ifo * cap;
     if (part) CUDA_TRY(cudaMalloc(&c->d_partial, part * sizeof(double)));
@@ -439,46 +603,52 @@ static void note_launch(bj_ctx* c, dim3 grid, size_t smem, int rec8, int model) 
     c->launch_info[7] = model;
 }
 
-template <int NIFO, int MODEL>
+template <int NIFO, int MODEL, bool SPCAL>
 static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     const size_t smem = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
-    auto kern = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64>;
+    auto kern = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, SPCAL>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
-    kern<<<grid, kThreads, smem, st>>>((const double*)c->d_rec, c->n_bins_kernel, c->bins_per_chunk, c->d_coef,
-                                       c->cap_walkers, n_walkers, c->d_partial);
+    kern<<<grid, kThreads, smem, st>>>((const double*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
+                                       c->d_partial, c->d_coef_ex, c->dims, c->d_spcal_freqs);
     CUDA_TRY(cudaGetLastError());
     note_launch(c, grid, smem, RS, MODEL);
     return BJ_OK;
 }
 
-template <int NIFO, int MODEL, int SC>
+template <int NIFO, int MODEL, int SC, bool SPCAL>
 static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st) {
     constexpr int RB = RecM<NIFO>::kBytes;
     const size_t smem = (size_t)kStages * kTileBins * RB + kStages * sizeof(uint64_t);
-    auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC, false>;
-    auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true>;
+    auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC, false, SPCAL>;
+    auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true, SPCAL>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
-    kern<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->n_bins_kernel, c->bins_per_chunk, c->d_coef,
-                                       c->cap_walkers, n_walkers, c->d_partial);
+    kern<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
+                                       c->d_partial, c->d_coef_ex, c->dims);
     // wide-phase fix-up: every CTA returns immediately unless the prologue flagged one of its walkers
-    fixup<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->n_bins_kernel, c->bins_per_chunk, c->d_coef,
-                                        c->cap_walkers, n_walkers, c->d_partial);
+    fixup<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers,
+                                        n_walkers, c->d_partial, c->d_coef_ex, c->dims);
     CUDA_TRY(cudaGetLastError());
     note_launch(c, grid, smem, RB / 8, MODEL);
     return BJ_OK;
 }
 
+template <int NIFO, int MODEL, bool SPCAL>
+static int launch_fullgrid_s(bj_ctx* c, long n_walkers, cudaStream_t st) {
+    switch (c->sincos) {
+        case BJ_SINCOS_MUFU: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_MUFU, SPCAL>(c, n_walkers, st);
+        case BJ_SINCOS_POLY32: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_POLY32, SPCAL>(c, n_walkers, st);
+        default: return launch_fullgrid_fp64<NIFO, MODEL, SPCAL>(c, n_walkers, st);
+    }
+}
+
 template <int NIFO, int MODEL>
 static int launch_fullgrid_m(bj_ctx* c, long n_walkers, cudaStream_t st) {
-    switch (c->sincos) {
-        case BJ_SINCOS_MUFU: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_MUFU>(c, n_walkers, st);
-        case BJ_SINCOS_POLY32: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_POLY32>(c, n_walkers, st);
-        default: return launch_fullgrid_fp64<NIFO, MODEL>(c, n_walkers, st);
-    }
+    if (c->dims.nspcal > 0) return launch_fullgrid_s<NIFO, MODEL, true>(c, n_walkers, st);
+    return launch_fullgrid_s<NIFO, MODEL, false>(c, n_walkers, st);
 }
 
 template <int NIFO>
@@ -487,9 +657,28 @@ static int launch_fullgrid_n(bj_ctx* c, long n_walkers, cudaStream_t st) {
     return launch_fullgrid_m<NIFO, MODEL_GENERIC>(c, n_walkers, st);
 }
 
+static int check_extra_map(const bj_ctx* c, const bj_extra_map* em, int ndim) {
+    const bool need = c->dims.nspcal > 0 || c->dims.nweights > 0;
+    if (need && !em)
+        return fail(BJ_ERR_INVALID, "this context was created with calibration envelopes / PSD weights: use the _ex entry");
+    if (!need) return BJ_OK;
+    if (c->kind != KIND_FULLGRID) return fail(BJ_ERR_UNSUPPORTED, "extras are only defined for the full-grid likelihood");
+    auto bad = [&](int col) { return col >= ndim || col < BJ_COL_CONST; };
+    for (int i = 0; i < c->cfg.n_ifo; ++i) {
+        for (int j = 0; j < c->dims.nspcal; ++j)
+            if (bad(em->spcal_amp_col[i][j]) || bad(em->spcal_phi_col[i][j]))
+                return fail(BJ_ERR_INVALID, "calibration node %d of detector %d is not mapped", j, i);
+        for (int b = 0; b < c->dims.nweights; ++b)
+            if (bad(em->weight_col[i][b])) return fail(BJ_ERR_INVALID, "PSD weight %d of detector %d is not mapped", b, i);
+    }
+    return BJ_OK;
+}
+
 static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, const bj_param_map* map,
-                      double* out_logl_dev, double* out_parts_dev, cudaStream_t st) {
+                      const bj_extra_map* emap, double* out_logl_dev, double* out_parts_dev, cudaStream_t st) {
     int rc = check_map(map, ndim);
+    if (rc) return rc;
+    rc = check_extra_map(c, emap, ndim);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(c->device));
     rc = ensure_workspace(c, n_walkers);
@@ -500,6 +689,9 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
     const unsigned nblk = (unsigned)((n_walkers + tpb - 1) / tpb);
     CUDA_TRY(cudaEventRecord(c->ev[0], st));
     prologue_kernel<<<nblk, tpb, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
+    if (c->d_coef_ex)
+        prologue_extras_kernel<<<nblk, tpb, 0, st>>>(c->cfg, c->dims, *emap, x_dev, ndim, n_walkers, c->d_coef,
+                                                     c->d_coef_ex, c->cap_walkers);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], st));
     if (c->kind == KIND_FULLGRID) {
@@ -510,8 +702,16 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
         }
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[2], st));
+        EpilogueTables tab;
+        tab.chunks = c->d_chunks;
+        tab.n_chunks = c->n_chunks;
+        tab.n_cells = c->n_cells;
+        tab.cell_band = c->d_cell_band;
+        tab.cell_seg = c->d_cell_seg;
+        tab.gram = c->d_gram;
+        tab.dd_band = c->d_dd_band;
         epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers), kEpiWalkers * kEpiSlices, 0, st>>>(
-            c->cfg, c->d_partial, c->n_chunks, c->d_gram, c->d_coef, c->cap_walkers, n_walkers, out_logl_dev,
+            c->cfg, tab, c->dims, c->d_partial, c->d_coef, c->d_coef_ex, c->cap_walkers, n_walkers, out_logl_dev,
             out_parts_dev);
         CUDA_TRY(cudaGetLastError());
     } else if (c->kind == KIND_ROQ) {
@@ -530,16 +730,22 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
     return BJ_OK;
 }
 
-extern "C" int bj_loglike_device(bj_ctx* c, const double* x_dev, int64_t n_walkers, int32_t ndim,
-                                 const bj_param_map* map, double* out_logl_dev, double* out_parts_dev, void* stream) {
+extern "C" int bj_loglike_device_ex(bj_ctx* c, const double* x_dev, int64_t n_walkers, int32_t ndim,
+                                    const bj_param_map* map, const bj_extra_map* emap, double* out_logl_dev,
+                                    double* out_parts_dev, void* stream) {
     if (!c) return fail(BJ_ERR_INVALID, "null context");
     if (n_walkers == 0) return BJ_OK;
     if (n_walkers < 0 || ndim <= 0 || !x_dev || !out_logl_dev) return fail(BJ_ERR_INVALID, "bad batch arguments");
-    return run_device(c, x_dev, (long)n_walkers, ndim, map, out_logl_dev, out_parts_dev, (cudaStream_t)stream);
+    return run_device(c, x_dev, (long)n_walkers, ndim, map, emap, out_logl_dev, out_parts_dev, (cudaStream_t)stream);
 }
 
-extern "C" int bj_loglike(bj_ctx* c, const double* x_host, int64_t n_walkers, int32_t ndim, const bj_param_map* map,
-                          double* out_logl_host) {
+extern "C" int bj_loglike_device(bj_ctx* c, const double* x_dev, int64_t n_walkers, int32_t ndim,
+                                 const bj_param_map* map, double* out_logl_dev, double* out_parts_dev, void* stream) {
+    return bj_loglike_device_ex(c, x_dev, n_walkers, ndim, map, nullptr, out_logl_dev, out_parts_dev, stream);
+}
+
+extern "C" int bj_loglike_ex(bj_ctx* c, const double* x_host, int64_t n_walkers, int32_t ndim, const bj_param_map* map,
+                             const bj_extra_map* emap, double* out_logl_host) {
     if (!c) return fail(BJ_ERR_INVALID, "null context");
     if (n_walkers == 0) return BJ_OK;
     if (n_walkers < 0 || ndim <= 0 || !x_host || !out_logl_host) return fail(BJ_ERR_INVALID, "bad batch arguments");
@@ -556,12 +762,17 @@ extern "C" int bj_loglike(bj_ctx* c, const double* x_host, int64_t n_walkers, in
     int rc = ensure_workspace(c, (long)n_walkers);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->d_x, x_host, (size_t)need * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    rc = run_device(c, c->d_x, (long)n_walkers, ndim, map, c->d_logl, nullptr, c->stream);
+    rc = run_device(c, c->d_x, (long)n_walkers, ndim, map, emap, c->d_logl, nullptr, c->stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_logl_host, c->d_logl, (size_t)n_walkers * sizeof(double), cudaMemcpyDeviceToHost,
                              c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return BJ_OK;
+}
+
+extern "C" int bj_loglike(bj_ctx* c, const double* x_host, int64_t n_walkers, int32_t ndim, const bj_param_map* map,
+                          double* out_logl_host) {
+    return bj_loglike_ex(c, x_host, n_walkers, ndim, map, nullptr, out_logl_host);
 }
 
 extern "C" int bj_last_kernel_ms(bj_ctx* c, float* ms3) {

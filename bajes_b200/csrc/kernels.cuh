@@ -215,6 +215,20 @@ __global__ void prologue_kernel(DeviceConfig cfg, ParamMapDev pm, const double* 
     for (int j = 0; j < C_NUM; ++j) coef[j * stride + w] = out[j];
 }
 
+// calibration-envelope node values and PSD weights of every walker (contexts created with extras)
+__global__ void prologue_extras_kernel(DeviceConfig cfg, ExtrasDims dims, ExtraMapDev em, const double* __restrict__ x,
+                                       int ndim, long n_walkers, double* __restrict__ coef,
+                                       double* __restrict__ coef_ex, long stride) {
+    const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_walkers) return;
+    if (!walker_extras(cfg, dims, em, x + w * ndim, coef_ex, stride, w)) coef[C_VALID * stride + w] = 0.0;
+}
+
+// per-chunk description: records [start, start + len) of the table, all in one (weight band, calibration segment) cell
+struct ChunkDesc {
+    int start, len, band, seg;
+};
+
 // ---- the fused full-grid kernel -----------------------------------------------------------------
 // One CTA = kThreads walkers (one per thread, coefficients in registers) x one frequency chunk.
 // Per bin and walker: phase (FP64 Horner, + magic constant so that the low word of the double IS the binary
@@ -228,9 +242,15 @@ struct WalkerRegs {
     double a[NA], a10, a12, bq[NBQ], c8, k0m, q[6], q6l, tau[NIFO];
 };
 
-template <int NIFO, int MODEL, int SC, int NB>
+// calibration envelope of the chunk's segment, FP64: cal(f) = c0 + dc * clamp((f - f0) * inv_width, 0, 1)
+template <int NIFO>
+struct Spcal64 {
+    double c0r[NIFO], c0i[NIFO], dcr[NIFO], dci[NIFO], f0, inv_width;
+};
+
+template <int NIFO, int MODEL, int SC, int NB, bool SPCAL>
 __device__ __forceinline__ void process_bins(const double* __restrict__ rec, const WalkerRegs<NIFO, MODEL>& w,
-                                             double (&zr)[NIFO], double (&zi)[NIFO]) {
+                                             const Spcal64<NIFO>& sp, double (&zr)[NIFO], double (&zi)[NIFO]) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     double u[NB], L[NB], w5[NB], f[NB], u2[NB], ph[NB], Q[NB];
     float Qf[NB];
@@ -314,6 +334,14 @@ __device__ __forceinline__ void process_bins(const double* __restrict__ rec, con
             } else {
                 scaled_phasor<SC>(__double2loint(tt), Q[j], Qf[j], cq, sq);
             }
+            if constexpr (SPCAL) {
+                // h *= cal  <=>  (cq - i sq) *= (calr + i cali)      (detector.py:517-519)
+                const double t = fmin(fmax((f[j] - sp.f0) * sp.inv_width, 0.0), 1.0);
+                const double calr = fma(sp.dcr[i], t, sp.c0r[i]), cali = fma(sp.dci[i], t, sp.c0i[i]);
+                const double c2 = cq * calr + sq * cali, s2 = sq * calr - cq * cali;
+                cq = c2;
+                sq = s2;
+            }
             const double2 d = *reinterpret_cast<const double2*>(rec + j * RS + 4 + 2 * i);
             // (dr + i di) * Q (c - i s)
             zr[i] = fma(d.x, cq, zr[i]);
@@ -324,11 +352,13 @@ __device__ __forceinline__ void process_bins(const double* __restrict__ rec, con
     }
 }
 
-template <int NIFO, int MODEL, int SC>
-__global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __restrict__ rec, long n_bins,
-                                                                 int bins_per_chunk, const double* __restrict__ coef,
-                                                                 long stride, long n_walkers,
-                                                                 double* __restrict__ partial) {
+template <int NIFO, int MODEL, int SC, bool SPCAL>
+__global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __restrict__ rec,
+                                                                 const ChunkDesc* __restrict__ chunks,
+                                                                 const double* __restrict__ coef, long stride,
+                                                                 long n_walkers, double* __restrict__ partial,
+                                                                 const double* __restrict__ coef_ex, ExtrasDims dims,
+                                                                 const double* __restrict__ spcal_freqs) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
@@ -356,10 +386,22 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
 #pragma unroll
     for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; }
 
-    const long bin0 = (long)blockIdx.x * bins_per_chunk;
-    long remaining = n_bins - bin0;
-    const int nb_total = remaining < bins_per_chunk ? (int)remaining : bins_per_chunk;
+    const ChunkDesc chunk = chunks[blockIdx.x];
+    const long bin0 = chunk.start;
+    const int nb_total = chunk.len;
     const int n_tiles = (nb_total + kTileBins - 1) / kTileBins;
+    Spcal64<NIFO> sp;
+    if constexpr (SPCAL) {
+        sp.f0 = spcal_freqs[chunk.seg];
+        sp.inv_width = 1.0 / (spcal_freqs[chunk.seg + 1] - sp.f0);
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            sp.c0r[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg, 0) * stride + wl];
+            sp.c0i[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg, 1) * stride + wl];
+            sp.dcr[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 0) * stride + wl] - sp.c0r[i];
+            sp.dci[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 1) * stride + wl] - sp.c0i[i];
+        }
+    }
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -386,8 +428,8 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
         const int nb = min(kTileBins, nb_total - t * kTileBins);
         int b = 0;
 #pragma unroll 1
-        for (; b + 2 <= nb; b += 2) process_bins<NIFO, MODEL, SC, 2>(tile + b * RS, w, zr, zi);
-        if (b < nb) process_bins<NIFO, MODEL, SC, 1>(tile + b * RS, w, zr, zi);
+        for (; b + 2 <= nb; b += 2) process_bins<NIFO, MODEL, SC, 2, SPCAL>(tile + b * RS, w, sp, zr, zi);
+        if (b < nb) process_bins<NIFO, MODEL, SC, 1, SPCAL>(tile + b * RS, w, sp, zr, zi);
         __syncthreads();
         if (threadIdx.x == 0 && t + kStages < n_tiles) {
             fence_proxy_async();
@@ -454,9 +496,15 @@ __device__ __forceinline__ double amp_series_f64(double u, double L, const doubl
     return fma(u * u, t, 1.0);
 }
 
-template <int NIFO, int MODEL, int SC, bool ROBUST>
+// calibration envelope of the chunk's segment, FP32 packed (re, im): cal(t) = c0 + dc * t, t in the record
+template <int NIFO>
+struct Spcal32 {
+    unsigned long long c0[NIFO], dc[NIFO];
+};
+
+template <int NIFO, int MODEL, int SC, bool ROBUST, bool SPCAL>
 __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restrict__ rec,
-                                                   const WalkerRegsM<NIFO, MODEL>& w,
+                                                   const WalkerRegsM<NIFO, MODEL>& w, const Spcal32<NIFO>& sp,
                                                    unsigned long long (&acc)[NIFO]) {
     constexpr int RB = RecM<NIFO>::kBytes;
     double u[2], L[2], w5[2], f[2], u2[2], ph[2];
@@ -469,6 +517,12 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
     }
     const unsigned long long up = *reinterpret_cast<const unsigned long long*>(rec + 32);        // (uf0, uf1)
     const unsigned long long lp = *reinterpret_cast<const unsigned long long*>(rec + RB + 32);   // (Lf0, Lf1)
+    float tcal[2] = {0.0f, 0.0f};
+    if constexpr (SPCAL) {
+        const float2 tt2 = *reinterpret_cast<const float2*>(rec + 40);                           // (t0, t1)
+        tcal[0] = tt2.x;
+        tcal[1] = tt2.y;
+    }
     // ---- phase in turns (+ magic), FP64 ----
     if constexpr (MODEL == MODEL_35) {
         double p[2], bl[2];
@@ -527,6 +581,14 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
             const double tt = fma(f[j], w.tau[i], ph[j]);
             float cq, sq;
             scaled_phasor_f32<SC>(ROBUST ? robust_angle(tt) : __double2loint(tt), Qf[j], cq, sq);
+            if constexpr (SPCAL) {
+                // h *= cal  <=>  (cq - i sq) *= (calr + i cali)      (detector.py:517-519)
+                float calr, cali;
+                unpack2(fma2(sp.dc[i], pack2(tcal[j], tcal[j]), sp.c0[i]), calr, cali);
+                const float c2 = fmaf(sq, cali, cq * calr), s2 = fmaf(-cq, cali, sq * calr);
+                cq = c2;
+                sq = s2;
+            }
             const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(rec + j * RB + 48 + 16 * i);
             // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
             acc[i] = fma2(d.x, pack2(cq, cq), acc[i]);
@@ -539,11 +601,13 @@ __device__ __forceinline__ void process_pair_mixed(const unsigned char* __restri
 // a CTA exits at once unless the prologue flagged one of its walkers as "wide phase" (|turns| may exceed 2^19, the
 // range of the binary-angle trick), otherwise it recomputes the tile with the exact reduction t - rint(t) and
 // overwrites the tile's partial sums.
-template <int NIFO, int MODEL, int SC, bool ROBUST>
+template <int NIFO, int MODEL, int SC, bool ROBUST, bool SPCAL>
 __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(const unsigned char* __restrict__ rec,
-                                                                       long n_bins, int bins_per_chunk,
+                                                                       const ChunkDesc* __restrict__ chunks,
                                                                        const double* __restrict__ coef, long stride,
-                                                                       long n_walkers, double* __restrict__ partial) {
+                                                                       long n_walkers, double* __restrict__ partial,
+                                                                       const double* __restrict__ coef_ex,
+                                                                       ExtrasDims dims) {
     constexpr int RB = RecM<NIFO>::kBytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
@@ -575,11 +639,37 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 #pragma unroll
     for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; acc[i] = 0ull; }
 
-    // n_bins is even by construction (the table is padded with one zero-weight record if needed)
-    const long bin0 = (long)blockIdx.x * bins_per_chunk;
-    long remaining = n_bins - bin0;
-    const int nb_total = remaining < bins_per_chunk ? (int)remaining : bins_per_chunk;
+    // every chunk starts on an even record and holds an even number of records (cells are padded with zero-weight
+    // records), so bins can be consumed in (even, odd) pairs
+    const ChunkDesc chunk = chunks[blockIdx.x];
+    const long bin0 = chunk.start;
+    const int nb_total = chunk.len;
     const int n_tiles = (nb_total + kTileBins - 1) / kTileBins;
+
+    // calibration envelope of this chunk's segment: FP32 node value + slope per detector, and the exact/rounded
+    // ratio at the chunk's first bin (noise-free, both sides in FP64) that rides on the flush
+    Spcal32<NIFO> sp;
+    double ccr[NIFO], cci[NIFO];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) { ccr[i] = 1.0; cci[i] = 0.0; sp.c0[i] = 0ull; sp.dc[i] = 0ull; }
+    if constexpr (SPCAL) {
+        const double t0 = (double)*reinterpret_cast<const float*>(rec + bin0 * RB + 40);
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            const double c0r = coef_ex[ex_cal_slot(dims, i, chunk.seg, 0) * stride + wl];
+            const double c0i = coef_ex[ex_cal_slot(dims, i, chunk.seg, 1) * stride + wl];
+            const double dr = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 0) * stride + wl] - c0r;
+            const double di = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 1) * stride + wl] - c0i;
+            const float c0rf = (float)c0r, c0if = (float)c0i, drf = (float)dr, dif = (float)di;
+            sp.c0[i] = pack2(c0rf, c0if);
+            sp.dc[i] = pack2(drf, dif);
+            const double er = fma(dr, t0, c0r), ei = fma(di, t0, c0i);                       // exact
+            const double rr = fma((double)drf, t0, (double)c0rf), ri = fma((double)dif, t0, (double)c0if);
+            const double den = rr * rr + ri * ri;
+            ccr[i] = (er * rr + ei * ri) / den;                                               // exact / rounded
+            cci[i] = (ei * rr - er * ri) / den;
+        }
+    }
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -609,8 +699,14 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
         for (int i = 0; i < NIFO; ++i) {
             float re, im;
             unpack2(acc[i], re, im);
-            zr[i] = fma((double)re, corr, zr[i]);
-            zi[i] = fma((double)im, corr, zi[i]);
+            if constexpr (SPCAL) {
+                const double fr = corr * ccr[i], fi = corr * cci[i];
+                zr[i] = fma((double)re, fr, fma(-(double)im, fi, zr[i]));
+                zi[i] = fma((double)re, fi, fma((double)im, fr, zi[i]));
+            } else {
+                zr[i] = fma((double)re, corr, zr[i]);
+                zi[i] = fma((double)im, corr, zi[i]);
+            }
             acc[i] = 0ull;
         }
     };
@@ -639,13 +735,13 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
         for (int blk = 0; blk < n_blocks; ++blk) {
             const unsigned char* base = tile + (size_t)blk * kBlockBins * RB;
 #pragma unroll (ROBUST ? 1 : kPairUnroll)
-            for (int b = 0; b < kBlockBins; b += 2) process_pair_mixed<NIFO, MODEL, SC, ROBUST>(base + b * RB, w, acc);
+            for (int b = 0; b < kBlockBins; b += 2) process_pair_mixed<NIFO, MODEL, SC, ROBUST, SPCAL>(base + b * RB, w, sp, acc);
             flush();
         }
         {
             const int done = n_blocks * kBlockBins;
 #pragma unroll 1
-            for (int b = done; b + 2 <= nb; b += 2) process_pair_mixed<NIFO, MODEL, SC, ROBUST>(tile + (size_t)b * RB, w, acc);
+            for (int b = done; b + 2 <= nb; b += 2) process_pair_mixed<NIFO, MODEL, SC, ROBUST, SPCAL>(tile + (size_t)b * RB, w, sp, acc);
             if (done < nb) flush();
         }
         __syncthreads();
@@ -684,24 +780,43 @@ __device__ inline double log_bessel_i0(double x) {
 // sums[W][n_ifo][3] (optional) receives Re<d|h>, Im<d|h>, <h|h> per detector.
 constexpr int kEpiWalkers = 32;   // walkers per epilogue CTA
 constexpr int kEpiSlices = 8;     // chunk slices summed in parallel, then combined in fixed order
+// Static tables of the epilogue.  Cells = runs of bins with constant (PSD-weight band, calibration segment); without
+// extras there is ONE cell.  gram[det][cell][3][kGram]: Gram moments of <h|h> weighted by (1-t)^2, t(1-t), t^2 (the
+// piecewise-linear |cal|^2); without calibration only the first set is non-zero and carries weight 1.
+struct EpilogueTables {
+    const ChunkDesc* chunks;
+    int n_chunks;
+    int n_cells;
+    const int* cell_band;
+    const int* cell_seg;
+    const double* gram;       // [n_ifo][n_cells][3][kGram]
+    const double* dd_band;    // [n_ifo][nweights]  (4/T) sum_{k in band} |d|^2 / S
+};
+
 __global__ void __launch_bounds__(kEpiWalkers * kEpiSlices)
-epilogue_kernel(DeviceConfig cfg, const double* __restrict__ partial, int n_chunks,
-                const double* __restrict__ gram, const double* __restrict__ coef, long stride,
-                long n_walkers, double* __restrict__ logl, double* __restrict__ sums) {
+epilogue_kernel(DeviceConfig cfg, EpilogueTables tab, ExtrasDims dims, const double* __restrict__ partial,
+                const double* __restrict__ coef, const double* __restrict__ coef_ex, long stride, long n_walkers,
+                double* __restrict__ logl, double* __restrict__ sums) {
     __shared__ double red[kEpiSlices][2 * BJ_MAX_IFO][kEpiWalkers];
     const int lane_w = threadIdx.x % kEpiWalkers, slice = threadIdx.x / kEpiWalkers;
     const long w = (long)blockIdx.x * kEpiWalkers + lane_w;
     const long wc = w < n_walkers ? w : n_walkers - 1;
-    // stage 1: slice s adds chunks s, s + kEpiSlices, ... in ascending order (fixed tree: bits do not depend on W)
-    for (int j = 0; j < 2 * cfg.n_ifo; ++j) {
+    const int nifo = cfg.n_ifo;
+    // stage 1: slice s adds chunks s, s + kEpiSlices, ... in ascending order (fixed tree: bits do not depend on W);
+    // with PSD weights every chunk lies in one band and is scaled by 1 / w_band (detector.py:529)
+    for (int j = 0; j < 2 * nifo; ++j) {
         double acc = 0.0;
-        for (int ch = slice; ch < n_chunks; ch += kEpiSlices)
-            acc += partial[((size_t)ch * (2 * cfg.n_ifo) + j) * stride + wc];
+        for (int ch = slice; ch < tab.n_chunks; ch += kEpiSlices) {
+            double v = partial[((size_t)ch * (2 * nifo) + j) * stride + wc];
+            if (dims.nweights > 0)
+                v *= coef_ex[ex_invw_slot(dims, nifo, j >> 1, tab.chunks[ch].band) * stride + wc];
+            acc += v;
+        }
         red[slice][j][lane_w] = acc;
     }
     __syncthreads();
     if (slice != 0 || w >= n_walkers) return;
-    const int nifo = cfg.n_ifo;
+
     const double amp = coef[C_AMP * stride + w];
     const bool valid = coef[C_VALID * stride + w] != 0.0;
     // amplitude-series coefficients in the basis phi = {1, u^2, ..., u^7, L u^6}
@@ -710,7 +825,7 @@ epilogue_kernel(DeviceConfig cfg, const double* __restrict__ partial, int n_chun
 #pragma unroll
     for (int j = 0; j < 6; ++j) g[1 + j] = coef[(C_Q2 + j) * stride + w];
     g[7] = coef[C_Q6L * stride + w];
-    double dh_re = 0.0, dh_im = 0.0, hh_tot = 0.0;
+    double dh_re = 0.0, dh_im = 0.0, hh_tot = 0.0, dd_tot = 0.0;
     for (int i = 0; i < nifo; ++i) {
         double zr = 0.0, zi = 0.0;
 #pragma unroll
@@ -718,13 +833,40 @@ epilogue_kernel(DeviceConfig cfg, const double* __restrict__ partial, int n_chun
             zr += red[sl][2 * i][lane_w];
             zi += red[sl][2 * i + 1][lane_w];
         }
+        // <h|h>_i: quadratic form of the Gram moments, per cell scaled by 1/w_band and |cal|^2 of its segment
         double h = 0.0;
-        const double* G = gram + i * kGram;
-        int idx = 0;
-        for (int m = 0; m < kBasis; ++m) {
-            double row = 0.0;
-            for (int n = m; n < kBasis; ++n, ++idx) row = fma((n == m ? 1.0 : 2.0) * g[n], G[idx], row);
-            h = fma(g[m], row, h);
+        for (int cell = 0; cell < tab.n_cells; ++cell) {
+            double a3[3] = {1.0, 0.0, 0.0};
+            int nset = 1;
+            if (dims.nspcal > 0) {
+                const int sg = tab.cell_seg[cell];
+                const double c0r = coef_ex[ex_cal_slot(dims, i, sg, 0) * stride + w];
+                const double c0i = coef_ex[ex_cal_slot(dims, i, sg, 1) * stride + w];
+                const double c1r = coef_ex[ex_cal_slot(dims, i, sg + 1, 0) * stride + w];
+                const double c1i = coef_ex[ex_cal_slot(dims, i, sg + 1, 1) * stride + w];
+                a3[0] = c0r * c0r + c0i * c0i;                  // |(1-t) c0 + t c1|^2
+                a3[1] = 2.0 * (c0r * c1r + c0i * c1i);
+                a3[2] = c1r * c1r + c1i * c1i;
+                nset = 3;
+            }
+            double hc = 0.0;
+            for (int st = 0; st < nset; ++st) {
+                const double* G = tab.gram + (((size_t)i * tab.n_cells + cell) * 3 + st) * kGram;
+                double q = 0.0;
+                int idx = 0;
+                for (int m = 0; m < kBasis; ++m) {
+                    double row = 0.0;
+                    for (int n = m; n < kBasis; ++n, ++idx) row = fma((n == m ? 1.0 : 2.0) * g[n], G[idx], row);
+                    q = fma(g[m], row, q);
+                }
+                hc = fma(a3[st], q, hc);
+            }
+            if (dims.nweights > 0) hc *= coef_ex[ex_invw_slot(dims, nifo, i, tab.cell_band[cell]) * stride + w];
+            h += hc;
+        }
+        if (dims.nweights > 0) {
+            for (int b = 0; b < dims.nweights; ++b)
+                dd_tot += tab.dd_band[i * dims.nweights + b] * coef_ex[ex_invw_slot(dims, nifo, i, b) * stride + w];
         }
         const double cr = coef[(C_CR0 + i) * stride + w];
         const double ci = coef[(C_CI0 + i) * stride + w];
@@ -746,8 +888,10 @@ epilogue_kernel(DeviceConfig cfg, const double* __restrict__ partial, int n_chun
     double R;
     if (cfg.marg_phi_ref) R = log_bessel_i0(hypot(dh_re, dh_im));
     else                  R = dh_re;
-    // log_like.py:181 with _psd_fact = 0
-    double v = -0.5 * (hh_tot + cfg.dd_sum) + R - cfg.logZ_noise;
+    // log_like.py:181:  -1/2 (hh + dd) + R - logZ_noise - 1/2 _psd_fact
+    const double dd = dims.nweights > 0 ? dd_tot : cfg.dd_sum;
+    const double pf = dims.nweights > 0 ? coef_ex[ex_psdfact_slot(dims, nifo) * stride + w] : 0.0;
+    double v = -0.5 * (hh_tot + dd) + R - cfg.logZ_noise - 0.5 * pf;
     if (!valid) v = -INFINITY;
     logl[w] = v;
 }

@@ -61,6 +61,57 @@ struct ParamMapDev {
     double value[BJ_NUM_PARAMS];
 };
 
+// calibration envelopes / PSD weights (detector.py:17-23,517-531): static dimensions + per-call parameter map
+struct ExtrasDims {
+    int nspcal;                        // 0 = off
+    int nweights;                      // 0 = off
+    int len_weights[BJ_MAX_WEIGHTS];   // bins per band
+};
+typedef bj_extra_map ExtraMapDev;
+
+// extras coefficient block (SoA, coef_ex[slot * stride + walker]):
+//   [(i * nspcal + j) * 2 + {0,1}]                      Re / Im of (1 + amp_j) exp(i phi_j), detector i, node j
+//   [2 n_ifo nspcal + i * nweights + b]                 1 / w_b of detector i
+//   [2 n_ifo nspcal + n_ifo nweights]                   sum_i sum_b len_b log w_b   ("_psd_fact", log_like.py:181)
+__host__ __device__ inline int ex_cal_slot(const ExtrasDims& d, int i, int j, int c) { return (i * d.nspcal + j) * 2 + c; }
+__host__ __device__ inline int ex_invw_slot(const ExtrasDims& d, int n_ifo, int i, int b) {
+    return 2 * n_ifo * d.nspcal + i * d.nweights + b;
+}
+__host__ __device__ inline int ex_psdfact_slot(const ExtrasDims& d, int n_ifo) {
+    return 2 * n_ifo * d.nspcal + n_ifo * d.nweights;
+}
+__host__ __device__ inline int ex_num_slots(const ExtrasDims& d, int n_ifo) { return ex_psdfact_slot(d, n_ifo) + 1; }
+
+// returns false when a weight is not positive (log w is NaN in the reference)
+__device__ inline bool walker_extras(const DeviceConfig& cfg, const ExtrasDims& d, const ExtraMapDev& em,
+                                     const double* __restrict__ x, double* __restrict__ coef_ex, long stride, long w) {
+    bool ok = true;
+    for (int i = 0; i < cfg.n_ifo; ++i) {
+        for (int j = 0; j < d.nspcal; ++j) {
+            const int ca = em.spcal_amp_col[i][j], cp = em.spcal_phi_col[i][j];
+            const double amp = ca >= 0 ? x[ca] : em.spcal_amp_val[i][j];
+            const double phi = cp >= 0 ? x[cp] : em.spcal_phi_val[i][j];
+            double sn, cs;
+            sincos(phi, &sn, &cs);
+            coef_ex[ex_cal_slot(d, i, j, 0) * stride + w] = (1.0 + amp) * cs;     // detector.py:17-20
+            coef_ex[ex_cal_slot(d, i, j, 1) * stride + w] = (1.0 + amp) * sn;
+            ok = ok && isfinite(amp) && isfinite(phi);
+        }
+    }
+    double fact = 0.0;
+    for (int i = 0; i < cfg.n_ifo; ++i) {
+        for (int b = 0; b < d.nweights; ++b) {
+            const int cw = em.weight_col[i][b];
+            const double wt = cw >= 0 ? x[cw] : em.weight_val[i][b];
+            coef_ex[ex_invw_slot(d, cfg.n_ifo, i, b) * stride + w] = 1.0 / wt;
+            fact += (double)d.len_weights[b] * log(wt);                            // detector.py:528
+            ok = ok && (wt > 0.0) && isfinite(wt);
+        }
+    }
+    coef_ex[ex_psdfact_slot(d, cfg.n_ifo) * stride + w] = fact;
+    return ok;
+}
+
 __device__ __forceinline__ bool has(const ParamMapDev& m, int slot) { return m.column[slot] != BJ_COL_ABSENT; }
 __device__ __forceinline__ double get(const ParamMapDev& m, const double* __restrict__ x, int slot) {
     int c = m.column[slot];

@@ -146,9 +146,6 @@ class Detector(object):
     # ---- measurement storage (set-up; detector.py:452-493) -------------------------------------------
     def store_measurement(self, series, noise, nspcal=0, spcal_freqs=None, nweights=0, len_weights=None):
         assert self.reference_time == series.t_gps
-        if nspcal or nweights:
-            raise NotImplementedError("spectral calibration envelopes / PSD weights are not in the fused GPU "
-                                      "likelihood yet (SURVEY.md section 8f N3); there is no CPU fallback")
         self.srate = series.srate
         self.seglen = series.seglen
         self._mask = series.mask

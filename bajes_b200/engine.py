@@ -15,6 +15,8 @@ import numpy as np
 
 BJ_ABI_VERSION = 1
 BJ_MAX_IFO = 3
+BJ_MAX_SPCAL = 16
+BJ_MAX_WEIGHTS = 16
 BJ_COL_CONST = -1
 BJ_COL_ABSENT = -2
 
@@ -67,6 +69,20 @@ class bj_config(C.Structure):
                 ("det", bj_detector * BJ_MAX_IFO)]
 
 
+class bj_extras(C.Structure):
+    _fields_ = [("nspcal", C.c_int32), ("nweights", C.c_int32),
+                ("spcal_freqs", C.POINTER(C.c_double)), ("len_weights", C.POINTER(C.c_int64))]
+
+
+class bj_extra_map(C.Structure):
+    _fields_ = [("spcal_amp_col", (C.c_int32 * BJ_MAX_SPCAL) * BJ_MAX_IFO),
+                ("spcal_phi_col", (C.c_int32 * BJ_MAX_SPCAL) * BJ_MAX_IFO),
+                ("weight_col", (C.c_int32 * BJ_MAX_WEIGHTS) * BJ_MAX_IFO),
+                ("spcal_amp_val", (C.c_double * BJ_MAX_SPCAL) * BJ_MAX_IFO),
+                ("spcal_phi_val", (C.c_double * BJ_MAX_SPCAL) * BJ_MAX_IFO),
+                ("weight_val", (C.c_double * BJ_MAX_WEIGHTS) * BJ_MAX_IFO)]
+
+
 class bj_roq_tables(C.Structure):
     _fields_ = [("n_join", C.c_int64), ("freqs_join", C.POINTER(C.c_double)),
                 ("n_lin", C.c_int64), ("mask_omega", C.POINTER(C.c_int32)),
@@ -88,7 +104,13 @@ EXPORTS = {
     "bj_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bj_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(bj_config), C.c_int64, _DP, _DPP, _DPP]),
+    "bj_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(bj_config), C.c_int64, _DP, _DPP, _DPP,
+                               C.POINTER(bj_extras)]),
     "bj_destroy": (C.c_int, [C.c_void_p]),
+    "bj_loglike_ex": (C.c_int, [C.c_void_p, _DP, C.c_int64, C.c_int32, C.POINTER(bj_param_map),
+                                C.POINTER(bj_extra_map), _DP]),
+    "bj_loglike_device_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(bj_param_map),
+                                       C.POINTER(bj_extra_map), C.c_void_p, C.c_void_p, C.c_void_p]),
     "bj_loglike": (C.c_int, [C.c_void_p, _DP, C.c_int64, C.c_int32, C.POINTER(bj_param_map), _DP]),
     "bj_loglike_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(bj_param_map),
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -177,17 +199,45 @@ class ParamMap:
     """names -> columns of the batch array, plus constants (replaces Prior.this_sample +
     the dict parsing in Waveform.compute_hphc; bajes/inf/prior.py:262-269, waveform.py:334-377)."""
 
-    UNSUPPORTED_PREFIXES = ("spcal_", "weight", "eos_")
+    UNSUPPORTED_PREFIXES = ("eos_",)
+    EXTRA_PREFIXES = ("spcal_amp", "spcal_phi", "weight")
 
-    def __init__(self, names: Sequence[str], const: Optional[Dict[str, float]] = None):
+    def __init__(self, names: Sequence[str], const: Optional[Dict[str, float]] = None, ifos: Sequence[str] = (),
+                 nspcal: int = 0, nweights: int = 0):
+        """``ifos`` / ``nspcal`` / ``nweights``: when the likelihood was built with calibration envelopes or PSD
+        weights, the parameters 'spcal_amp{j}_{ifo}', 'spcal_phi{j}_{ifo}', 'weight{b}_{ifo}'
+        (bajes/obs/gw/detector.py:17-23) are looked up among the sampled names, then the constants."""
         const = dict(const or {})
         self.names = list(names)
         self.ndim = len(self.names)
         for n in list(self.names) + list(const):
-            if n.startswith(self.UNSUPPORTED_PREFIXES) and n != "weights":
+            if n.startswith(self.UNSUPPORTED_PREFIXES):
                 raise NotImplementedError(
-                    "parameter '%s' (calibration envelopes / PSD weights / EOS sampling) is outside the "
-                    "fused GPU likelihood; there is no CPU fallback" % n)
+                    "parameter '%s' (EOS sampling) is outside the fused GPU likelihood; there is no CPU fallback" % n)
+            if n.startswith(self.EXTRA_PREFIXES) and n != "weights" and not (nspcal or nweights):
+                raise NotImplementedError(
+                    "parameter '%s' given but the likelihood was built without calibration envelopes / PSD weights "
+                    "(nspcal = nweights = 0)" % n)
+        self.extra = None
+        if nspcal or nweights:
+            self.extra = bj_extra_map()
+            col = {n: i for i, n in enumerate(self.names)}
+
+            def place(cols, vals, i, j, key):
+                if key in col:
+                    cols[i][j] = col[key]
+                elif key in const:
+                    cols[i][j] = BJ_COL_CONST
+                    vals[i][j] = float(const[key])
+                else:
+                    raise KeyError("parameter '%s' is neither sampled nor constant" % key)
+
+            for i, ifo in enumerate(ifos):
+                for j in range(nspcal):
+                    place(self.extra.spcal_amp_col, self.extra.spcal_amp_val, i, j, "spcal_amp{}_{}".format(j, ifo))
+                    place(self.extra.spcal_phi_col, self.extra.spcal_phi_val, i, j, "spcal_phi{}_{}".format(j, ifo))
+                for b in range(nweights):
+                    place(self.extra.weight_col, self.extra.weight_val, i, b, "weight{}_{}".format(b, ifo))
         self.c = bj_param_map()
         for i in range(BJ_NUM_PARAMS):
             self.c.column[i] = BJ_COL_ABSENT
@@ -199,13 +249,15 @@ class ParamMap:
         for col, n in enumerate(self.names):
             if n in SLOT_INDEX:
                 self.c.column[SLOT_INDEX[n]] = col
-        self.ignored = [n for n in self.names if n not in SLOT_INDEX]
+        self.ignored = [n for n in self.names if n not in SLOT_INDEX and not n.startswith(self.EXTRA_PREFIXES)]
 
     @classmethod
-    def from_dict(cls, params: Dict[str, float]):
+    def from_dict(cls, params: Dict[str, float], ifos: Sequence[str] = (), nspcal: int = 0, nweights: int = 0):
         """Map for a single parameter dict (GWLikelihood.log_like(params))."""
         names = [n for n in PARAM_SLOTS if n in params]
-        m = cls(names, {})
+        if nspcal or nweights:
+            names += [n for n in params if n.startswith(cls.EXTRA_PREFIXES) and n != "weights"]
+        m = cls(names, {}, ifos=ifos, nspcal=nspcal, nweights=nweights)
         x = np.array([float(params[n]) for n in names], dtype=np.float64)
         return m, x
 
@@ -253,7 +305,7 @@ class Engine:
 
     # -- constructors --------------------------------------------------------------------------
     @classmethod
-    def fullgrid(cls, cfg: bj_config, freqs, datas, psds) -> "Engine":
+    def fullgrid(cls, cfg: bj_config, freqs, datas, psds, spcal_freqs=None, len_weights=None) -> "Engine":
         lib = load_library()
         freqs = _as_f64(freqs)
         d_ri = [np.ascontiguousarray(np.asarray(d, dtype=np.complex128)).view(np.float64) for d in datas]
@@ -263,8 +315,17 @@ class Engine:
         for a in p:
             assert a.size == freqs.size
         h = C.c_void_p()
-        _check(lib, lib.bj_create(C.byref(h), C.byref(cfg), freqs.size, _ptr(freqs), _ptr_array(d_ri), _ptr_array(p)),
-               "bj_create")
+        ex = bj_extras()
+        sf = lw = None
+        if spcal_freqs is not None and len(spcal_freqs) > 0:
+            sf = _as_f64(spcal_freqs)
+            ex.nspcal, ex.spcal_freqs = sf.size, _ptr(sf)
+        if len_weights is not None and len(len_weights) > 0:
+            lw = np.ascontiguousarray(len_weights, dtype=np.int64)
+            ex.nweights, ex.len_weights = lw.size, lw.ctypes.data_as(C.POINTER(C.c_int64))
+        _check(lib, lib.bj_create_ex(C.byref(h), C.byref(cfg), freqs.size, _ptr(freqs), _ptr_array(d_ri), _ptr_array(p),
+                                     C.byref(ex) if (sf is not None or lw is not None) else None),
+               "bj_create_ex")
         return cls(h, cfg.n_ifo, "fullgrid", freqs.size)
 
     @classmethod
@@ -311,17 +372,20 @@ class Engine:
         out = np.empty(x.shape[0], dtype=np.float64)
         if x.shape[0] == 0:
             return out
-        _check(self._lib, self._lib.bj_loglike(self._h, _ptr(x), x.shape[0], x.shape[1], C.byref(pmap.c), _ptr(out)),
+        ex = C.byref(pmap.extra) if pmap.extra is not None else None
+        _check(self._lib, self._lib.bj_loglike_ex(self._h, _ptr(x), x.shape[0], x.shape[1], C.byref(pmap.c), ex,
+                                                  _ptr(out)),
                "bj_loglike")
         return out
 
     def loglike_device(self, x_ptr: int, n_walkers: int, ndim: int, pmap: ParamMap, out_ptr: int,
                        parts_ptr: int = 0, stream: int = 0) -> None:
         """Device pointers (ints), asynchronous on ``stream`` (a cudaStream_t handle as int)."""
+        ex = C.byref(pmap.extra) if pmap.extra is not None else None
         _check(self._lib,
-               self._lib.bj_loglike_device(self._h, C.c_void_p(x_ptr), n_walkers, ndim, C.byref(pmap.c),
-                                           C.c_void_p(out_ptr), C.c_void_p(parts_ptr or None),
-                                           C.c_void_p(stream or None)),
+               self._lib.bj_loglike_device_ex(self._h, C.c_void_p(x_ptr), n_walkers, ndim, C.byref(pmap.c), ex,
+                                              C.c_void_p(out_ptr), C.c_void_p(parts_ptr or None),
+                                              C.c_void_p(stream or None)),
                "bj_loglike_device")
 
     def project_waveform(self, x: np.ndarray, pmap: ParamMap) -> np.ndarray:

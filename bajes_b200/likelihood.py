@@ -65,9 +65,14 @@ class GWLikelihood(Likelihood):
         if self.marg_time_shift:
             raise NotImplementedError("time-shift marginalisation needs the per-bin <d|h> array + FFT per point and "
                                       "is not part of the fused GPU likelihood (SURVEY.md section 8e/f N4)")
-        if nspcal or nweights:
-            raise NotImplementedError("spectral calibration envelopes / PSD weights are not in the fused GPU "
-                                      "likelihood yet (SURVEY.md section 8f N3); there is no CPU fallback")
+        if (nspcal or nweights) and roq is not None:
+            raise AttributeError("The ROQ approximation has not yet been extended to incorporate calibration "
+                                 "uncertainties.")          # bajes/pipe/__init__.py:737-739
+        if nspcal > _engine.BJ_MAX_SPCAL or nweights > _engine.BJ_MAX_WEIGHTS:
+            raise NotImplementedError("at most %d calibration nodes / %d PSD-weight bands"
+                                      % (_engine.BJ_MAX_SPCAL, _engine.BJ_MAX_WEIGHTS))
+        self.spcal_freqs = None if not nspcal else np.asarray(spcal_freqs, dtype=float)
+        self.len_weights = None if not nweights else np.asarray(len_weights, dtype=np.int64)
         if len(self.ifos) > _engine.BJ_MAX_IFO:
             raise NotImplementedError("more than %d detectors in one fused pass" % _engine.BJ_MAX_IFO)
 
@@ -119,7 +124,8 @@ class GWLikelihood(Likelihood):
             d0 = self.dets[self.ifos[0]]
             self._engine = _engine.Engine.fullgrid(cfg, d0.freqs,
                                                    [self.dets[i].data for i in self.ifos],
-                                                   [self.dets[i].psd for i in self.ifos])
+                                                   [self.dets[i].psd for i in self.ifos],
+                                                   spcal_freqs=self.spcal_freqs, len_weights=self.len_weights)
         else:
             from .roq import spline_tables
             knots, coefs, tc_min, tc_max = [], [], None, None
@@ -151,7 +157,11 @@ class GWLikelihood(Likelihood):
 
     # ---- evaluation -------------------------------------------------------------------------------
     def param_map(self, names: Sequence[str], const: Optional[Dict[str, float]] = None) -> _engine.ParamMap:
-        return _engine.ParamMap(names, const)
+        return _engine.ParamMap(names, const, ifos=self.ifos, nspcal=self.nspcal, nweights=self.nweights)
+
+    def _point_map(self, params):
+        return _engine.ParamMap.from_dict(_physical_subset(params), ifos=self.ifos, nspcal=self.nspcal,
+                                          nweights=self.nweights)
 
     def log_like_batch(self, X, names: Sequence[str], const: Optional[Dict[str, float]] = None) -> np.ndarray:
         """``[log_like({**dict(zip(names, x)), **const}) for x in X]`` in one GPU call.
@@ -163,15 +173,13 @@ class GWLikelihood(Likelihood):
 
     def log_like(self, params):
         """Reference per-point contract (log_like.py:107-183): dict -> float."""
-        sub = _physical_subset(params)
-        pmap, x = _engine.ParamMap.from_dict(sub)
+        pmap, x = self._point_map(params)
         return float(self.engine.loglike(x.reshape(1, -1), pmap)[0])
 
     def _parts(self, params):
         """per-detector Re<d|h>, Im<d|h>, <h|h> of one point via the device entry."""
         import torch
-        sub = _physical_subset(params)
-        pmap, x = _engine.ParamMap.from_dict(sub)
+        pmap, x = self._point_map(params)
         dev = torch.device("cuda", self.device)
         xd = torch.from_numpy(x.reshape(1, -1)).to(dev)
         out = torch.empty(1, dtype=torch.float64, device=dev)
@@ -201,9 +209,10 @@ def _physical_subset(params):
     dict already carries the derived entries compute_hphc adds (mtot from mchirp, iota from cos_iota,
     cartesian from spherical spins) the primary ones win, as in waveform.py:334-377."""
     for k in params:
-        if k.startswith(_engine.ParamMap.UNSUPPORTED_PREFIXES) and k != "weights":
+        if k.startswith(_engine.ParamMap.UNSUPPORTED_PREFIXES):
             raise NotImplementedError("parameter '%s' is outside the fused GPU likelihood; no CPU fallback" % k)
-    sub = {k: v for k, v in params.items() if k in _engine.SLOT_INDEX}
+    sub = {k: v for k, v in params.items()
+           if k in _engine.SLOT_INDEX or (k.startswith(_engine.ParamMap.EXTRA_PREFIXES) and k != "weights")}
     if "mchirp" in sub:
         sub.pop("mtot", None)
     if "cos_iota" in sub:

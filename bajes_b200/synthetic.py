@@ -191,3 +191,35 @@ def write_jenpyroq(path, basis, cfg):
     np.save(os.path.join(path, "ROQ_data/quadratic/basis_interpolant_quadratic.npy"), basis["quad_b"])
     with open(os.path.join(path, "ROQ_data/ROQ_metadata.txt"), "w") as fh:
         fh.write("# fmin fmax seglen\n%.17g %.17g %.17g\n" % (cfg["f_min"], cfg["f_max"], cfg["seglen"]))
+
+
+
+def extras_setup(cfg, nspcal=0, nweights=0):
+    """spcal node frequencies and PSD-weight band lengths exactly as bajes builds them
+    (bajes/pipe/gw_init.py:690-703,729): log-spaced between the first and last in-band frequency."""
+    f = frequency_axis(cfg)
+    fb = f[(f >= cfg["f_min"]) & (f <= cfg["f_max"])]
+    out = dict(nspcal=nspcal, spcal_freqs=None, nweights=nweights, len_weights=None)
+    if nweights:
+        f_cut = np.logspace(1.0, np.log(np.max(fb)) / np.log(np.min(fb)), base=np.min(fb), num=nweights + 1)
+        lw = np.array([len(fb[np.where((fb >= f_cut[i]) & (fb < f_cut[i + 1]))]) for i in range(nweights)])
+        lw[-1] += 1
+        lw[-1] += len(fb) - int(np.sum(lw))
+        out["len_weights"] = lw
+    if nspcal:
+        out["spcal_freqs"] = np.logspace(1.0, np.log(np.max(fb)) / np.log(np.min(fb)), base=np.min(fb), num=nspcal)
+    return out
+
+
+def extras_columns(cfg, n, seed, nspcal=0, nweights=0, amp_sigma=0.05, phi_sigma=0.05):
+    """Random calibration / weight parameters: (X_extra [n, m], names) with the bajes naming
+    (bajes/obs/gw/detector.py:17-23)."""
+    rng = np.random.default_rng(seed)
+    cols, names = [], []
+    for ifo in cfg["ifos"]:
+        for j in range(nspcal):
+            names.append("spcal_amp{}_{}".format(j, ifo)); cols.append(rng.normal(0.0, amp_sigma, n))
+            names.append("spcal_phi{}_{}".format(j, ifo)); cols.append(rng.normal(0.0, phi_sigma, n))
+        for b in range(nweights):
+            names.append("weight{}_{}".format(b, ifo)); cols.append(rng.uniform(0.7, 1.4, n))
+    return (np.stack(cols, axis=1) if cols else np.zeros((n, 0))), names

@@ -29,6 +29,8 @@ extern "C" {
 
 #define BJ_ABI_VERSION 1
 #define BJ_MAX_IFO 3            /* detectors fused in one pass of the kernel            */
+#define BJ_MAX_SPCAL 16         /* spectral-calibration nodes per detector               */
+#define BJ_MAX_WEIGHTS 16       /* PSD-weight bands per detector                         */
 
 typedef enum {
     BJ_OK = 0,
@@ -118,6 +120,33 @@ int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* 
               const double* const* data_ri, const double* const* psd);
 int bj_destroy(bj_ctx* ctx);
 
+/* Calibration envelopes and PSD weights (the nspcal / nweights options of GWLikelihood,
+ * pipe/log_like.py:27-33; Detector.compute_inner_products, detector.py:517-531):
+ *   spcal  : h_i(f) *= interp(f; spcal_freqs, (1 + amp_j) exp(i phi_j))      (detector.py:17-20,517-519)
+ *   weights: S_i(f) *= w_b on nweights contiguous bands of len_weights[b] bins; dd is recomputed and
+ *            logL gets -1/2 sum log w                                          (detector.py:22-23,524-531) */
+typedef struct {
+    int32_t nspcal;               /* 0 = no calibration envelope, else 2..BJ_MAX_SPCAL            */
+    int32_t nweights;             /* 0 = no PSD weights, else 1..BJ_MAX_WEIGHTS                   */
+    const double*  spcal_freqs;   /* [nspcal] ascending node frequencies                          */
+    const int64_t* len_weights;   /* [nweights] bins per band, sum == n_bins                      */
+} bj_extras;
+
+/* where the per-point values of 'spcal_amp{j}_{ifo}', 'spcal_phi{j}_{ifo}', 'weight{b}_{ifo}' live:
+ * column >= 0 reads x[column], BJ_COL_CONST uses the value (same convention as bj_param_map) */
+typedef struct {
+    int32_t spcal_amp_col[BJ_MAX_IFO][BJ_MAX_SPCAL];
+    int32_t spcal_phi_col[BJ_MAX_IFO][BJ_MAX_SPCAL];
+    int32_t weight_col[BJ_MAX_IFO][BJ_MAX_WEIGHTS];
+    double  spcal_amp_val[BJ_MAX_IFO][BJ_MAX_SPCAL];
+    double  spcal_phi_val[BJ_MAX_IFO][BJ_MAX_SPCAL];
+    double  weight_val[BJ_MAX_IFO][BJ_MAX_WEIGHTS];
+} bj_extra_map;
+
+/* bj_create with extras (ex may be NULL = bj_create). */
+int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
+                 const double* const* data_ri, const double* const* psd, const bj_extras* ex);
+
 /* Batched GWLikelihood.log_like (pipe/log_like.py:107-183) for W points; x is row-major
  * [W, ndim] float64 in HOST memory; out_logl[W] in HOST memory.  Includes H2D/D2H copies. */
 int bj_loglike(bj_ctx* ctx, const double* x_host, int64_t n_walkers, int32_t ndim,
@@ -129,6 +158,13 @@ int bj_loglike(bj_ctx* ctx, const double* x_host, int64_t n_walkers, int32_t ndi
 int bj_loglike_device(bj_ctx* ctx, const double* x_dev, int64_t n_walkers, int32_t ndim,
                       const bj_param_map* map, double* out_logl_dev, double* out_parts_dev,
                       void* stream);
+
+/* The same two entries for contexts created with extras; emap gives the calibration / weight parameters. */
+int bj_loglike_ex(bj_ctx* ctx, const double* x_host, int64_t n_walkers, int32_t ndim,
+                  const bj_param_map* map, const bj_extra_map* emap, double* out_logl_host);
+int bj_loglike_device_ex(bj_ctx* ctx, const double* x_dev, int64_t n_walkers, int32_t ndim,
+                         const bj_param_map* map, const bj_extra_map* emap, double* out_logl_dev,
+                         double* out_parts_dev, void* stream);
 
 /* Projected frequency-domain waveform of ONE parameter point on every detector
  * (Waveform.compute_hphc + Detector.project_fdwave, waveform.py:270-395, detector.py:394-418).

@@ -566,9 +566,11 @@ class DetectorPort:
             return proj * np.exp(-2j * np.pi * self.freqs * delay)
         return proj
 
-    def store_measurement(self, series, noise):
-        """detector.py:452-493 (no spcal / PSD weights)."""
+    def store_measurement(self, series, noise, nspcal=0, spcal_freqs=None, nweights=0, len_weights=None):
+        """detector.py:452-493."""
         assert self.reference_time == series.t_gps
+        self.nspcal, self.spcal_freqs = nspcal, spcal_freqs
+        self.nweights, self.len_weights = nweights, len_weights
         self.srate = series.srate
         self.seglen = series.seglen
         self._mask = series.mask
@@ -578,10 +580,30 @@ class DetectorPort:
         self.psd = noise.interp_psd_pad(self.freqs) * series.window_factor
         self._dd = (4.0 / self.seglen) * np.sum(np.abs(self.data) ** 2.0 / self.psd)
 
-    def compute_inner_products(self, hphc, params, tag="freq", roq=None):
-        """detector.py:496-544 without spcal / PSD weights.  Returns (dh, hh, dd) where ``dh`` is
-        the per-bin integrand on the full axis (non-ROQ) or the scalar product (ROQ)."""
+    def compute_inner_products(self, hphc, params, tag="freq", roq=None, psd_weight_factor=False):
+        """detector.py:496-544.  Returns (dh, hh, dd[, sum log w]) where ``dh`` is the per-bin integrand on the
+        full axis (non-ROQ) or the scalar product (ROQ)."""
         wav = self.project_fdwave(hphc, params, tag, roq=roq)
+        psd = self.psd
+        dd = self._dd
+        logw = 0.0
+        if getattr(self, "nspcal", 0) > 0:
+            # detector.py:17-20,517-519
+            amp = np.array([params["spcal_amp{}_{}".format(i, self.ifo)] for i in range(self.nspcal)])
+            phi = np.array([params["spcal_phi{}_{}".format(i, self.ifo)] for i in range(self.nspcal)])
+            wav = wav * np.interp(self.freqs, self.spcal_freqs, (1.0 + amp) * np.exp(1j * phi))
+        if getattr(self, "nweights", 0) > 0:
+            # detector.py:22-23,524-531
+            weights = np.concatenate([np.ones(self.len_weights[i]) * params["weight{}_{}".format(i, self.ifo)]
+                                      for i in range(self.nweights)])
+            logw = (np.log(weights)).sum()
+            psd = psd * weights
+            dd = (4.0 / self.seglen) * (np.abs(self.data) ** 2.0 / psd).sum()
+        if roq is None:
+            hh = (4.0 / self.seglen) * (np.abs(wav) ** 2.0 / psd).sum()
+            dh = np.zeros(self._nfr, dtype=complex)
+            dh[self._mask] = (4.0 / self.seglen) * np.conj(self.data) * wav / psd
+            return (dh, hh, dd, logw) if psd_weight_factor else (dh, hh, dd)
         if roq is not None:
             hh = np.dot(roq[self.ifo]["psi_weights"], np.abs(wav[roq["mask_psi"]]) ** 2)
             tc = (self.seglen / 2.0
@@ -608,7 +630,8 @@ class GWLikelihoodPort:
     """Restatement of GWLikelihood (pipe/log_like.py:21-183) without spcal / PSD weights."""
 
     def __init__(self, ifos, datas, dets, noises, freqs, srate, seglen, approx,
-                 marg_phi_ref=False, marg_time_shift=False, roq=None):
+                 marg_phi_ref=False, marg_time_shift=False, roq=None,
+                 nspcal=0, spcal_freqs=None, nweights=0, len_weights=None):
         self.ifos = ifos
         self.dets = dets
         self.roq = roq
@@ -619,7 +642,7 @@ class GWLikelihoodPort:
         self.logZ_noise = 0.0
         mask = None
         for ifo in ifos:
-            self.dets[ifo].store_measurement(datas[ifo], noises[ifo])
+            self.dets[ifo].store_measurement(datas[ifo], noises[ifo], nspcal, spcal_freqs, nweights, len_weights)
             if datas[ifo].seglen != seglen:
                 raise ValueError("Input seglen of data and model do not match in detector {}.".format(ifo))
             self.logZ_noise += -0.5 * self.dets[ifo]._dd
@@ -651,14 +674,17 @@ class GWLikelihoodPort:
             return -np.inf
         hh = 0.0
         dd = 0.0
+        psd_fact = 0.0
         if self.marg_time_shift:
             # log_like.py:135-156
             arr = np.zeros(self.Nfr, dtype=complex)
             for ifo in self.ifos:
-                dh_i, hh_i, dd_i = self.dets[ifo].compute_inner_products(wave, params, "freq")
+                dh_i, hh_i, dd_i, lw = self.dets[ifo].compute_inner_products(wave, params, "freq",
+                                                                               psd_weight_factor=True)
                 arr = arr + np.fft.fft(dh_i)
                 hh += np.real(hh_i)
                 dd += np.real(dd_i)
+                psd_fact += lw
             if self.marg_phi_ref:
                 r = logsumexp(_log_i0(np.abs(arr)) - np.log(self.Nfr))
             else:
@@ -667,12 +693,18 @@ class GWLikelihoodPort:
             # log_like.py:158-179
             dh = 0.0 + 0.0j
             for ifo in self.ifos:
-                dh_i, hh_i, dd_i = self.dets[ifo].compute_inner_products(wave, params, "freq", roq=self.roq)
+                if self.roq is not None:
+                    dh_i, hh_i, dd_i = self.dets[ifo].compute_inner_products(wave, params, "freq", roq=self.roq)
+                    lw = 0.0
+                else:
+                    dh_i, hh_i, dd_i, lw = self.dets[ifo].compute_inner_products(wave, params, "freq",
+                                                                                   psd_weight_factor=True)
                 dh += dh_i if self.roq is not None else dh_i.sum()
                 hh += np.real(hh_i)
                 dd += np.real(dd_i)
+                psd_fact += lw
             r = _log_i0(np.abs(dh)) if self.marg_phi_ref else np.real(dh)
-        return -0.5 * (hh + dd) + r - self.logZ_noise
+        return -0.5 * (hh + dd) + r - self.logZ_noise - 0.5 * psd_fact
 
 
 # --------------------------------------------------------------------------------------

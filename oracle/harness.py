@@ -52,21 +52,21 @@ def port_classes(gmst_reference=None, sday=None):
                            Waveform=port.WaveformPort, design_asd=design_asd, make_series=make_series)
 
 
-def reference_likelihood(cfg, approx=None, marg_phi_ref=False, roq=None, net=None):
+def reference_likelihood(cfg, approx=None, marg_phi_ref=False, roq=None, net=None, extras=None):
     from oracle import shims
     shims.import_reference()
     from bajes.pipe.log_like import GWLikelihood
     cl = reference_classes()
     ifos, datas, dets, noises, f = net if net is not None else syn.build_network(cfg, cl)
     return GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], approx or cfg["approx"],
-                        marg_phi_ref=marg_phi_ref, roq=roq)
+                        marg_phi_ref=marg_phi_ref, roq=roq, **(extras or {}))
 
 
-def port_likelihood(cfg, approx=None, marg_phi_ref=False, roq=None, net=None, **kw):
+def port_likelihood(cfg, approx=None, marg_phi_ref=False, roq=None, net=None, extras=None, **kw):
     cl = port_classes(**kw)
     ifos, datas, dets, noises, f = net if net is not None else syn.build_network(cfg, cl)
     return port.GWLikelihoodPort(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], approx or cfg["approx"],
-                                 marg_phi_ref=marg_phi_ref, roq=roq)
+                                 marg_phi_ref=marg_phi_ref, roq=roq, **(extras or {}))
 
 
 def eval_batch(like, X, names, const):

@@ -160,8 +160,35 @@ def gen_roq():
     print("roq: finite %d/%d" % (np.isfinite(out["logl_marg0"]).sum(), len(X)))
 
 
+def gen_extras():
+    """C2_small with calibration envelopes and/or PSD weights (detector.py:517-531)."""
+    cfg = syn.CONFIGS["C2_small"]
+    cl = harness.reference_classes()
+    const = syn.constants(cfg)
+    out = {}
+    Xb, names_b = _walkers(cfg, 48, 48, 51)
+    for tag, nsp, nw, marg in (("spcal", 6, 0, False), ("weights", 0, 4, False), ("both", 5, 3, False), ("both", 5, 3, True)):
+        ex = syn.extras_setup(cfg, nsp, nw)
+        Xe, names_e = syn.extras_columns(cfg, len(Xb), 52, nsp, nw)
+        X, names = np.concatenate([Xb, Xe], axis=1), names_b + names_e
+        net = syn.build_network(cfg, cl)
+        like = harness.reference_likelihood(cfg, marg_phi_ref=marg, net=net, extras=ex)
+        key = "%s_marg%d" % (tag, int(marg))
+        with np.errstate(all="ignore"):
+            out["logl_" + key] = harness.eval_batch(like, X, names, const)
+        out["X_" + key] = X
+        out["names_" + key] = np.array(names)
+        if ex["spcal_freqs"] is not None:
+            out["spcal_freqs_" + key] = ex["spcal_freqs"]
+        if ex["len_weights"] is not None:
+            out["len_weights_" + key] = ex["len_weights"]
+        print("  extras %s: finite %d/%d" % (key, np.isfinite(out["logl_" + key]).sum(), len(X)))
+    dets = net[2]
+    np.savez_compressed(os.path.join(GOLDEN, "extras_small.npz"), **_det_constants(dets, cfg["ifos"]), **out)
+
+
 def main(argv):
-    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq"}
+    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq", "extras"}
     os.makedirs(GOLDEN, exist_ok=True)
     if "asd" in what:
         write_design_asd()
@@ -176,6 +203,8 @@ def main(argv):
         gen_c2("C2", 128, 128, [("TaylorF2_3.5PN", 256, False), ("TaylorF2_5.5PN_7.5PNTides", 32, False)])
     if "roq" in what:
         gen_roq()
+    if "extras" in what:
+        gen_extras()
 
 
 if __name__ == "__main__":

@@ -64,19 +64,24 @@ def emit(rec, fh):
         fh.flush()
 
 
-def fullgrid(name, fh, sincos="mufu", walkers=None, approx=None):
+def fullgrid(name, fh, sincos="mufu", walkers=None, approx=None, nspcal=0, nweights=0):
     cfg = dict(syn.CONFIGS[name])
     if approx:
         cfg["approx"] = approx
     cl = syn.product_classes()
-    like = GWLikelihood(*syn.build_network(cfg, cl), cfg["srate"], cfg["seglen"], cfg["approx"], sincos=sincos)
+    ex = syn.extras_setup(cfg, nspcal, nweights)
+    like = GWLikelihood(*syn.build_network(cfg, cl), cfg["srate"], cfg["seglen"], cfg["approx"], sincos=sincos, **ex)
     W = walkers or cfg["n_walkers"]
     X, names = syn.draw_walkers(cfg, W, 5, "narrow")
+    if nspcal or nweights:
+        Xe, ne = syn.extras_columns(cfg, W, 6, nspcal, nweights)
+        X, names = np.ascontiguousarray(np.concatenate([X, Xe], axis=1)), names + ne
     const = syn.constants(cfg)
     step_ms, kms, _ = time_device(like, X, names, const)
     host_ms = time_host(like, X, names, const)
     nb = like.engine.n_bins
     emit({"config": name, "kind": "fullgrid", "approx": cfg["approx"], "sincos": sincos, "walkers": W, "n_bins": nb,
+          "nspcal": nspcal, "nweights": nweights, "ndim": X.shape[1],
           "n_ifo": len(cfg["ifos"]), "step_ms_device": step_ms, "kernel_ms": kms, "step_ms_host_api": host_ms,
           "walker_bins_per_s": W * nb / (step_ms * 1e-3), "evals_per_s": W / (step_ms * 1e-3),
           "launch": like.engine.last_launch_info()}, fh)
@@ -156,6 +161,10 @@ if __name__ == "__main__":
         fullgrid("C2", fh, approx="TaylorF2_5.5PN_7.5PNTides")
         fullgrid("C2", fh, walkers=64)
         fullgrid("C2", fh, walkers=512)
+    if want("extras"):
+        fullgrid("C2", fh, nspcal=10)
+        fullgrid("C2", fh, nweights=8)
+        fullgrid("C2", fh, nspcal=10, nweights=8)
     if want("c3"):
         roq_c3(fh)
     if want("c4"):

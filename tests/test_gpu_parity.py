@@ -291,6 +291,36 @@ def test_relbin_tracks_full_grid_likelihood():
     assert np.max(np.abs(a - b)) <= 0.02 * (np.max(a) - np.min(a)) + 0.05
 
 
+# ------------------------------------------------------------------------------------------------------
+# calibration envelopes + PSD weights (detector.py:517-531), against reference golden vectors
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sincos", ["mufu", "poly32", "fp64"])
+@pytest.mark.parametrize("key", ["spcal_marg0", "weights_marg0", "both_marg0", "both_marg1"])
+def test_calibration_envelopes_and_psd_weights(key, sincos):
+    cfg = syn.CONFIGS["C2_small"]
+    gold = load_golden("extras_small.npz")
+    kw = {}
+    if "spcal_freqs_" + key in gold:
+        kw.update(nspcal=len(gold["spcal_freqs_" + key]), spcal_freqs=gold["spcal_freqs_" + key])
+    if "len_weights_" + key in gold:
+        kw.update(nweights=len(gold["len_weights_" + key]), len_weights=gold["len_weights_" + key])
+    like = _like(cfg, gold, marg_phi_ref=key.endswith("1"), sincos=sincos, **kw)
+    names = [str(n) for n in gold["names_" + key]]
+    X, const = gold["X_" + key], syn.constants(cfg)
+    got = like.log_like_batch(X, names, const)
+    _check(got, gold["logl_" + key], "extras %s %s" % (key, sincos))
+    # dict-in / float-out contract with the extra parameters in the dict
+    p = {k: float(v) for k, v in zip(names, X[2])}
+    p.update(const)
+    assert like.log_like(dict(p)) == got[2]
+    # parameters may also arrive as constants (e.g. a fixed calibration node)
+    n0 = len(syn.WALKER_NAMES)
+    const2 = dict(const)
+    const2.update({k: float(v) for k, v in zip(names[n0:], X[5, n0:])})
+    one = like.log_like_batch(X[5:6, :n0], names[:n0], const2)
+    assert one[0] == got[5]
+
+
 def test_engine_reports_launch_and_timing():
     cfg = syn.CONFIGS["C1"]
     gold = load_golden("c1_bbh.npz")

@@ -72,15 +72,24 @@ def test_no_silent_cpu_fallback():
 
 def test_unsupported_features_raise():
     with pytest.raises(NotImplementedError):
-        engine.ParamMap(["mchirp", "q", "spcal_amp0_H1"], {})
+        engine.ParamMap(["mchirp", "q", "spcal_amp0_H1"], {})          # likelihood built without calibration nodes
+    with pytest.raises(NotImplementedError):
+        engine.ParamMap(["mchirp", "q", "eos_logp1"], {})
     with pytest.raises(NotImplementedError):
         engine.make_config(0, "TEOBResumS", 2, 4.0, [])
-    det = Detector("H1", syn.T_GPS)
-    s = Series("freq", np.ones(9, dtype=complex), 16., seglen=1.0, f_min=2., f_max=6., t_gps=syn.T_GPS, only=True,
-               importfreqs=np.arange(9.))
-    fa, asd = design_asd("H1")
-    with pytest.raises(NotImplementedError):
-        det.store_measurement(s, Noise(fa, asd), nspcal=3, spcal_freqs=np.arange(3))
+    with pytest.raises(KeyError):
+        engine.ParamMap(["mchirp", "q"], {}, ifos=["H1"], nspcal=2)     # calibration parameters missing
+
+
+def test_param_map_extras_columns_and_constants():
+    names = ["mchirp", "spcal_amp0_H1", "spcal_phi1_L1", "weight0_H1"]
+    const = {"spcal_amp1_H1": 0.01, "spcal_phi0_H1": 0.0, "spcal_phi1_H1": 0.02, "spcal_amp0_L1": 0.0,
+             "spcal_amp1_L1": 0.0, "spcal_phi0_L1": 0.0, "weight0_L1": 1.5, "weight1_H1": 1.0, "weight1_L1": 0.9}
+    m = engine.ParamMap(names, const, ifos=["H1", "L1"], nspcal=2, nweights=2)
+    e = m.extra
+    assert e.spcal_amp_col[0][0] == 1 and e.spcal_amp_col[0][1] == engine.BJ_COL_CONST and e.spcal_amp_val[0][1] == 0.01
+    assert e.spcal_phi_col[1][1] == 2 and e.weight_col[0][0] == 3 and e.weight_val[1][0] == 1.5
+    assert m.ignored == []
 
 
 # ---- parameter packing -------------------------------------------------------------------------------
