@@ -1,0 +1,159 @@
+"""
+GPU edge cases (``-m gpu``): ragged and empty batches, odd / tiny frequency bands, 1 and 2 detectors, alternative
+parametrisations (mtot, iota, spherical and in-plane spins, constants vs sampled), pickling, the pool adapter.
+Every value is compared with the oracle port evaluated live on the host.
+"""
+import pickle
+
+import numpy as np
+import pytest
+
+from bajes_b200 import GWLikelihood, Posterior, synthetic as syn
+from bajes_b200.ensemble import BoxPrior
+from bajes_b200.pool import BatchedPool
+from oracle import harness
+
+from conftest import product_network_from_port
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(cfg, **kw):
+    """(GPU likelihood, oracle-port likelihood) on identical data."""
+    cl = harness.port_classes()
+    net = syn.build_network(cfg, cl)
+    port = harness.port_likelihood(cfg, net=net, marg_phi_ref=kw.get("marg_phi_ref", False))
+    ifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"], **kw)
+    return like, port
+
+
+def _agree(got, want, what):
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin), what
+    err = np.abs(got[fin] - want[fin])
+    assert np.all(err <= harness.tolerance(want[fin])), "%s: %g x tol" % (what, np.max(err / harness.tolerance(want[fin])))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 300])
+def test_ragged_and_empty_batches(n):
+    cfg = syn.CONFIGS["C1"]
+    like, port = _pair(cfg)
+    X, names = syn.draw_walkers(cfg, max(n, 1), 3, "wide")
+    X = X[:n]
+    const = syn.constants(cfg)
+    got = like.log_like_batch(X, names, const)
+    assert got.shape == (n,)
+    if n:
+        _agree(got, harness.eval_batch(port, X, names, const), "batch of %d" % n)
+
+
+@pytest.mark.parametrize("band", [(20.0, 21.0), (20.0, 36.0), (20.25, 100.0), (30.0, 511.75)])
+def test_tiny_odd_and_even_bands(band):
+    """5, 65, 320 and 1928 in-band bins: below one tile, one bin over a tile, odd and even counts."""
+    cfg = dict(syn.CONFIGS["C1"])
+    cfg.update(f_min=band[0], f_max=band[1])
+    like, port = _pair(cfg, sincos="poly32")
+    n_bins = int(round((band[1] - band[0]) * cfg["seglen"])) + 1
+    assert like.engine.n_bins == n_bins
+    X, names = syn.draw_walkers(cfg, 40, 4, "wide")
+    const = syn.constants(cfg)
+    _agree(like.log_like_batch(X, names, const), harness.eval_batch(port, X, names, const), "band %s" % (band,))
+
+
+@pytest.mark.parametrize("ifos", [["V1"], ["L1", "K1"], ["H1", "L1", "V1"]])
+def test_detector_networks(ifos):
+    from bajes_b200 import noise as nz
+    cfg = dict(syn.CONFIGS["C1"])
+    cfg.update(ifos=ifos)
+    if "K1" in ifos:
+        # no KAGRA curve is bundled: reuse the aLIGO table for the test (both sides get the same PSD)
+        nz._DESIGN_KEY["K1"] = "aLIGO"
+    like, port = _pair(cfg)
+    X, names = syn.draw_walkers(cfg, 48, 5, "wide")
+    const = syn.constants(cfg)
+    _agree(like.log_like_batch(X, names, const), harness.eval_batch(port, X, names, const), "ifos %s" % ifos)
+    nz._DESIGN_KEY.pop("K1", None)
+
+
+def test_alternative_parametrisations():
+    """mtot instead of mchirp, iota instead of cos_iota, spherical spins, in-plane cartesian spins, and a mix of
+    sampled columns and constants (waveform.py:334-377)."""
+    cfg = syn.CONFIGS["C2_small"]
+    like, port = _pair(cfg, sincos="poly32")
+    base = syn.constants(cfg)
+    rng = np.random.default_rng(8)
+    n = 24
+    cols = dict(mtot=rng.uniform(2.5, 3.2, n), q=rng.uniform(1.0, 1.8, n), s1=rng.uniform(0, 0.3, n),
+                tilt1=rng.uniform(0, np.pi, n), phi_1l=rng.uniform(0, 2 * np.pi, n), s2=rng.uniform(0, 0.3, n),
+                tilt2=rng.uniform(0, np.pi, n), phi_2l=rng.uniform(0, 2 * np.pi, n), lambda1=rng.uniform(0, 1000, n),
+                iota=rng.uniform(0, np.pi, n), ra=rng.uniform(0, 6.28, n), dec=rng.uniform(-1.5, 1.5, n),
+                psi=rng.uniform(0, 3.14, n), time_shift=rng.uniform(-0.01, 0.01, n), phi_ref=rng.uniform(0, 6.28, n))
+    names = list(cols)
+    X = np.stack([cols[k] for k in names], axis=1)
+    const = {k: v for k, v in base.items() if k not in ("s1x", "s1y", "s2x", "s2y")}
+    const.update(lambda2=250.0, distance=60.0)            # constants instead of sampled columns
+    got = like.log_like_batch(X, names, const)
+    _agree(got, harness.eval_batch(port, X, names, const), "mtot / iota / spherical spins")
+    # in-plane cartesian components enter the 3.5PN spin-spin terms (taylorf2.py:199-205)
+    names2 = ["mchirp", "q", "s1x", "s1y", "s1z", "s2x", "s2y", "s2z", "cos_iota", "ra", "dec", "psi", "time_shift",
+              "phi_ref", "distance"]
+    X2 = np.stack([rng.uniform(1.1, 1.3, n), rng.uniform(1, 2, n)] + [rng.uniform(-0.2, 0.2, n) for _ in range(6)] +
+                  [rng.uniform(-1, 1, n), rng.uniform(0, 6.28, n), rng.uniform(-1.5, 1.5, n), rng.uniform(0, 3.14, n),
+                   rng.uniform(-0.01, 0.01, n), rng.uniform(0, 6.28, n), rng.uniform(20, 80, n)], axis=1)
+    const2 = {k: v for k, v in base.items() if k not in ("s1x", "s1y", "s2x", "s2y")}
+    const2.update(lambda1=0.0, lambda2=0.0)                # both zero: the tidal branch is skipped (taylorf2.py:394)
+    _agree(like.log_like_batch(X2, names2, const2), harness.eval_batch(port, X2, names2, const2), "cartesian spins")
+    # per-point dict API with the same content
+    p = {k: float(v) for k, v in zip(names2, X2[0])}
+    p.update(const2)
+    assert abs(like.log_like(dict(p)) - port.log_like(dict(p))) <= float(harness.tolerance(port.log_like(dict(p))))
+
+
+def test_missing_required_parameter_raises():
+    from bajes_b200.engine import EngineError
+    cfg = syn.CONFIGS["C1"]
+    like, _ = _pair(cfg)
+    X, names = syn.draw_walkers(cfg, 4, 1, "narrow")
+    const = syn.constants(cfg)
+    keep = [i for i, n in enumerate(names) if n != "distance"]
+    with pytest.raises(EngineError):
+        like.log_like_batch(X[:, keep], [names[i] for i in keep], const)
+    with pytest.raises(ValueError):
+        like.log_like_batch(X[:, :5], names, const)
+
+
+def test_pickle_round_trip_rebuilds_the_engine_lazily():
+    cfg = syn.CONFIGS["C1"]
+    like, _ = _pair(cfg, marg_phi_ref=True)
+    X, names = syn.draw_walkers(cfg, 16, 2, "narrow")
+    const = syn.constants(cfg)
+    a = like.log_like_batch(X, names, const)
+    clone = pickle.loads(pickle.dumps(like))
+    assert clone._engine is None                       # device handles never travel
+    assert np.array_equal(clone.log_like_batch(X, names, const), a)
+    assert clone.dets["H1"]._owner is clone
+
+
+def test_posterior_and_pool_adapter_on_the_gpu():
+    """pool.map(posterior.log_post / log_likeprior / log_like) == the per-point Posterior, row by row."""
+    cfg = syn.CONFIGS["C1"]
+    like, port = _pair(cfg)
+    X, names = syn.draw_walkers(cfg, 33, 6, "wide")
+    lo, hi = X.min(axis=0), X.max(axis=0)
+    prior = BoxPrior(names, np.stack([lo - 1e-9, hi + 1e-9], axis=1), syn.constants(cfg))
+    Xq = X.copy()
+    Xq[4, 0] = hi[0] + 1.0                              # one point outside the prior box
+    post = Posterior(like, prior)
+    ref_post = Posterior(port, prior)
+    pool = BatchedPool(post, processes=4)
+    lp = np.array(pool.map(post.log_post, list(Xq)))
+    assert lp[4] == -np.inf and pool.n_batched_calls == 1
+    want = np.array([ref_post.log_post(x) for x in Xq])
+    keep = np.isfinite(want)
+    assert np.array_equal(np.isfinite(lp), keep)
+    assert np.all(np.abs(lp[keep] - want[keep]) <= harness.tolerance(want[keep]))
+    lnl_lnp = pool.map(post.log_likeprior, list(Xq))
+    assert lnl_lnp[4] == (0.0, -np.inf)                 # inf/likelihood.py:79-80
+    ll = np.array(pool.map(post.log_like, list(Xq[:8])))
+    assert np.all(np.abs(ll - np.array([ref_post.log_like(x) for x in Xq[:8]])) <= harness.tolerance(ll))
