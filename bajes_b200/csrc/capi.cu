@@ -604,57 +604,86 @@ static void note_launch(bj_ctx* c, dim3 grid, size_t smem, int rec8, int model) 
 }
 
 template <int NIFO, int MODEL, bool SPCAL>
-static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st) {
+static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     const size_t smem = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
     auto kern = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, SPCAL>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
+    dim3 grid((unsigned)(c1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
     kern<<<grid, kThreads, smem, st>>>((const double*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
-                                       c->d_partial, c->d_coef_ex, c->dims, c->d_spcal_freqs);
+                                       c->d_partial, c->d_coef_ex, c->dims, c->d_spcal_freqs, c0);
     CUDA_TRY(cudaGetLastError());
     note_launch(c, grid, smem, RS, MODEL);
     return BJ_OK;
 }
 
 template <int NIFO, int MODEL, int SC, bool SPCAL>
-static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st) {
+static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
     constexpr int RB = RecM<NIFO>::kBytes;
     const size_t smem = (size_t)kStages * kTileBins * RB + kStages * sizeof(uint64_t);
     auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC, false, SPCAL>;
     auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true, SPCAL>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)c->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
+    dim3 grid((unsigned)(c1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
     kern<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
-                                       c->d_partial, c->d_coef_ex, c->dims);
+                                       c->d_partial, c->d_coef_ex, c->dims, c0);
     // wide-phase fix-up: every CTA returns immediately unless the prologue flagged one of its walkers
     fixup<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers,
-                                        n_walkers, c->d_partial, c->d_coef_ex, c->dims);
+                                        n_walkers, c->d_partial, c->d_coef_ex, c->dims, c0);
     CUDA_TRY(cudaGetLastError());
     note_launch(c, grid, smem, RB / 8, MODEL);
     return BJ_OK;
 }
 
 template <int NIFO, int MODEL, bool SPCAL>
-static int launch_fullgrid_s(bj_ctx* c, long n_walkers, cudaStream_t st) {
+static int launch_fullgrid_s(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
     switch (c->sincos) {
-        case BJ_SINCOS_MUFU: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_MUFU, SPCAL>(c, n_walkers, st);
-        case BJ_SINCOS_POLY32: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_POLY32, SPCAL>(c, n_walkers, st);
-        default: return launch_fullgrid_fp64<NIFO, MODEL, SPCAL>(c, n_walkers, st);
+        case BJ_SINCOS_MUFU: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_MUFU, SPCAL>(c, n_walkers, st, c0, c1);
+        case BJ_SINCOS_POLY32: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_POLY32, SPCAL>(c, n_walkers, st, c0, c1);
+        default: return launch_fullgrid_fp64<NIFO, MODEL, SPCAL>(c, n_walkers, st, c0, c1);
     }
 }
 
 template <int NIFO, int MODEL>
-static int launch_fullgrid_m(bj_ctx* c, long n_walkers, cudaStream_t st) {
-    if (c->dims.nspcal > 0) return launch_fullgrid_s<NIFO, MODEL, true>(c, n_walkers, st);
-    return launch_fullgrid_s<NIFO, MODEL, false>(c, n_walkers, st);
+static int launch_fullgrid_m(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
+    if (c->dims.nspcal > 0) return launch_fullgrid_s<NIFO, MODEL, true>(c, n_walkers, st, c0, c1);
+    return launch_fullgrid_s<NIFO, MODEL, false>(c, n_walkers, st, c0, c1);
 }
 
 template <int NIFO>
-static int launch_fullgrid_n(bj_ctx* c, long n_walkers, cudaStream_t st) {
-    if (c->cfg.approx == BJ_APPROX_TAYLORF2_35PN) return launch_fullgrid_m<NIFO, MODEL_35>(c, n_walkers, st);
-    return launch_fullgrid_m<NIFO, MODEL_GENERIC>(c, n_walkers, st);
+static int launch_fullgrid_n(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
+    if (c->cfg.approx == BJ_APPROX_TAYLORF2_35PN) return launch_fullgrid_m<NIFO, MODEL_35>(c, n_walkers, st, c0, c1);
+    return launch_fullgrid_m<NIFO, MODEL_GENERIC>(c, n_walkers, st, c0, c1);
+}
+
+static int launch_fullgrid(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
+    switch (c->cfg.n_ifo) {
+        case 1: return launch_fullgrid_n<1>(c, n_walkers, st, c0, c1);
+        case 2: return launch_fullgrid_n<2>(c, n_walkers, st, c0, c1);
+        default: return launch_fullgrid_n<3>(c, n_walkers, st, c0, c1);
+    }
+}
+
+static EpilogueTables epilogue_tables(const bj_ctx* c) {
+    EpilogueTables tab;
+    tab.chunks = c->d_chunks;
+    tab.n_chunks = c->n_chunks;
+    tab.n_cells = c->n_cells;
+    tab.cell_band = c->d_cell_band;
+    tab.cell_seg = c->d_cell_seg;
+    tab.gram = c->d_gram;
+    tab.dd_band = c->d_dd_band;
+    return tab;
+}
+
+static int launch_epilogue(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl, double* parts, int mode, int c0,
+                           int c1, double* sums_io) {
+    epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers), kEpiWalkers * kEpiSlices, 0, st>>>(
+        c->cfg, epilogue_tables(c), c->dims, c->d_partial, c->d_coef, c->d_coef_ex, c->cap_walkers, n_walkers, logl,
+        parts, mode, c0, c1, sums_io);
+    CUDA_TRY(cudaGetLastError());
+    return BJ_OK;
 }
 
 static int check_extra_map(const bj_ctx* c, const bj_extra_map* em, int ndim) {
@@ -695,25 +724,11 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], st));
     if (c->kind == KIND_FULLGRID) {
-        switch (c->cfg.n_ifo) {
-            case 1: rc = launch_fullgrid_n<1>(c, n_walkers, st); break;
-            case 2: rc = launch_fullgrid_n<2>(c, n_walkers, st); break;
-            default: rc = launch_fullgrid_n<3>(c, n_walkers, st); break;
-        }
+        rc = launch_fullgrid(c, n_walkers, st, 0, c->n_chunks);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[2], st));
-        EpilogueTables tab;
-        tab.chunks = c->d_chunks;
-        tab.n_chunks = c->n_chunks;
-        tab.n_cells = c->n_cells;
-        tab.cell_band = c->d_cell_band;
-        tab.cell_seg = c->d_cell_seg;
-        tab.gram = c->d_gram;
-        tab.dd_band = c->d_dd_band;
-        epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers), kEpiWalkers * kEpiSlices, 0, st>>>(
-            c->cfg, tab, c->dims, c->d_partial, c->d_coef, c->d_coef_ex, c->cap_walkers, n_walkers, out_logl_dev,
-            out_parts_dev);
-        CUDA_TRY(cudaGetLastError());
+        rc = launch_epilogue(c, n_walkers, st, out_logl_dev, out_parts_dev, 0, 0, c->n_chunks, nullptr);
+        if (rc) return rc;
     } else if (c->kind == KIND_ROQ) {
         rc = launch_roq(c->cfg, c->roq, c->d_coef, c->cap_walkers, n_walkers, out_logl_dev, out_parts_dev, st,
                         c->launch_info);
@@ -737,6 +752,56 @@ extern "C" int bj_loglike_device_ex(bj_ctx* c, const double* x_dev, int64_t n_wa
     if (n_walkers == 0) return BJ_OK;
     if (n_walkers < 0 || ndim <= 0 || !x_dev || !out_logl_dev) return fail(BJ_ERR_INVALID, "bad batch arguments");
     return run_device(c, x_dev, (long)n_walkers, ndim, map, emap, out_logl_dev, out_parts_dev, (cudaStream_t)stream);
+}
+
+// ---- frequency-axis split: local partial sums of a chunk range, and the epilogue on reduced sums -----------
+extern "C" int bj_num_chunks(bj_ctx* c, int32_t* n_chunks) {
+    if (!c || !n_chunks) return fail(BJ_ERR_INVALID, "null argument");
+    if (c->kind != KIND_FULLGRID) return fail(BJ_ERR_UNSUPPORTED, "only the full-grid likelihood has frequency chunks");
+    *n_chunks = c->n_chunks;
+    return BJ_OK;
+}
+
+extern "C" int bj_partial_device(bj_ctx* c, const double* x_dev, int64_t n_walkers, int32_t ndim,
+                                 const bj_param_map* map, const bj_extra_map* emap, int32_t chunk_begin,
+                                 int32_t chunk_end, double* out_sums_dev, void* stream) {
+    if (!c) return fail(BJ_ERR_INVALID, "null context");
+    if (c->kind != KIND_FULLGRID) return fail(BJ_ERR_UNSUPPORTED, "only the full-grid likelihood can be split in frequency");
+    if (n_walkers <= 0 || ndim <= 0 || !x_dev || !out_sums_dev) return fail(BJ_ERR_INVALID, "bad batch arguments");
+    if (chunk_begin < 0 || chunk_end > c->n_chunks || chunk_begin > chunk_end)
+        return fail(BJ_ERR_INVALID, "chunk range [%d, %d) outside [0, %d)", chunk_begin, chunk_end, c->n_chunks);
+    int rc = check_map(map, ndim);
+    if (rc) return rc;
+    rc = check_extra_map(c, emap, ndim);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = ensure_workspace(c, (long)n_walkers);
+    if (rc) return rc;
+    ParamMapDev pm;
+    to_dev_map(map, pm);
+    const unsigned nblk = (unsigned)((n_walkers + 127) / 128);
+    prologue_kernel<<<nblk, 128, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
+    if (c->d_coef_ex)
+        prologue_extras_kernel<<<nblk, 128, 0, st>>>(c->cfg, c->dims, *emap, x_dev, ndim, n_walkers, c->d_coef,
+                                                     c->d_coef_ex, c->cap_walkers);
+    CUDA_TRY(cudaGetLastError());
+    if (chunk_end > chunk_begin) {
+        rc = launch_fullgrid(c, (long)n_walkers, st, chunk_begin, chunk_end);
+        if (rc) return rc;
+    }
+    return launch_epilogue(c, (long)n_walkers, st, nullptr, nullptr, 1, chunk_begin, chunk_end, out_sums_dev);
+}
+
+extern "C" int bj_finish_device(bj_ctx* c, const double* sums_dev, int64_t n_walkers, double* out_logl_dev,
+                                double* out_parts_dev, void* stream) {
+    if (!c) return fail(BJ_ERR_INVALID, "null context");
+    if (c->kind != KIND_FULLGRID) return fail(BJ_ERR_UNSUPPORTED, "only the full-grid likelihood can be split in frequency");
+    if (n_walkers <= 0 || !sums_dev || !out_logl_dev) return fail(BJ_ERR_INVALID, "bad arguments");
+    if (n_walkers > c->cap_walkers) return fail(BJ_ERR_INVALID, "bj_finish_device must follow bj_partial_device on the same batch");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return launch_epilogue(c, (long)n_walkers, (cudaStream_t)stream, out_logl_dev, out_parts_dev, 2, 0, 0,
+                           const_cast<double*>(sums_dev));
 }
 
 extern "C" int bj_loglike_device(bj_ctx* c, const double* x_dev, int64_t n_walkers, int32_t ndim,

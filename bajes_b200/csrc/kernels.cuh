@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
                                                                  const double* __restrict__ coef, long stride,
                                                                  long n_walkers, double* __restrict__ partial,
                                                                  const double* __restrict__ coef_ex, ExtrasDims dims,
-                                                                 const double* __restrict__ spcal_freqs) {
+                                                                 const double* __restrict__ spcal_freqs, int chunk0) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
@@ -386,7 +386,8 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
 #pragma unroll
     for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; }
 
-    const ChunkDesc chunk = chunks[blockIdx.x];
+    const int chunk_id = chunk0 + (int)blockIdx.x;
+    const ChunkDesc chunk = chunks[chunk_id];
     const long bin0 = chunk.start;
     const int nb_total = chunk.len;
     const int n_tiles = (nb_total + kTileBins - 1) / kTileBins;
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
     }
 
     if (wi < n_walkers) {
-        double* out = partial + (size_t)blockIdx.x * (2 * NIFO) * stride + wi;
+        double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
             out[(2 * i + 0) * stride] = zr[i];
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
                                                                        const double* __restrict__ coef, long stride,
                                                                        long n_walkers, double* __restrict__ partial,
                                                                        const double* __restrict__ coef_ex,
-                                                                       ExtrasDims dims) {
+                                                                       ExtrasDims dims, int chunk0) {
     constexpr int RB = RecM<NIFO>::kBytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
@@ -641,7 +642,8 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 
     // every chunk starts on an even record and holds an even number of records (cells are padded with zero-weight
     // records), so bins can be consumed in (even, odd) pairs
-    const ChunkDesc chunk = chunks[blockIdx.x];
+    const int chunk_id = chunk0 + (int)blockIdx.x;
+    const ChunkDesc chunk = chunks[chunk_id];
     const long bin0 = chunk.start;
     const int nb_total = chunk.len;
     const int n_tiles = (nb_total + kTileBins - 1) / kTileBins;
@@ -752,7 +754,7 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
     }
 
     if (wi < n_walkers) {
-        double* out = partial + (size_t)blockIdx.x * (2 * NIFO) * stride + wi;
+        double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
             out[(2 * i + 0) * stride] = zr[i];
@@ -793,10 +795,14 @@ struct EpilogueTables {
     const double* dd_band;    // [n_ifo][nweights]  (4/T) sum_{k in band} |d|^2 / S
 };
 
+// mode 0: reduce the chunks [chunk_begin, chunk_end) and finish (the normal single-GPU epilogue)
+// mode 1: reduce the chunks only and write sums_io[2 n_ifo][n_walkers]            (frequency-split, before all-reduce)
+// mode 2: take sums_io as the already reduced sums and finish                     (frequency-split, after all-reduce)
 __global__ void __launch_bounds__(kEpiWalkers * kEpiSlices)
 epilogue_kernel(DeviceConfig cfg, EpilogueTables tab, ExtrasDims dims, const double* __restrict__ partial,
                 const double* __restrict__ coef, const double* __restrict__ coef_ex, long stride, long n_walkers,
-                double* __restrict__ logl, double* __restrict__ sums) {
+                double* __restrict__ logl, double* __restrict__ sums, int mode, int chunk_begin, int chunk_end,
+                double* __restrict__ sums_io) {
     __shared__ double red[kEpiSlices][2 * BJ_MAX_IFO][kEpiWalkers];
     const int lane_w = threadIdx.x % kEpiWalkers, slice = threadIdx.x / kEpiWalkers;
     const long w = (long)blockIdx.x * kEpiWalkers + lane_w;
@@ -806,16 +812,29 @@ epilogue_kernel(DeviceConfig cfg, EpilogueTables tab, ExtrasDims dims, const dou
     // with PSD weights every chunk lies in one band and is scaled by 1 / w_band (detector.py:529)
     for (int j = 0; j < 2 * nifo; ++j) {
         double acc = 0.0;
-        for (int ch = slice; ch < tab.n_chunks; ch += kEpiSlices) {
-            double v = partial[((size_t)ch * (2 * nifo) + j) * stride + wc];
-            if (dims.nweights > 0)
-                v *= coef_ex[ex_invw_slot(dims, nifo, j >> 1, tab.chunks[ch].band) * stride + wc];
-            acc += v;
+        if (mode != 2) {
+            for (int ch = chunk_begin + slice; ch < chunk_end; ch += kEpiSlices) {
+                double v = partial[((size_t)ch * (2 * nifo) + j) * stride + wc];
+                if (dims.nweights > 0)
+                    v *= coef_ex[ex_invw_slot(dims, nifo, j >> 1, tab.chunks[ch].band) * stride + wc];
+                acc += v;
+            }
+        } else if (slice == 0) {
+            acc = sums_io[(size_t)j * n_walkers + wc];
         }
         red[slice][j][lane_w] = acc;
     }
     __syncthreads();
     if (slice != 0 || w >= n_walkers) return;
+    if (mode == 1) {
+        for (int j = 0; j < 2 * nifo; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < kEpiSlices; ++sl) acc += red[sl][j][lane_w];
+            sums_io[(size_t)j * n_walkers + w] = acc;
+        }
+        return;
+    }
 
     const double amp = coef[C_AMP * stride + w];
     const bool valid = coef[C_VALID * stride + w] != 0.0;

@@ -114,6 +114,10 @@ EXPORTS = {
     "bj_loglike": (C.c_int, [C.c_void_p, _DP, C.c_int64, C.c_int32, C.POINTER(bj_param_map), _DP]),
     "bj_loglike_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(bj_param_map),
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bj_num_chunks": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "bj_partial_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(bj_param_map),
+                                    C.POINTER(bj_extra_map), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bj_finish_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bj_project_waveform": (C.c_int, [C.c_void_p, _DP, C.c_int32, C.POINTER(bj_param_map), _DP]),
     "bj_polarizations": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int64, _DP, _DP, C.c_int32,
                                    C.POINTER(bj_param_map), _DP, _DP]),
@@ -387,6 +391,26 @@ class Engine:
                                               C.c_void_p(out_ptr), C.c_void_p(parts_ptr or None),
                                               C.c_void_p(stream or None)),
                "bj_loglike_device")
+
+    def num_chunks(self) -> int:
+        n = C.c_int32()
+        _check(self._lib, self._lib.bj_num_chunks(self._h, C.byref(n)), "bj_num_chunks")
+        return n.value
+
+    def partial_device(self, x_ptr: int, n_walkers: int, ndim: int, pmap: ParamMap, chunk_begin: int, chunk_end: int,
+                       sums_ptr: int, stream: int = 0) -> None:
+        """Frequency-split: local partial sums [2 n_ifo][W] of the chunk range (device pointers)."""
+        ex = C.byref(pmap.extra) if pmap.extra is not None else None
+        _check(self._lib,
+               self._lib.bj_partial_device(self._h, C.c_void_p(x_ptr), n_walkers, ndim, C.byref(pmap.c), ex,
+                                           chunk_begin, chunk_end, C.c_void_p(sums_ptr), C.c_void_p(stream or None)),
+               "bj_partial_device")
+
+    def finish_device(self, sums_ptr: int, n_walkers: int, out_ptr: int, parts_ptr: int = 0, stream: int = 0) -> None:
+        _check(self._lib,
+               self._lib.bj_finish_device(self._h, C.c_void_p(sums_ptr), n_walkers, C.c_void_p(out_ptr),
+                                          C.c_void_p(parts_ptr or None), C.c_void_p(stream or None)),
+               "bj_finish_device")
 
     def project_waveform(self, x: np.ndarray, pmap: ParamMap) -> np.ndarray:
         x = _as_f64(x).reshape(-1)

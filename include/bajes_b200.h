@@ -166,6 +166,18 @@ int bj_loglike_device_ex(bj_ctx* ctx, const double* x_dev, int64_t n_walkers, in
                          const bj_param_map* map, const bj_extra_map* emap, double* out_logl_dev,
                          double* out_parts_dev, void* stream);
 
+/* Frequency-axis split (small batches on several GPUs): rank r evaluates the table chunks
+ * [chunk_begin, chunk_end) of EVERY walker and returns the local partial sums
+ * sums[2 * n_ifo][n_walkers] (Re, Im of the un-normalised <d|h> per detector, PSD weights applied).  The caller
+ * all-reduces (sums) them across ranks and hands the result to bj_finish_device, which runs the epilogue
+ * (<h|h> from the Gram moments, amplitude, logL).  bj_num_chunks gives the number of table chunks. */
+int bj_num_chunks(bj_ctx* ctx, int32_t* n_chunks);
+int bj_partial_device(bj_ctx* ctx, const double* x_dev, int64_t n_walkers, int32_t ndim,
+                      const bj_param_map* map, const bj_extra_map* emap, int32_t chunk_begin, int32_t chunk_end,
+                      double* out_sums_dev, void* stream);
+int bj_finish_device(bj_ctx* ctx, const double* sums_dev, int64_t n_walkers, double* out_logl_dev,
+                     double* out_parts_dev, void* stream);
+
 /* Projected frequency-domain waveform of ONE parameter point on every detector
  * (Waveform.compute_hphc + Detector.project_fdwave, waveform.py:270-395, detector.py:394-418).
  * out_h_host: [n_ifo][n_bins][2] (re, im), FP64 sin/cos.  Used for injections / SNR helpers. */

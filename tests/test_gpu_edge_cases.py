@@ -157,3 +157,39 @@ def test_posterior_and_pool_adapter_on_the_gpu():
     assert lnl_lnp[4] == (0.0, -np.inf)                 # inf/likelihood.py:79-80
     ll = np.array(pool.map(post.log_like, list(Xq[:8])))
     assert np.all(np.abs(ll - np.array([ref_post.log_like(x) for x in Xq[:8]])) <= harness.tolerance(ll))
+
+
+def test_frequency_split_partial_sums_recombine():
+    """The frequency-axis split used for small batches on several GPUs, emulated on one GPU: partial sums of disjoint
+    chunk ranges, added (the all-reduce), then the epilogue == the single-call result to rounding."""
+    import torch
+    cfg = syn.CONFIGS["C2_small"]
+    ex = syn.extras_setup(cfg, 4, 3)
+    cl = syn.product_classes()
+    like = GWLikelihood(*syn.build_network(cfg, cl), cfg["srate"], cfg["seglen"], cfg["approx"], **ex)
+    X, names = syn.draw_walkers(cfg, 50, 9, "narrow")
+    Xe, ne = syn.extras_columns(cfg, 50, 10, 4, 3)
+    X, names = np.ascontiguousarray(np.concatenate([X, Xe], axis=1)), names + ne
+    const = syn.constants(cfg)
+    whole = like.log_like_batch(X, names, const)
+    dev = torch.device("cuda", 0)
+    pm = like.param_map(names, const)
+    xd = torch.from_numpy(X).to(dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    nch = like.engine.num_chunks()
+    assert nch >= 3
+    cuts = [0, nch // 3, nch // 3, 2 * nch // 3 + 1, nch]            # includes an empty range
+    total = torch.zeros((2 * len(like.ifos), len(X)), dtype=torch.float64, device=dev)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = torch.empty_like(total)
+        like.engine.partial_device(xd.data_ptr(), len(X), X.shape[1], pm, a, b, part.data_ptr(), st)
+        total += part
+    out = torch.empty(len(X), dtype=torch.float64, device=dev)
+    like.engine.finish_device(total.data_ptr(), len(X), out.data_ptr(), 0, st)
+    torch.cuda.synchronize(dev)
+    got = out.cpu().numpy()
+    assert np.all(np.abs(got - whole) <= 1e-9 * (np.abs(whole) + 1.0)), np.max(np.abs(got - whole))
+    # and the single-rank FrequencySplitEvaluator path
+    from bajes_b200.dist import FrequencySplitEvaluator
+    ev = FrequencySplitEvaluator(like, names, const)
+    assert np.array_equal(ev.evaluate(X), whole) or np.all(np.abs(ev.evaluate(X) - whole) <= 1e-9 * (np.abs(whole) + 1))
