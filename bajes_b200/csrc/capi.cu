@@ -12,6 +12,7 @@
 
 #include "kernels.cuh"
 #include "roq_relbin.cuh"
+#include "timemarg.cuh"
 
 using namespace bj;
 
@@ -19,6 +20,7 @@ using namespace bj;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
+static bj::CufftApi g_cufft;
 
 static int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -93,6 +95,14 @@ struct bj_ctx {
     double* d_dd_band = nullptr;
     double* d_spcal_freqs = nullptr;
     double* d_coef_ex = nullptr;
+    // time-shift marginalisation
+    int tm = 0;
+    long tm_n_full = 0, tm_offset = 0, tm_batch = 0;
+    double2* d_tm = nullptr;
+    double* d_tm_R = nullptr;
+    long cap_tm_R = 0;
+    int tm_plan = 0;
+    bool tm_plan_ok = false;
     // ROQ / relbin static tables
     RoqDevice roq;
     RelbinDevice relbin;
@@ -438,6 +448,15 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
     for (int b = 0; b < nw; ++b) c->dims.len_weights[b] = (int)ex->len_weights[b];
     c->cfg.f_lo = freqs[0];
     c->cfg.f_hi = freqs[n_bins - 1];
+    if (ex && ex->marg_time_shift) {
+        if (nsp || nw) { bj_destroy(c); return fail(BJ_ERR_UNSUPPORTED, "time-shift marginalisation with spcal / PSD weights"); }
+        if (cfg->sincos == BJ_SINCOS_FP64) { bj_destroy(c); return fail(BJ_ERR_UNSUPPORTED, "time-shift marginalisation uses the mixed-precision tables: choose sincos mufu or poly32"); }
+        if (ex->n_full < ex->band_offset + n_bins || ex->band_offset < 0) { bj_destroy(c); return fail(BJ_ERR_INVALID, "band [%lld, %lld) does not fit the full axis of %lld samples", (long long)ex->band_offset, (long long)(ex->band_offset + n_bins), (long long)ex->n_full); }
+        if (!g_cufft.load()) { bj_destroy(c); return fail(BJ_ERR_UNSUPPORTED, "time-shift marginalisation needs libcufft.so.11, which could not be loaded"); }
+        c->tm = 1;
+        c->tm_n_full = (long)ex->n_full;
+        c->tm_offset = (long)ex->band_offset;
+    }
 
     Layout L;
     if (build_layout(L, n_bins, freqs, ex)) { bj_destroy(c); return fail(BJ_ERR_INVALID, "len_weights do not cover the band"); }
@@ -533,6 +552,9 @@ extern "C" int bj_destroy(bj_ctx* c) {
     cudaFree(c->d_dd_band);
     cudaFree(c->d_spcal_freqs);
     cudaFree(c->d_coef_ex);
+    cudaFree(c->d_tm);
+    cudaFree(c->d_tm_R);
+    if (c->tm_plan_ok) g_cufft.Destroy(c->tm_plan);
     cudaFree(c->d_coef);
     cudaFree(c->d_partial);
     cudaFree(c->d_x);
@@ -686,6 +708,69 @@ static int launch_epilogue(bj_ctx* c, long n_walkers, cudaStream_t st, double* l
     return BJ_OK;
 }
 
+template <int NIFO, int MODEL, int SC>
+static void launch_tm_integrand(bj_ctx* c, long w0, long n_sub, cudaStream_t st) {
+    dim3 grid((unsigned)c->n_chunks, (unsigned)((n_sub + kThreads - 1) / kThreads));
+    timemarg_integrand_kernel<NIFO, MODEL, SC><<<grid, kThreads, 0, st>>>(
+        c->cfg, (const unsigned char*)c->d_rec, c->d_chunks, c->n_bins, c->d_coef, c->cap_walkers, w0, n_sub,
+        c->tm_n_full, c->tm_offset, c->d_tm);
+}
+template <int NIFO, int MODEL>
+static void launch_tm_integrand_sc(bj_ctx* c, long w0, long n_sub, cudaStream_t st) {
+    if (c->sincos == BJ_SINCOS_MUFU) launch_tm_integrand<NIFO, MODEL, BJ_SINCOS_MUFU>(c, w0, n_sub, st);
+    else                             launch_tm_integrand<NIFO, MODEL, BJ_SINCOS_POLY32>(c, w0, n_sub, st);
+}
+template <int NIFO>
+static void launch_tm_integrand_m(bj_ctx* c, long w0, long n_sub, cudaStream_t st) {
+    if (c->cfg.approx == BJ_APPROX_TAYLORF2_35PN) launch_tm_integrand_sc<NIFO, MODEL_35>(c, w0, n_sub, st);
+    else                                          launch_tm_integrand_sc<NIFO, MODEL_GENERIC>(c, w0, n_sub, st);
+}
+
+// time-marginalised logL of walkers [0, n_walkers): sub-batches of integrand -> batched FFT -> logsumexp
+static int run_timemarg(bj_ctx* c, long n_walkers, cudaStream_t st, double* out_logl_dev) {
+    if (!c->d_tm) {
+        // sub-batch: at most ~2 GiB of complex128 spectra
+        long b = (long)((2LL << 30) / (c->tm_n_full * (long)sizeof(double2)));
+        if (b < 1) b = 1;
+        if (b > 1024) b = 1024;
+        c->tm_batch = b;
+        CUDA_TRY(cudaMalloc(&c->d_tm, (size_t)b * c->tm_n_full * sizeof(double2)));
+        int n = (int)c->tm_n_full;
+        if (g_cufft.PlanMany(&c->tm_plan, 1, &n, nullptr, 1, n, nullptr, 1, n, kCufftZ2Z, (int)b) != 0)
+            return fail(BJ_ERR_CUDA, "cufftPlanMany(n=%d, batch=%ld) failed", n, b);
+        c->tm_plan_ok = true;
+    }
+    if (n_walkers > c->cap_tm_R) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(c->d_tm_R);
+        c->d_tm_R = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_tm_R, (size_t)n_walkers * sizeof(double)));
+        c->cap_tm_R = n_walkers;
+    }
+    if (g_cufft.SetStream(c->tm_plan, st) != 0) return fail(BJ_ERR_CUDA, "cufftSetStream failed");
+    for (long w0 = 0; w0 < n_walkers; w0 += c->tm_batch) {
+        const long n_sub = std::min(c->tm_batch, n_walkers - w0);
+        // the plan always transforms tm_batch rows; rows beyond n_sub are zero and ignored
+        CUDA_TRY(cudaMemsetAsync(c->d_tm, 0, (size_t)c->tm_batch * c->tm_n_full * sizeof(double2), st));
+        switch (c->cfg.n_ifo) {
+            case 1: launch_tm_integrand_m<1>(c, w0, n_sub, st); break;
+            case 2: launch_tm_integrand_m<2>(c, w0, n_sub, st); break;
+            default: launch_tm_integrand_m<3>(c, w0, n_sub, st); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        if (g_cufft.ExecZ2Z(c->tm_plan, c->d_tm, c->d_tm, kCufftForward) != 0) return fail(BJ_ERR_CUDA, "cufftExecZ2Z failed");
+        timemarg_reduce_kernel<<<(unsigned)n_sub, 256, 0, st>>>(c->d_tm, c->tm_n_full, c->cfg.marg_phi_ref, w0, c->d_tm_R);
+        CUDA_TRY(cudaGetLastError());
+    }
+    timemarg_finish_kernel<<<(unsigned)((n_walkers + 127) / 128), 128, 0, st>>>(c->cfg, c->d_gram, c->d_coef, c->cap_walkers,
+                                                                                n_walkers, c->d_tm_R, out_logl_dev);
+    CUDA_TRY(cudaGetLastError());
+    c->launch_info[0] = c->n_chunks; c->launch_info[1] = (int)c->tm_batch; c->launch_info[2] = kThreads; c->launch_info[3] = 0;
+    c->launch_info[4] = c->bins_per_chunk; c->launch_info[5] = c->n_chunks; c->launch_info[6] = (int)(c->tm_n_full & 0x7fffffff);
+    c->launch_info[7] = 300;
+    return BJ_OK;
+}
+
 static int check_extra_map(const bj_ctx* c, const bj_extra_map* em, int ndim) {
     const bool need = c->dims.nspcal > 0 || c->dims.nweights > 0;
     if (need && !em)
@@ -723,7 +808,11 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
                                                      c->d_coef_ex, c->cap_walkers);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], st));
-    if (c->kind == KIND_FULLGRID) {
+    if (c->kind == KIND_FULLGRID && c->tm) {
+        rc = run_timemarg(c, n_walkers, st, out_logl_dev);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    } else if (c->kind == KIND_FULLGRID) {
         rc = launch_fullgrid(c, n_walkers, st, 0, c->n_chunks);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[2], st));

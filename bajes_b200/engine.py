@@ -71,7 +71,9 @@ class bj_config(C.Structure):
 
 class bj_extras(C.Structure):
     _fields_ = [("nspcal", C.c_int32), ("nweights", C.c_int32),
-                ("spcal_freqs", C.POINTER(C.c_double)), ("len_weights", C.POINTER(C.c_int64))]
+                ("spcal_freqs", C.POINTER(C.c_double)), ("len_weights", C.POINTER(C.c_int64)),
+                ("marg_time_shift", C.c_int32), ("reserved", C.c_int32),
+                ("n_full", C.c_int64), ("band_offset", C.c_int64)]
 
 
 class bj_extra_map(C.Structure):
@@ -309,7 +311,8 @@ class Engine:
 
     # -- constructors --------------------------------------------------------------------------
     @classmethod
-    def fullgrid(cls, cfg: bj_config, freqs, datas, psds, spcal_freqs=None, len_weights=None) -> "Engine":
+    def fullgrid(cls, cfg: bj_config, freqs, datas, psds, spcal_freqs=None, len_weights=None,
+                 marg_time_shift=False, n_full=0, band_offset=0) -> "Engine":
         lib = load_library()
         freqs = _as_f64(freqs)
         d_ri = [np.ascontiguousarray(np.asarray(d, dtype=np.complex128)).view(np.float64) for d in datas]
@@ -327,8 +330,10 @@ class Engine:
         if len_weights is not None and len(len_weights) > 0:
             lw = np.ascontiguousarray(len_weights, dtype=np.int64)
             ex.nweights, ex.len_weights = lw.size, lw.ctypes.data_as(C.POINTER(C.c_int64))
+        if marg_time_shift:
+            ex.marg_time_shift, ex.n_full, ex.band_offset = 1, int(n_full), int(band_offset)
         _check(lib, lib.bj_create_ex(C.byref(h), C.byref(cfg), freqs.size, _ptr(freqs), _ptr_array(d_ri), _ptr_array(p),
-                                     C.byref(ex) if (sf is not None or lw is not None) else None),
+                                     C.byref(ex) if (sf is not None or lw is not None or marg_time_shift) else None),
                "bj_create_ex")
         return cls(h, cfg.n_ifo, "fullgrid", freqs.size)
 

@@ -62,9 +62,9 @@ class GWLikelihood(Likelihood):
 
         if self.roq is not None and self.marg_time_shift:
             raise AttributeError("Time-shift marginalization has not been implemented with the ROQ approximation.")
-        if self.marg_time_shift:
-            raise NotImplementedError("time-shift marginalisation needs the per-bin <d|h> array + FFT per point and "
-                                      "is not part of the fused GPU likelihood (SURVEY.md section 8e/f N4)")
+        if self.marg_time_shift and (nspcal or nweights):
+            raise NotImplementedError("time-shift marginalisation together with calibration envelopes / PSD weights is "
+                                      "not implemented on the GPU; there is no CPU fallback")
         if (nspcal or nweights) and roq is not None:
             raise AttributeError("The ROQ approximation has not yet been extended to incorporate calibration "
                                  "uncertainties.")          # bajes/pipe/__init__.py:737-739
@@ -99,6 +99,10 @@ class GWLikelihood(Likelihood):
             self.logZ_noise += -0.5 * self.dets[ifo]._dd
             self.Nfr = n_freqs
             mask = datas[ifo].mask
+        idx = np.asarray(mask[0] if isinstance(mask, tuple) else mask)
+        self._band_offset = int(idx[0]) if len(idx) else 0
+        if self.marg_time_shift and len(idx) and not np.array_equal(idx, np.arange(idx[0], idx[0] + len(idx))):
+            raise NotImplementedError("time-shift marginalisation needs a contiguous in-band mask")
 
         freqs = np.asarray(freqs)
         if self.roq is not None:
@@ -125,7 +129,9 @@ class GWLikelihood(Likelihood):
             self._engine = _engine.Engine.fullgrid(cfg, d0.freqs,
                                                    [self.dets[i].data for i in self.ifos],
                                                    [self.dets[i].psd for i in self.ifos],
-                                                   spcal_freqs=self.spcal_freqs, len_weights=self.len_weights)
+                                                   spcal_freqs=self.spcal_freqs, len_weights=self.len_weights,
+                                                   marg_time_shift=self.marg_time_shift, n_full=self.Nfr,
+                                                   band_offset=self._band_offset)
         else:
             from .roq import spline_tables
             knots, coefs, tc_min, tc_max = [], [], None, None

@@ -130,6 +130,15 @@ typedef struct {
     int32_t nweights;             /* 0 = no PSD weights, else 1..BJ_MAX_WEIGHTS                   */
     const double*  spcal_freqs;   /* [nspcal] ascending node frequencies                          */
     const int64_t* len_weights;   /* [nweights] bins per band, sum == n_bins                      */
+    /* time-shift marginalisation (GWLikelihood(marg_time_shift=True), pipe/log_like.py:135-156): the per-bin
+     * <d|h> integrand summed over detectors is placed on the full one-sided axis of n_full samples (zeros outside
+     * the band, which starts at band_offset), Fourier transformed (numpy.fft.fft convention, length n_full) and
+     * R = logsumexp_m(Re S[m] - ln n_full)  (or ln I0|S[m]| with marg_phi_ref).  Needs libcufft at run time
+     * (loaded lazily); not combinable with spcal / weights / ROQ. */
+    int32_t marg_time_shift;
+    int32_t reserved;
+    int64_t n_full;               /* len(series.freqs): T * srate / 2 + 1                          */
+    int64_t band_offset;          /* index of the first in-band bin on that axis                   */
 } bj_extras;
 
 /* where the per-point values of 'spcal_amp{j}_{ifo}', 'spcal_phi{j}_{ifo}', 'weight{b}_{ifo}' live:

@@ -187,8 +187,32 @@ def gen_extras():
     np.savez_compressed(os.path.join(GOLDEN, "extras_small.npz"), **_det_constants(dets, cfg["ifos"]), **out)
 
 
+def gen_tmarg():
+    """Time-shift marginalised likelihood (log_like.py:135-156) on C1 and the reduced C2."""
+    shims.import_reference()
+    from bajes.pipe.log_like import GWLikelihood
+    out = {}
+    for name, n_narrow, n_wide in (("C1", 48, 16), ("C2_small", 24, 8)):
+        cfg = syn.CONFIGS[name]
+        cl = harness.reference_classes()
+        net = syn.build_network(cfg, cl)
+        const = syn.constants(cfg)
+        X, names = _walkers(cfg, n_narrow, n_wide, 61)
+        for mphi in (False, True):
+            like = GWLikelihood(net[0], net[1], net[2], net[3], net[4], cfg["srate"], cfg["seglen"], cfg["approx"],
+                                marg_time_shift=True, marg_phi_ref=mphi)
+            with np.errstate(all="ignore"):
+                out["logl_%s_mphi%d" % (name, int(mphi))] = harness.eval_batch(like, X, names, const)
+        out["X_" + name] = X
+        out["names"] = np.array(names)
+        out["gmst_" + name] = np.array([net[2][i].gmst_reference for i in cfg["ifos"]])
+        out["sday_" + name] = np.array([net[2][i].sday for i in cfg["ifos"]])
+        print("  tmarg %s: finite %d/%d" % (name, np.isfinite(out["logl_%s_mphi0" % name]).sum(), len(X)))
+    np.savez_compressed(os.path.join(GOLDEN, "tmarg.npz"), **out)
+
+
 def main(argv):
-    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq", "extras"}
+    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq", "extras", "tmarg"}
     os.makedirs(GOLDEN, exist_ok=True)
     if "asd" in what:
         write_design_asd()
@@ -205,6 +229,8 @@ def main(argv):
         gen_roq()
     if "extras" in what:
         gen_extras()
+    if "tmarg" in what:
+        gen_tmarg()
 
 
 if __name__ == "__main__":

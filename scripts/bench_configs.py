@@ -64,13 +64,14 @@ def emit(rec, fh):
         fh.flush()
 
 
-def fullgrid(name, fh, sincos="mufu", walkers=None, approx=None, nspcal=0, nweights=0):
+def fullgrid(name, fh, sincos="mufu", walkers=None, approx=None, nspcal=0, nweights=0, tmarg=False):
     cfg = dict(syn.CONFIGS[name])
     if approx:
         cfg["approx"] = approx
     cl = syn.product_classes()
     ex = syn.extras_setup(cfg, nspcal, nweights)
-    like = GWLikelihood(*syn.build_network(cfg, cl), cfg["srate"], cfg["seglen"], cfg["approx"], sincos=sincos, **ex)
+    like = GWLikelihood(*syn.build_network(cfg, cl), cfg["srate"], cfg["seglen"], cfg["approx"], sincos=sincos,
+                        marg_time_shift=tmarg, **ex)
     W = walkers or cfg["n_walkers"]
     X, names = syn.draw_walkers(cfg, W, 5, "narrow")
     if nspcal or nweights:
@@ -81,7 +82,7 @@ def fullgrid(name, fh, sincos="mufu", walkers=None, approx=None, nspcal=0, nweig
     host_ms = time_host(like, X, names, const)
     nb = like.engine.n_bins
     emit({"config": name, "kind": "fullgrid", "approx": cfg["approx"], "sincos": sincos, "walkers": W, "n_bins": nb,
-          "nspcal": nspcal, "nweights": nweights, "ndim": X.shape[1],
+          "nspcal": nspcal, "nweights": nweights, "ndim": X.shape[1], "marg_time_shift": tmarg,
           "n_ifo": len(cfg["ifos"]), "step_ms_device": step_ms, "kernel_ms": kms, "step_ms_host_api": host_ms,
           "walker_bins_per_s": W * nb / (step_ms * 1e-3), "evals_per_s": W / (step_ms * 1e-3),
           "launch": like.engine.last_launch_info()}, fh)
@@ -165,6 +166,9 @@ if __name__ == "__main__":
         fullgrid("C2", fh, nspcal=10)
         fullgrid("C2", fh, nweights=8)
         fullgrid("C2", fh, nspcal=10, nweights=8)
+    if want("tmarg"):
+        fullgrid("C2", fh, tmarg=True, walkers=1024)
+        fullgrid("C1", fh, tmarg=True, walkers=4096)
     if want("c3"):
         roq_c3(fh)
     if want("c4"):

@@ -321,6 +321,29 @@ def test_calibration_envelopes_and_psd_weights(key, sincos):
     assert one[0] == got[5]
 
 
+# ------------------------------------------------------------------------------------------------------
+# time-shift marginalisation (log_like.py:135-156), against reference golden vectors
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sincos", ["mufu", "poly32"])
+@pytest.mark.parametrize("name", ["C1", "C2_small"])
+@pytest.mark.parametrize("mphi", [False, True])
+def test_time_marginalised_likelihood(name, mphi, sincos):
+    cfg = syn.CONFIGS[name]
+    gold = load_golden("tmarg.npz")
+    cl = harness.port_classes(gmst_reference=float(gold["gmst_" + name][0]), sday=float(gold["sday_" + name][0]))
+    net = syn.build_network(cfg, cl)
+    ifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"],
+                        marg_time_shift=True, marg_phi_ref=mphi, sincos=sincos)
+    names = [str(n) for n in gold["names"]]
+    X, const = gold["X_" + name], syn.constants(cfg)
+    got = like.log_like_batch(X, names, const)
+    _check(got, gold["logl_%s_mphi%d" % (name, int(mphi))], "tmarg %s mphi=%s %s" % (name, mphi, sincos))
+    p = {k: float(v) for k, v in zip(names, X[1])}
+    p.update(const)
+    assert like.log_like(dict(p)) == got[1]
+
+
 def test_engine_reports_launch_and_timing():
     cfg = syn.CONFIGS["C1"]
     gold = load_golden("c1_bbh.npz")

@@ -148,3 +148,19 @@ def test_calibration_envelopes_and_psd_weights(key):
     with np.errstate(all="ignore"):
         got = harness.eval_batch(like, gold["X_" + key], names, syn.constants(cfg))
     _assert_close(got, gold["logl_" + key], "extras " + key)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2_small"])
+@pytest.mark.parametrize("mphi", [False, True])
+def test_time_marginalised_likelihood(name, mphi):
+    """log_like.py:135-156: FFT of the per-bin <d|h> on the full one-sided axis + logsumexp over lags."""
+    cfg = syn.CONFIGS[name]
+    gold = load_golden("tmarg.npz")
+    cl = harness.port_classes(gmst_reference=float(gold["gmst_" + name][0]), sday=float(gold["sday_" + name][0]))
+    net = syn.build_network(cfg, cl)
+    like = port.GWLikelihoodPort(net[0], net[1], net[2], net[3], net[4], cfg["srate"], cfg["seglen"], cfg["approx"],
+                                 marg_time_shift=True, marg_phi_ref=mphi)
+    names = [str(n) for n in gold["names"]]
+    with np.errstate(all="ignore"):
+        got = harness.eval_batch(like, gold["X_" + name], names, syn.constants(cfg))
+    _assert_close(got, gold["logl_%s_mphi%d" % (name, int(mphi))], "tmarg %s mphi=%s" % (name, mphi))
