@@ -48,6 +48,9 @@ class BoxPrior(object):
     def prior_transform(self, u):
         return self._lo + np.asarray(u) * (self._hi - self._lo)
 
+    def prior_transform_batch(self, U):
+        return self._lo + np.asarray(U, dtype=float) * (self._hi - self._lo)
+
 
 class EnsembleSampler(object):
     """Goodman-Weare stretch move on two half-ensembles; every likelihood evaluation goes through

@@ -243,6 +243,11 @@ class Posterior(object):
     def prior_transform(self, u):
         return self.prior.prior_transform(u)
 
+    def prior_transform_batch(self, U):
+        if hasattr(self.prior, "prior_transform_batch"):
+            return np.asarray(self.prior.prior_transform_batch(U), dtype=np.float64)
+        return np.stack([np.asarray(self.prior.prior_transform(u), dtype=np.float64) for u in U])
+
     def _fill(self, x):
         return self.prior.this_sample({k: v for k, v in zip(self.prior.names, x)})
 

@@ -5,8 +5,9 @@ Every wrapper in bajes/inf/sampler/ evaluates points through ``pool.map(fn, poin
 ``fn`` one of ``posterior.log_like`` / ``log_post`` / ``log_likeprior`` (SURVEY.md section 3.4:
 emcee.py:175, ptmcmc.py:274, ultranest.py:41-42, dynesty.py:140).  ``BatchedPool.map`` recognises those
 bound methods, stacks the iterable into one [W, ndim] array, makes ONE batched call and returns the
-results in input order -- the contract of ``MPIPool.map`` (bajes/pipe/utils/mpi.py:120-159).  Anything
-else is mapped serially.
+results in input order -- the contract of ``MPIPool.map`` (bajes/pipe/utils/mpi.py:120-159).  dynesty's
+``pool.map(evolve_point, args)`` is recognised as well when ``evolve_point`` is ``LockstepRandomWalk.propose``
+(rwalk.py): the chains of one queue are advanced in lock-step.  Anything else is mapped serially.
 
 It subclasses ``multiprocessing.pool.Pool`` only nominally (no worker processes are started) because
 ultranest's wrapper insists on ``isinstance(pool, multiprocessing.pool.Pool)`` (ultranest.py:92-96).
@@ -37,6 +38,9 @@ class BatchedPool(multiprocessing.pool.Pool):
     def map(self, func, iterable, chunksize=None):
         owner = getattr(func, "__self__", None)
         name = getattr(func, "__name__", "")
+        if name in ("propose", "sample_rwalk") and hasattr(owner, "propose_batch"):
+            # dynesty's evolve_point fan-out (dynesty.py:244, :406-407): all chains advance in lock-step (rwalk.py)
+            return owner.propose_batch(list(iterable))
         batched = _BATCHED.get(name)
         if owner is not None and batched is not None and hasattr(owner, batched):
             if isinstance(iterable, np.ndarray) and iterable.ndim == 2:

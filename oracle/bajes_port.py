@@ -820,3 +820,77 @@ class GWBinningLikelihoodPort:
             return -np.inf
         r = _log_i0(np.abs(dh)) if self.marg_phi_ref else np.real(dh)
         return float(np.real(r - 0.5 * hh))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dynesty random-walk proposal (bajes/inf/sampler/dynesty.py:503-614), ONE chain, sequential -- the checker
+# of the product's lock-step version (bajes_b200/rwalk.py).  ``rstate`` stands for the global ``numpy.random``
+# the reference draws from (same legacy generator, same call sequence).
+# ---------------------------------------------------------------------------------------------------------
+
+def _nmcmc_port(accept_ratio, old_act, maxmcmc, safety=5):
+    """inf/utils.py:140-161."""
+    tau = maxmcmc / safety
+    if accept_ratio == 0.0:
+        exact = (1 + 1 / tau) * old_act
+    else:
+        exact = float(min((1.0 - 1.0 / tau) * old_act + (safety / tau) * (2.0 / accept_ratio - 1.0), maxmcmc))
+    return max(safety, int(exact))
+
+
+def _inside_port(u, nonbounded):
+    """dynesty.py:27-42."""
+    if nonbounded is not None and not np.any(nonbounded):
+        nonbounded = None
+    if nonbounded is None:
+        return u.min() > 0 and u.max() < 1
+    hard, soft = u[nonbounded], u[~nonbounded]
+    return hard.min() > 0 and hard.max() < 1 and soft.min() > -0.5 and soft.max() < 1.5
+
+
+def sample_rwalk_port(args, maxmcmc, walks, nact, rstate):
+    u, loglstar, axes, scale, prior_transform, loglikelihood, _seedseq, kwargs = args
+    nonbounded, periodic, reflective = kwargs.get("nonbounded"), kwargs.get("periodic"), kwargs.get("reflective")
+    n = len(u)
+    n_acc = n_rej = n_out = 0
+    act = np.inf
+    chain = []                                   # (u, v, logl) per recorded step
+    here = None
+    while 0.5 * nact * act >= len(chain):
+        direction = rstate.randn(n)
+        direction /= np.linalg.norm(direction)
+        step = direction * rstate.rand() ** (1.0 / n)
+        trial = u + scale * np.dot(axes, step)
+        if periodic is not None:
+            trial[periodic] = np.mod(trial[periodic], 1)
+        if reflective is not None:
+            x = trial[reflective]
+            even = np.mod(x, 2) < 1
+            trial[reflective] = np.where(even, np.mod(x, 1), 1 - np.mod(x, 1))
+        if not _inside_port(trial, nonbounded):
+            n_out += 1
+            if n_acc > 0:
+                chain.append(here)
+            continue
+        v_trial = prior_transform(np.array(trial))
+        l_trial = loglikelihood(np.array(v_trial))
+        if l_trial > loglstar:
+            u = trial
+            here = (trial, v_trial, l_trial)
+            n_acc += 1
+            chain.append(here)
+        else:
+            n_rej += 1
+            if n_acc > 0:
+                chain.append(here)
+        if n_acc + n_rej > walks and n_acc > 1:
+            act = _nmcmc_port(n_acc / (n_acc + n_rej + n_out), walks, maxmcmc)
+        if n_acc + n_rej > maxmcmc:
+            break
+    if np.isfinite(act) and int(0.5 * nact * act) < len(chain):
+        u_out, v_out, l_out = chain[rstate.randint(int(0.5 * nact * act), len(chain))]
+    else:
+        u_out = rstate.uniform(size=n)
+        v_out = prior_transform(u_out)
+        l_out = loglikelihood(v_out)
+    return u_out, v_out, l_out, n_acc + n_rej, {"accept": n_acc, "reject": n_rej, "fail": n_out, "scale": scale}

@@ -211,8 +211,39 @@ def gen_tmarg():
     np.savez_compressed(os.path.join(GOLDEN, "tmarg.npz"), **out)
 
 
+def gen_rwalk():
+    """dynesty random-walk proposal (dynesty.py:503-614): the unmodified ``sample_rwalk`` on seeded toy chains.
+    dynesty itself is not installable offline; the proposal only reads ``dynesty.__version__`` (:511), so a stub
+    module carrying a version string is registered before the import."""
+    import types
+    shims.import_reference()
+    if "dynesty" not in sys.modules:
+        stub = types.ModuleType("dynesty")
+        stub.__version__ = "1.2.3"
+        sys.modules["dynesty"] = stub
+    import logging
+    logging.disable(logging.WARNING)
+    from bajes.inf.sampler.dynesty import BajesDynestyProposal
+    from oracle import rwalk_cases as rc
+    out = {}
+    for group, g in rc.GROUPS.items():
+        args, seeds = rc.make_args(group)
+        prop = BajesDynestyProposal(g["maxmcmc"], walks=g["walks"], nact=g["nact"])
+        rows = []
+        for a, s in zip(args, seeds):
+            np.random.seed(s)
+            u, v, logl, ncall, blob = prop.propose(a)
+            rows.append(np.concatenate([u, v, [logl, ncall, blob["accept"], blob["reject"], blob["fail"], blob["scale"]]]))
+        out[group] = np.array(rows)
+        r = out[group]
+        print("  rwalk %-10s chains %2d  accept %s  fail %s" % (group, len(rows), r[:, -4].astype(int).tolist()[:8],
+                                                                 r[:, -2].astype(int).tolist()[:8]))
+    logging.disable(logging.NOTSET)
+    np.savez_compressed(os.path.join(GOLDEN, "rwalk.npz"), **out)
+
+
 def main(argv):
-    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq", "extras", "tmarg"}
+    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq", "extras", "tmarg", "rwalk"}
     os.makedirs(GOLDEN, exist_ok=True)
     if "asd" in what:
         write_design_asd()
@@ -231,6 +262,8 @@ def main(argv):
         gen_extras()
     if "tmarg" in what:
         gen_tmarg()
+    if "rwalk" in what:
+        gen_rwalk()
 
 
 if __name__ == "__main__":

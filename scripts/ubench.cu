@@ -26,6 +26,13 @@ __global__ void k(const double* in, double* out) {
                 if (MODE == 8) { a[i] = fma(a[i], b[i], c[i]); fa[i] = __int2float_rn(ia[i]); ia[i] += 3; }   // DFMA + I2FP + IADD
                 if (MODE == 9) { a[i] = fma(a[i], b[i], c[i]); double d = (double)fa[i]; fa[i] += fb[i]; c[i] += d*1e-30; } // DFMA+F2F+FADD+DFMA
                 if (MODE == 10) a[i] = a[i] * b[i];                              // DMUL 2 regs
+                if (MODE == 12) { asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(fa[i])); }                       // MUFU.SIN
+                if (MODE == 13) { a[i] = fma(a[i], b[0], c[i]); asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(fa[i])); }
+                if (MODE == 14) { a[i] = fma(a[i], b[0], c[i]); c[i] = fma(c[i], b[1], a[(i+1)&7]); a[i] = fma(a[i], b[2], c[i]);
+                                  asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(fa[i])); }                         // 3 DFMA : 1 MUFU
+                if (MODE == 15) { a[i] = fma(a[i], b[0], c[i]); c[i] = fma(c[i], b[1], a[(i+1)&7]); a[i] = fma(a[i], b[2], c[i]);
+                                  asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(fa[i]));
+                                  fb[i] = fmaf(fb[i], fa[(i+1)&7], fb[(i+2)&7]); fb[i] = fmaf(fb[i], fa[(i+3)&7], fb[(i+5)&7]); }  // + 2 FFMA
                 if (MODE == 11) { a[i] = fma(a[i], b[i], c[i]); c[i] = fma(c[i], b[(i+1)&7], a[(i+3)&7]); }
             }
         }
@@ -61,5 +68,9 @@ int main() {
     run<7>("FFMA2 r,r,r", 1, in, out, sms);
     run<8>("DFMA + I2FP + IADD (triples)", 1, in, out, sms);
     run<9>("DFMA+F2F+FADD+DFMA (quads)", 1, in, out, sms);
+    run<12>("MUFU.SIN", 1, in, out, sms);
+    run<13>("DFMA + MUFU (pairs)", 1, in, out, sms);
+    run<14>("3 DFMA + MUFU (quads)", 1, in, out, sms);
+    run<15>("3 DFMA + MUFU + 2 FFMA (groups)", 1, in, out, sms);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 }
