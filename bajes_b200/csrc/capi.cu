@@ -82,6 +82,8 @@ struct bj_ctx {
     int rec_doubles = 0;
     double calib[2] = {0.0, 0.0}; // measured phasor bias (eps_a, eps_p)
     void* d_rec = nullptr;
+    void* d_tile_basis = nullptr; // tables of the tensor-core kernel; null: Horner kernels only
+    void* d_tile_data = nullptr;
     double* d_freqs = nullptr;
     double* d_gram = nullptr;
     int bins_per_chunk = 0;
@@ -388,6 +390,58 @@ static int build_records_mixed(std::vector<unsigned char>& rec, const Layout& L,
     return 0;
 }
 
+// tables of the tensor-core kernel (kernels.cuh: TileRec): basis[bin][K] -- the K basis values of the phase GEMM in the
+// order of tile_basis_slot<MODEL>, products formed in long double from the same (u, L, w5) the Horner kernels read --
+// and data[bin] = f, the FP32 pair slot and the scaled data weights of build_records_mixed (same 2^-e)
+template <int MODEL>
+static void build_records_tile(std::vector<double>& tab_basis, std::vector<unsigned char>& rec, const Layout& L,
+                               const double* freqs, const double* const* data_ri, const double* const* psd,
+                               double seglen, int nifo, int e2) {
+    using R = TileRec<MODEL>;
+    constexpr int RB = R::kDataBytes;
+    const size_t n = L.slot_bin.size();
+    rec.assign(n * RB, 0);
+    tab_basis.assign(n * R::K, 0.0);
+    const double four_over_t = 4.0 / seglen;
+    const double sc = std::ldexp(1.0, -e2);
+    for (size_t sidx = 0; sidx < n; ++sidx) {
+        const long k = L.slot_bin[sidx];
+        const BinStatics b = bin_statics(freqs[k], seglen);
+        unsigned char* r = &rec[sidx * RB];
+        double* basis = &tab_basis[sidx * R::K];
+        long double up[16];
+        up[0] = 1.0L;
+        for (int j = 1; j < 16; ++j) up[j] = up[j - 1] * (long double)b.u;
+        const long double w5 = b.w5, Lg = b.L;
+        if (MODEL == MODEL_35) {
+            const int ex[9] = {0, 2, 3, 4, 5, 6, 7, 10, 12};
+            for (int j = 0; j < 9; ++j) basis[j] = (double)(w5 * up[ex[j]]);
+            basis[9] = (double)Lg;
+            basis[10] = (double)(Lg * up[1]);
+            basis[11] = 1.0;
+        } else {
+            for (int j = 0; j < 16; ++j) basis[j] = (double)(w5 * up[j]);
+            for (int j = 0; j < 7; ++j) basis[16 + j] = (double)(Lg * up[j]);
+            basis[23] = (double)(Lg * Lg * up[3]);
+            basis[24] = 1.0;
+        }
+        memcpy(r + R::kF, &b.f, 8);
+        const size_t se = sidx & ~(size_t)1, so = se + 1;
+        const BinStatics be = bin_statics(freqs[L.slot_bin[se]], seglen);
+        const BinStatics bo = bin_statics(freqs[L.slot_bin[so < n ? so : se]], seglen);
+        float hf[2];
+        if ((sidx & 1) == 0) { hf[0] = (float)be.u; hf[1] = (float)bo.u; }
+        else                 { hf[0] = (float)be.L; hf[1] = (float)bo.L; }
+        memcpy(r + R::kPair, hf, 8);
+        for (int i = 0; i < nifo; ++i) {
+            double wr = 0.0, wi = 0.0;
+            if (L.slot_real[sidx]) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            const float d2[2] = {(float)(wr * sc), (float)(wi * sc)};
+            memcpy(r + R::kData + 8 * i, d2, 8);
+        }
+    }
+}
+
 template <int SC>
 static int calibrate(double* eps2) {
     double* d = nullptr;
@@ -513,6 +567,21 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
         c->calib[1] = eps[1];
         rec_ptr = recm.data();
         rec_bytes = recm.size();
+        // no calibration envelopes: the tensor-core kernel (phase as an FP64 GEMM) is the production path
+        if (nsp == 0 && !getenv("BAJES_B200_NO_TC")) {
+            std::vector<unsigned char> rect;
+            std::vector<double> basis;
+            if (cfg->approx == BJ_APPROX_TAYLORF2_35PN) build_records_tile<MODEL_35>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2);
+            else                                        build_records_tile<MODEL_GENERIC>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2);
+            cudaError_t et = cudaMalloc(&c->d_tile_data, rect.size());
+            if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_data, rect.data(), rect.size(), cudaMemcpyHostToDevice);
+            if (et == cudaSuccess) et = cudaMalloc(&c->d_tile_basis, basis.size() * sizeof(double));
+            if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_basis, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice);
+            if (et != cudaSuccess) {
+                bj_destroy(c);
+                return fail(BJ_ERR_CUDA, "uploading the tensor-core tables failed: %s", cudaGetErrorString(et));
+            }
+        }
     }
     cudaError_t e = cudaMalloc(&c->d_rec, rec_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, rec_ptr, rec_bytes, cudaMemcpyHostToDevice);
@@ -544,6 +613,8 @@ extern "C" int bj_destroy(bj_ctx* c) {
     if (!c) return BJ_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_rec);
+    cudaFree(c->d_tile_basis);
+    cudaFree(c->d_tile_data);
     cudaFree(c->d_freqs);
     cudaFree(c->d_gram);
     cudaFree(c->d_chunks);
@@ -614,10 +685,10 @@ static int check_map(const bj_param_map* m, int ndim) {
     return BJ_OK;
 }
 
-static void note_launch(bj_ctx* c, dim3 grid, size_t smem, int rec8, int model) {
+static void note_launch(bj_ctx* c, dim3 grid, size_t smem, int rec8, int model, int threads = kThreads) {
     c->launch_info[0] = (int)grid.x;
     c->launch_info[1] = (int)grid.y;
-    c->launch_info[2] = kThreads;
+    c->launch_info[2] = threads;
     c->launch_info[3] = (int)smem;
     c->launch_info[4] = c->bins_per_chunk;
     c->launch_info[5] = c->n_chunks;
@@ -645,16 +716,28 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
     const size_t smem = (size_t)kStages * kTileBins * RB + kStages * sizeof(uint64_t);
     auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC, false, SPCAL>;
     auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true, SPCAL>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(c1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
-    kern<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
-                                       c->d_partial, c->d_coef_ex, c->dims, c0);
+    if (!SPCAL && c->d_tile_basis) {
+        constexpr int RT = TileRec<MODEL>::kBasisBytes + TileRec<MODEL>::kDataBytes;
+        const size_t smem_t = (size_t)kStagesT * kTileBinsT * RT + kStagesT * sizeof(uint64_t);
+        auto tkern = fullgrid_tile_kernel<NIFO, MODEL, SC>;
+        CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        dim3 tgrid((unsigned)(c1 - c0), (unsigned)((n_walkers + kTileWalkers - 1) / kTileWalkers));
+        tkern<<<tgrid, kTileThreads, smem_t, st>>>((const unsigned char*)c->d_tile_basis, (const unsigned char*)c->d_tile_data,
+                                                   (const unsigned char*)c->d_rec, RB, c->d_chunks, c->d_coef,
+                                                   c->cap_walkers, n_walkers, c->d_partial, c0);
+        note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers,
+                                           n_walkers, c->d_partial, c->d_coef_ex, c->dims, c0);
+        note_launch(c, grid, smem, RB / 8, MODEL);
+    }
     // wide-phase fix-up: every CTA returns immediately unless the prologue flagged one of its walkers
     fixup<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers,
                                         n_walkers, c->d_partial, c->d_coef_ex, c->dims, c0);
     CUDA_TRY(cudaGetLastError());
-    note_launch(c, grid, smem, RB / 8, MODEL);
     return BJ_OK;
 }
 

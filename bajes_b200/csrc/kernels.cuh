@@ -763,6 +763,277 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
     }
 }
 
+// ---- the tensor-core kernel: the phase as an FP64 GEMM (the default production path) ------------------------------
+// The Horner kernels above are bound neither by a pipe nor by memory but by instruction issue / register-operand
+// bandwidth: B200 delivers one 64-bit register operand per lane and cycle (scripts/ubench_operands.cu: DFMA and FFMA2
+// with three distinct operands issue every 3 cycles, with one operand from the reuse cache every 2), so the ~56
+// instructions per walker and bin cost ~97 cycles per warp (profiles/r01_ablation.txt: removing every MUFU gains 7 %,
+// removing the phase gains 25 %).  The phase is LINEAR in the per-walker coefficients:
+//     Phi_c[w, k] = sum_n A[w, n] B[n, k],   B[n, k] = w5 u^j, L u^j, L^2 u^3, 1   (static per bin)
+// i.e. a [walkers x K] x [K x bins] GEMM with K = 12 (3.5PN) or 28 (5.5PN + tides), which the FP64 tensor cores
+// (DMMA.8x8x4, mma.sync.m8n8k4.f64) evaluate at the FLOP rate of DFMA with 1/8 of the instructions
+// (scripts/ubench_dmma.cu; tcgen05 has no FP64 kind, mma.sync IS the FP64 tensor path on sm_100a).
+//
+// Layout: a warp owns 8 walkers x 32 bins per step.  In the m8n8k4 accumulator fragment lane (g = lane / 4,
+// t = lane % 4) holds walker g and bins {8m + 2t, 8m + 2t + 1}, m = 0..3: ONE walker per lane (coefficients and
+// accumulators as in the kernels above), 8 bins per step, an (even, odd) pair per n-tile for the packed FP32
+// amplitude.  The four lanes of a walker are reduced by two shuffles at the end of the kernel.  A CTA = 8 warps = 64
+// walkers streams the chunk through a 3-stage TMA ring of 128 bins.
+// Two static tables (SoA, so that both access patterns are free of shared-memory bank conflicts):
+//   basis[bin][K]  f64      stride 96 B (K = 12) / 224 B (K = 28): the B-fragment load of a half warp (4 bins x 4
+//                           doubles) covers all 32 banks exactly once;
+//   data[bin]      48 B     [f : f64][pair slot : f32 x2][(dr, di) : f32 x2] x 3, 8 B padding: the four bins a
+//                           quarter warp reads (2 records = 24 words apart) fall into disjoint banks.
+// Every 128-bit load serves 8 walkers here instead of 32, and shared-memory wavefronts are what this kernel runs out
+// of: with the 16-byte (dr, di, di, -dr) entries of the Horner kernels it sat at 87 % of the LSU's cycles (5.04 ms),
+// hence the 8-byte entries and the two scalar FFMAs with a negated operand in the MAC.  (A hybrid that keeps one
+// walker per thread and transposes the accumulator fragments through shared memory was measured too: 5.49 ms,
+// against 5.59 ms for the Horner kernel; 4096 walkers x 521 729 bins x 3 detectors.)
+template <int MODEL> struct TileRec {
+    static constexpr int K = (MODEL == MODEL_35) ? 12 : 28;
+    static constexpr int kSteps = K / 4;
+    static constexpr int kBasisBytes = K * 8;
+    static constexpr int kDataBytes = 48;
+    static constexpr int kF = 0;
+    static constexpr int kPair = 8;
+    static constexpr int kData = 16;
+};
+static_assert(TileRec<MODEL_35>::kData + 8 * BJ_MAX_IFO <= TileRec<MODEL_35>::kDataBytes, "record too small");
+constexpr int kTileBinsT = 128;      // bins per TMA stage
+constexpr int kStagesT = 3;
+constexpr int kTileThreads = 256;
+constexpr int kTileWalkers = 64;     // 8 per warp
+constexpr int kStepBins = 32;
+
+// coefficient slot of basis function n (-1: zero padding); the host builds B in the same order (capi.cu)
+template <int MODEL>
+__host__ __device__ constexpr int tile_basis_slot(int n) {
+    if (MODEL == MODEL_35) {
+        // w5 u^{0,2,3,4,5,6,7,10,12}, L, L u, 1
+        return n == 0 ? C_A0 : n <= 6 ? C_A0 + n + 1 : n == 7 ? C_A0 + 10 : n == 8 ? C_A0 + 12
+             : n == 9 ? C_B0 : n == 10 ? C_B0 + 1 : C_K0;
+    }
+    // w5 u^0..15, L u^0..6, L^2 u^3, 1, 3 x padding
+    return n < 16 ? C_A0 + n : n < 23 ? C_B0 + (n - 16) : n == 23 ? C_C8 : n == 24 ? C_K0 : -1;
+}
+
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+template <int NIFO>
+struct TileWalker {
+    double tau[NIFO];
+    float q[6], q6l;
+};
+
+// one step: 8 walkers x 32 bins per warp.  `limit` = number of valid bins of the step (32 except at the ragged end
+// of a chunk; always even); GUARD = false compiles the test away.
+template <int NIFO, int MODEL, int SC, bool GUARD>
+__device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basis, const unsigned char* __restrict__ base,
+                                          const double (&afrag)[TileRec<MODEL>::kSteps], const TileWalker<NIFO>& w,
+                                          int g, int t, int limit, unsigned long long (&acc)[NIFO]) {
+    using R = TileRec<MODEL>;
+    constexpr int RB = R::kDataBytes;
+    // ---- phase: D[m][h] = turns (+ magic) of walker g at bin 8m + 2t + h ----
+    double D[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { D[m][0] = 0.0; D[m][1] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < R::kSteps; ++s) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const double b = *reinterpret_cast<const double*>(basis + (size_t)(8 * m + g) * R::kBasisBytes + (4 * s + t) * 8);
+            dmma884(D[m], afrag[s], b);
+        }
+    }
+    // ---- amplitude: packed FP32 Horner over the lane's four (even, odd) pairs ----
+    float Qf[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const unsigned char* re = base + (size_t)(8 * m + 2 * t) * RB;
+        const unsigned long long up = *reinterpret_cast<const unsigned long long*>(re + R::kPair);        // (uf0, uf1)
+        const unsigned long long lp = *reinterpret_cast<const unsigned long long*>(re + RB + R::kPair);   // (Lf0, Lf1)
+        unsigned long long q = fma2(pack2(w.q6l, w.q6l), lp, pack2(w.q[4], w.q[4]));
+        q = fma2(pack2(w.q[5], w.q[5]), up, q);
+        q = fma2(q, up, pack2(w.q[3], w.q[3]));
+        q = fma2(q, up, pack2(w.q[2], w.q[2]));
+        q = fma2(q, up, pack2(w.q[1], w.q[1]));
+        q = fma2(q, up, pack2(w.q[0], w.q[0]));
+        q = fma2(mul2(up, up), q, pack2(1.0f, 1.0f));
+        unpack2(q, Qf[m][0], Qf[m][1]);
+    }
+    // ---- per bin and detector: ramp, phasor, packed complex MAC ----
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (GUARD && 8 * m + 2 * t >= limit) continue;        // ring memory beyond the chunk is never used
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned char* rb = base + (size_t)(8 * m + 2 * t + h) * RB;
+            const double f = *reinterpret_cast<const double*>(rb + R::kF);
+            unsigned long long dd[NIFO];
+            if constexpr (NIFO >= 2) {
+                const ulonglong2 d01 = *reinterpret_cast<const ulonglong2*>(rb + R::kData);
+                dd[0] = d01.x;
+                dd[1] = d01.y;
+                if constexpr (NIFO == 3) dd[2] = *reinterpret_cast<const unsigned long long*>(rb + R::kData + 16);
+            } else {
+                dd[0] = *reinterpret_cast<const unsigned long long*>(rb + R::kData);
+            }
+#pragma unroll
+            for (int i = 0; i < NIFO; ++i) {
+                float cq, sq;
+                scaled_phasor_f32<SC>(__double2loint(fma(f, w.tau[i], D[m][h])), Qf[m][h], cq, sq);
+                // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
+                float dr, di, ar, ai;
+                unpack2(dd[i], dr, di);
+                unpack2(fma2(dd[i], pack2(cq, cq), acc[i]), ar, ai);
+                acc[i] = pack2(fmaf(di, sq, ar), fmaf(-dr, sq, ai));
+            }
+        }
+    }
+}
+
+template <int NIFO, int MODEL, int SC>
+__global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const unsigned char* __restrict__ tab_basis,
+                                                                  const unsigned char* __restrict__ tab_data,
+                                                                  const unsigned char* __restrict__ rec_ul,
+                                                                  int rec_ul_stride,
+                                                                  const ChunkDesc* __restrict__ chunks,
+                                                                  const double* __restrict__ coef, long stride,
+                                                                  long n_walkers, double* __restrict__ partial,
+                                                                  int chunk0) {
+    using R = TileRec<MODEL>;
+    constexpr int RB = R::kDataBytes, BB = R::kBasisBytes;
+    constexpr int kStageBytes = kTileBinsT * (BB + RB);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* stages = smem_raw;                    // per stage: [kTileBinsT x BB basis][kTileBinsT x RB data]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStagesT * kStageBytes);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long wi = (long)blockIdx.y * kTileWalkers + warp * 8 + g;
+    const long wl = wi < n_walkers ? wi : n_walkers - 1;
+
+    // A fragments: row g (this lane's walker), columns 4 s + t; the magic constant rides on the constant term
+    double afrag[R::kSteps];
+#pragma unroll
+    for (int s = 0; s < R::kSteps; ++s) {
+        // t is a run-time value: pick among the four compile-time slots of this k-step
+        const int s0 = tile_basis_slot<MODEL>(4 * s + 0), s1 = tile_basis_slot<MODEL>(4 * s + 1);
+        const int s2 = tile_basis_slot<MODEL>(4 * s + 2), s3 = tile_basis_slot<MODEL>(4 * s + 3);
+        const int slot = t == 0 ? s0 : t == 1 ? s1 : t == 2 ? s2 : s3;
+        double a = slot >= 0 ? coef[(size_t)slot * stride + wl] : 0.0;
+        if (slot == C_K0) a += kMagic;
+        afrag[s] = a;
+    }
+    TileWalker<NIFO> w;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) w.q[j] = (float)coef[(C_Q2 + j) * stride + wl];
+    w.q6l = (float)coef[C_Q6L * stride + wl];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
+
+    double zr[NIFO], zi[NIFO];
+    unsigned long long acc[NIFO];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; acc[i] = 0ull; }
+
+    const int chunk_id = chunk0 + (int)blockIdx.x;
+    const ChunkDesc chunk = chunks[chunk_id];
+    const long bin0 = chunk.start;
+    const int nb_total = chunk.len;
+    const int n_tiles = (nb_total + kTileBinsT - 1) / kTileBinsT;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStagesT; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int slot) {
+        const int nb = min(kTileBinsT, nb_total - tile * kTileBinsT);
+        const long first = bin0 + (long)tile * kTileBinsT;
+        unsigned char* dst = stages + (size_t)slot * kStageBytes;
+        mbar_expect_tx(&full[slot], (uint32_t)nb * (BB + RB));
+        tma_bulk_g2s(dst, tab_basis + first * BB, (uint32_t)nb * BB, &full[slot]);
+        tma_bulk_g2s(dst + (size_t)kTileBinsT * BB, tab_data + first * RB, (uint32_t)nb * RB, &full[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStagesT && s < n_tiles; ++s) issue(s, s);
+    }
+
+    double corr = 1.0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            float re, im;
+            unpack2(acc[i], re, im);
+            zr[i] = fma((double)re, corr, zr[i]);
+            zi[i] = fma((double)im, corr, zi[i]);
+            acc[i] = 0ull;
+        }
+    };
+
+    for (int tl = 0; tl < n_tiles; ++tl) {
+        const int slot = tl % kStagesT;
+        const unsigned char* tbasis = stages + (size_t)slot * kStageBytes;
+        const unsigned char* tdata = tbasis + (size_t)kTileBinsT * BB;
+        const int nb = min(kTileBinsT, nb_total - tl * kTileBinsT);
+        {
+            // smooth systematic factor of the FP32 amplitude series at the tile's first bin (see
+            // fullgrid_mixed_kernel); (u, L) of that bin come from the pair-format table
+            const double2 h0 = *reinterpret_cast<const double2*>(rec_ul + (size_t)(bin0 + (long)tl * kTileBinsT) * rec_ul_stride);
+            const double q_exact = amp_series_f64(h0.x, h0.y, coef, stride, wl);
+            double tq = fma((double)w.q6l, h0.y, (double)w.q[4]);
+            tq = fma((double)w.q[5], h0.x, tq);
+            tq = fma(tq, h0.x, (double)w.q[3]);
+            tq = fma(tq, h0.x, (double)w.q[2]);
+            tq = fma(tq, h0.x, (double)w.q[1]);
+            tq = fma(tq, h0.x, (double)w.q[0]);
+            corr = q_exact / fma(h0.x * h0.x, tq, 1.0);
+        }
+        mbar_wait(&full[slot], (uint32_t)((tl / kStagesT) & 1));
+        const int n_steps = nb / kStepBins;
+#pragma unroll 1
+        for (int st = 0; st < n_steps; ++st) {
+            tile_step<NIFO, MODEL, SC, false>(tbasis + (size_t)st * kStepBins * BB, tdata + (size_t)st * kStepBins * RB,
+                                              afrag, w, g, t, kStepBins, acc);
+            flush();
+        }
+        if (n_steps * kStepBins < nb) {
+            tile_step<NIFO, MODEL, SC, true>(tbasis + (size_t)n_steps * kStepBins * BB,
+                                             tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
+                                             nb - n_steps * kStepBins, acc);
+            flush();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && tl + kStagesT < n_tiles) {
+            fence_proxy_async();
+            issue(tl + kStagesT, slot);
+        }
+    }
+
+    // the four lanes of a walker hold disjoint bins: fixed-order butterfly, lane t = 0 stores
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) {
+        zr[i] += __shfl_xor_sync(0xffffffffu, zr[i], 1);
+        zi[i] += __shfl_xor_sync(0xffffffffu, zi[i], 1);
+        zr[i] += __shfl_xor_sync(0xffffffffu, zr[i], 2);
+        zi[i] += __shfl_xor_sync(0xffffffffu, zi[i], 2);
+    }
+    if (t == 0 && wi < n_walkers) {
+        double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            out[(2 * i + 0) * stride] = zr[i];
+            out[(2 * i + 1) * stride] = zi[i];
+        }
+    }
+}
+
 // log(I0(x)) = log(i0e(x)) + x for x >= 0   (log_like.py:176-177)
 __device__ inline double log_bessel_i0(double x) {
     if (x < 500.0) return log(cyl_bessel_i0(x));

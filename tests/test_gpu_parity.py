@@ -352,4 +352,4 @@ def test_engine_reports_launch_and_timing():
     ms = like.engine.last_kernel_ms()
     info = like.engine.last_launch_info()
     assert all(m >= 0 for m in ms) and ms[1] > 0
-    assert info[2] == 128 and info[0] * info[4] >= int(gold["band"].sum())
+    assert info[2] in (128, 256) and info[0] * info[4] >= int(gold["band"].sum())
