@@ -83,6 +83,7 @@ struct bj_ctx {
     double calib[2] = {0.0, 0.0}; // measured phasor bias (eps_a, eps_p)
     void* d_rec = nullptr;
     void* d_tile_basis = nullptr; // tables of the tensor-core kernel; null: Horner kernels only
+    double grid_df = 0.0;         // bin spacing if the in-band grid is uniform (integer time-delay ramps), else 0
     void* d_tile_data = nullptr;
     double* d_freqs = nullptr;
     double* d_gram = nullptr;
@@ -581,6 +582,14 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
                 bj_destroy(c);
                 return fail(BJ_ERR_CUDA, "uploading the tensor-core tables failed: %s", cudaGetErrorString(et));
             }
+            // uniform in-band grid (every FFT grid bajes produces): integer time-delay ramps
+            if (n_bins >= 2 && !getenv("BAJES_B200_NO_IRAMP")) {
+                const double df = (freqs[n_bins - 1] - freqs[0]) / (double)(n_bins - 1);
+                bool uniform = df > 0.0;
+                for (int64_t k = 0; k < n_bins && uniform; ++k)
+                    uniform = std::fabs(freqs[k] - (freqs[0] + (double)k * df)) <= 1e-7 * df;
+                if (uniform) c->grid_df = df;
+            }
         }
     }
     cudaError_t e = cudaMalloc(&c->d_rec, rec_bytes);
@@ -721,12 +730,12 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
     if (!SPCAL && c->d_tile_basis) {
         constexpr int RT = TileRec<MODEL>::kBasisBytes + TileRec<MODEL>::kDataBytes;
         const size_t smem_t = (size_t)kStagesT * kTileBinsT * RT + kStagesT * sizeof(uint64_t);
-        auto tkern = fullgrid_tile_kernel<NIFO, MODEL, SC>;
+        auto tkern = c->grid_df > 0.0 ? fullgrid_tile_kernel<NIFO, MODEL, SC, true> : fullgrid_tile_kernel<NIFO, MODEL, SC, false>;
         CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         dim3 tgrid((unsigned)(c1 - c0), (unsigned)((n_walkers + kTileWalkers - 1) / kTileWalkers));
         tkern<<<tgrid, kTileThreads, smem_t, st>>>((const unsigned char*)c->d_tile_basis, (const unsigned char*)c->d_tile_data,
                                                    (const unsigned char*)c->d_rec, RB, c->d_chunks, c->d_coef,
-                                                   c->cap_walkers, n_walkers, c->d_partial, c0);
+                                                   c->cap_walkers, n_walkers, c->d_partial, c0, c->grid_df);
         note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

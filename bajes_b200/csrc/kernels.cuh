@@ -826,14 +826,21 @@ template <int NIFO>
 struct TileWalker {
     double tau[NIFO];
     float q[6], q6l;
+    int d1[NIFO], d7[NIFO];     // uniform grids: one-bin step of the time-delay ramp, df tau_i, in 2^-32 turns (and x 7)
 };
 
 // one step: 8 walkers x 32 bins per warp.  `limit` = number of valid bins of the step (32 except at the ragged end
 // of a chunk; always even); GUARD = false compiles the test away.
-template <int NIFO, int MODEL, int SC, bool GUARD>
+//
+// IRAMP (uniform grids, i.e. every FFT grid bajes produces): the time-delay ramp f_k tau_i is advanced in 32-bit binary
+// angles from one FP64 anchor per step and detector, taken at the CENTRE of the step: the rounding of the increment
+// (<= 2^-33 turns per bin, <= 1.2e-8 rad at the step's ends) is antisymmetric about the anchor and leaves no phase
+// bias.  This replaces one DFMA (which competes with the DMMAs for the FP64 pipe) and the load of f per bin and
+// detector by two integer adds.
+template <int NIFO, int MODEL, int SC, bool GUARD, bool IRAMP>
 __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basis, const unsigned char* __restrict__ base,
                                           const double (&afrag)[TileRec<MODEL>::kSteps], const TileWalker<NIFO>& w,
-                                          int g, int t, int limit, unsigned long long (&acc)[NIFO]) {
+                                          int g, int t, int limit, double df16, unsigned long long (&acc)[NIFO]) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes;
     // ---- phase: D[m][h] = turns (+ magic) of walker g at bin 8m + 2t + h ----
@@ -865,13 +872,20 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
         unpack2(q, Qf[m][0], Qf[m][1]);
     }
     // ---- per bin and detector: ramp, phasor, packed complex MAC ----
+    int e[NIFO];
+    if constexpr (IRAMP) {
+        const double fc = *reinterpret_cast<const double*>(base + R::kF) + df16;     // bin 16 of the step
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) e[i] = __double2loint(fma(fc, w.tau[i], kMagic)) + (2 * t - 16) * w.d1[i];
+    }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         if (GUARD && 8 * m + 2 * t >= limit) continue;        // ring memory beyond the chunk is never used
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const unsigned char* rb = base + (size_t)(8 * m + 2 * t + h) * RB;
-            const double f = *reinterpret_cast<const double*>(rb + R::kF);
+            double f = 0.0;
+            if constexpr (!IRAMP) f = *reinterpret_cast<const double*>(rb + R::kF);
             unsigned long long dd[NIFO];
             if constexpr (NIFO >= 2) {
                 const ulonglong2 d01 = *reinterpret_cast<const ulonglong2*>(rb + R::kData);
@@ -884,7 +898,14 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
 #pragma unroll
             for (int i = 0; i < NIFO; ++i) {
                 float cq, sq;
-                scaled_phasor_f32<SC>(__double2loint(fma(f, w.tau[i], D[m][h])), Qf[m][h], cq, sq);
+                int32_t b;
+                if constexpr (IRAMP) {
+                    b = __double2loint(D[m][h]) + e[i];
+                    e[i] += h == 0 ? w.d1[i] : w.d7[i];           // next bin of this lane: + 1, then + 7
+                } else {
+                    b = __double2loint(fma(f, w.tau[i], D[m][h]));
+                }
+                scaled_phasor_f32<SC>(b, Qf[m][h], cq, sq);
                 // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
                 float dr, di, ar, ai;
                 unpack2(dd[i], dr, di);
@@ -895,7 +916,7 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
     }
 }
 
-template <int NIFO, int MODEL, int SC>
+template <int NIFO, int MODEL, int SC, bool IRAMP>
 __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const unsigned char* __restrict__ tab_basis,
                                                                   const unsigned char* __restrict__ tab_data,
                                                                   const unsigned char* __restrict__ rec_ul,
@@ -903,7 +924,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
                                                                   const ChunkDesc* __restrict__ chunks,
                                                                   const double* __restrict__ coef, long stride,
                                                                   long n_walkers, double* __restrict__ partial,
-                                                                  int chunk0) {
+                                                                  int chunk0, double df) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes, BB = R::kBasisBytes;
     constexpr int kStageBytes = kTileBinsT * (BB + RB);
@@ -933,7 +954,12 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
     for (int j = 0; j < 6; ++j) w.q[j] = (float)coef[(C_Q2 + j) * stride + wl];
     w.q6l = (float)coef[C_Q6L * stride + wl];
 #pragma unroll
-    for (int i = 0; i < NIFO; ++i) w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
+    for (int i = 0; i < NIFO; ++i) {
+        w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
+        w.d1[i] = __double2loint(fma(df, w.tau[i], kMagic));
+        w.d7[i] = 7 * w.d1[i];
+    }
+    const double df16 = 16.0 * df;
 
     double zr[NIFO], zi[NIFO];
     unsigned long long acc[NIFO];
@@ -999,14 +1025,14 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
         const int n_steps = nb / kStepBins;
 #pragma unroll 1
         for (int st = 0; st < n_steps; ++st) {
-            tile_step<NIFO, MODEL, SC, false>(tbasis + (size_t)st * kStepBins * BB, tdata + (size_t)st * kStepBins * RB,
-                                              afrag, w, g, t, kStepBins, acc);
+            tile_step<NIFO, MODEL, SC, false, IRAMP>(tbasis + (size_t)st * kStepBins * BB, tdata + (size_t)st * kStepBins * RB,
+                                                     afrag, w, g, t, kStepBins, df16, acc);
             flush();
         }
         if (n_steps * kStepBins < nb) {
-            tile_step<NIFO, MODEL, SC, true>(tbasis + (size_t)n_steps * kStepBins * BB,
-                                             tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
-                                             nb - n_steps * kStepBins, acc);
+            tile_step<NIFO, MODEL, SC, true, IRAMP>(tbasis + (size_t)n_steps * kStepBins * BB,
+                                                    tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
+                                                    nb - n_steps * kStepBins, df16, acc);
             flush();
         }
         __syncthreads();
