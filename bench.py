@@ -42,15 +42,20 @@ METRIC = "likelihood evals/sec (walkers x freq bins / s)"
 UNIT = "walker*bins/s"
 
 # Algorithmic instruction counts per walker*bin of the fused kernel:
-#   FP64: phase Horner (13 for 3.5PN + 6PN tides, 27 for the 5.5PN family) + one time-delay ramp FMA per detector
-#         (+ 2 FMAs per detector per 8 bins for the FP32 -> FP64 flush)
+#   FP64, Horner kernels : phase Horner (13 for 3.5PN + 6PN tides, 27 for the 5.5PN family) + one time-delay ramp FMA
+#         per detector (+ 2 FMAs per detector per 8 bins for the FP32 -> FP64 flush)
+#   FP64, tensor-core kernel : K = 12 / 28 FMAs of the phase GEMM (executed as DMMA.8x8x4) + per 8 bins and detector
+#         2 flush FMAs and 1 FP64 ramp anchor (uniform grids; else one ramp FMA per bin and detector)
 #   SFU : one MUFU.SIN + one MUFU.COS per detector ("mufu" mode; none in "poly32")
-def instr_per_unit(approx, n_ifo, sincos):
+def instr_per_unit(approx, n_ifo, sincos, tensor_core=False):
     phase = 13 if approx == "TaylorF2_3.5PN" else 27
     if sincos == "fp64":
         fp64 = phase + 7 + 5 * n_ifo
         return fp64, 0
-    fp64 = phase + n_ifo + 2.0 * n_ifo / 8.0
+    if tensor_core:
+        fp64 = (12 if approx == "TaylorF2_3.5PN" else 28) + 3.0 * n_ifo / 8.0
+    else:
+        fp64 = phase + n_ifo + 2.0 * n_ifo / 8.0
     sfu = 2 * n_ifo if sincos == "mufu" else 0
     return fp64, sfu
 
@@ -351,7 +356,9 @@ def main():
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------
     units_per_launch = W * nb
-    fp64_pu, sfu_pu = instr_per_unit(cfg["approx"], nifo, args.sincos)
+    info = like.engine.last_launch_info()
+    tensor_core = info[2] == 256           # fullgrid_tile_kernel: 256 threads = 64 walkers per CTA
+    fp64_pu, sfu_pu = instr_per_unit(cfg["approx"], nifo, args.sincos, tensor_core)
     k_s = float(np.mean(kern_ms)) * 1e-3
     peak_dfma = engine.measure_peak("dfma", local)
     peak_mufu = engine.measure_peak("mufu", local)
@@ -361,8 +368,7 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    info = like.engine.last_launch_info()
-    n_wtiles = (W + 127) // 128
+    n_wtiles = (W + 63) // 64 if tensor_core else (W + 127) // 128
     # algorithmic bytes: every walker tile streams the static table once; coefficient block; partial sums
     alg_bytes = n_wtiles * nb * info[6] * 8 + W * 50 * 8 + info[5] * 2 * nifo * W * 8
     traffic = None
@@ -381,8 +387,8 @@ def main():
     roofline = {"bound": bound, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": unit,
                 "frac": achieved / peak, "traffic": traffic, "instr_per_unit": ipu,
                 "units_per_launch": units_per_launch, "kernel_ms": k_s * 1e3,
-                "kernel": "fullgrid_%s_kernel<%d ifo, %s, %s>" % ("mixed" if args.sincos != "fp64" else "fp64", nifo,
-                                                                 cfg["approx"], args.sincos),
+                "kernel": "fullgrid_%s_kernel<%d ifo, %s, %s>" % (
+                    "tile" if tensor_core else "mixed" if args.sincos != "fp64" else "fp64", nifo, cfg["approx"], args.sincos),
                 "peak_source": "measured live by bj_measure_peak (register-resident DFMA / MUFU chains); "
                                "MEASURED_PEAKS.json has no FP64 or SFU figure",
                 other: {"instr_per_unit": lines[other][0], "achieved": units_per_launch * lines[other][0] / k_s / 1e9,
