@@ -905,12 +905,19 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
                 } else {
                     b = __double2loint(fma(f, w.tau[i], D[m][h]));
                 }
-                scaled_phasor_f32<SC>(b, Qf[m][h], cq, sq);
-                // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
                 float dr, di, ar, ai;
                 unpack2(dd[i], dr, di);
-                unpack2(fma2(dd[i], pack2(cq, cq), acc[i]), ar, ai);
-                acc[i] = pack2(fmaf(di, sq, ar), fmaf(-dr, sq, ai));
+                if constexpr (SC == BJ_SINCOS_MUFU) {
+                    // acc += Q [(dr, di) c + (di, -dr) s]: Q enters once, on the accumulate
+                    scaled_phasor_f32<SC>(b, 1.0f, cq, sq);
+                    unpack2(mul2(dd[i], pack2(cq, cq)), ar, ai);
+                    acc[i] = fma2(pack2(fmaf(di, sq, ar), fmaf(-dr, sq, ai)), pack2(Qf[m][h], Qf[m][h]), acc[i]);
+                } else {
+                    // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
+                    scaled_phasor_f32<SC>(b, Qf[m][h], cq, sq);
+                    unpack2(fma2(dd[i], pack2(cq, cq), acc[i]), ar, ai);
+                    acc[i] = pack2(fmaf(di, sq, ar), fmaf(-dr, sq, ai));
+                }
             }
         }
     }
@@ -1027,8 +1034,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
         for (int st = 0; st < n_steps; ++st) {
             tile_step<NIFO, MODEL, SC, false, IRAMP>(tbasis + (size_t)st * kStepBins * BB, tdata + (size_t)st * kStepBins * RB,
                                                      afrag, w, g, t, kStepBins, df16, acc);
-            flush();
+            if (st & 1) flush();                 // FP32 sums of 16 bins per lane
         }
+        if (n_steps & 1) flush();
         if (n_steps * kStepBins < nb) {
             tile_step<NIFO, MODEL, SC, true, IRAMP>(tbasis + (size_t)n_steps * kStepBins * BB,
                                                     tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
