@@ -353,3 +353,24 @@ def test_engine_reports_launch_and_timing():
     info = like.engine.last_launch_info()
     assert all(m >= 0 for m in ms) and ms[1] > 0
     assert info[2] in (128, 256) and info[0] * info[4] >= int(gold["band"].sum())
+
+
+# ------------------------------------------------------------------------------------------------------
+# the three production code paths of the full grid: tensor-core kernel with integer ramps (default), tensor-core kernel
+# with FP64 ramps (non-uniform grids), Horner kernel (calibration envelopes / BAJES_B200_NO_TC)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env", [{}, {"BAJES_B200_NO_IRAMP": "1"}, {"BAJES_B200_NO_TC": "1"}])
+@pytest.mark.parametrize("approx", ["TaylorF2_3.5PN", "TaylorF2_5.5PN_7.5PNTides"])
+def test_kernel_variants_vs_reference_golden(env, approx, monkeypatch):
+    for k in ("BAJES_B200_NO_IRAMP", "BAJES_B200_NO_TC"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)                     # read when the context is created
+    cfg = syn.CONFIGS["C2_small"]
+    gold = load_golden("c2_small.npz")
+    like = _like(cfg, gold, approx=approx)
+    n = 64
+    got = like.log_like_batch(gold["X"][:n], _names(gold), syn.constants(cfg))
+    _check(got, gold["logl_%s_marg0" % approx][:n], "C2_small %s %s" % (approx, env or "default"))
+    threads = like.engine.last_launch_info()[2]
+    assert threads == (128 if "BAJES_B200_NO_TC" in env else 256)
