@@ -434,6 +434,8 @@ static void build_records_tile(std::vector<double>& tab_basis, std::vector<unsig
         if ((sidx & 1) == 0) { hf[0] = (float)be.u; hf[1] = (float)bo.u; }
         else                 { hf[0] = (float)be.L; hf[1] = (float)bo.L; }
         memcpy(r + R::kPair, hf, 8);
+        const float tcal = (float)L.slot_t[sidx];
+        memcpy(r + R::kT, &tcal, 4);
         for (int i = 0; i < nifo; ++i) {
             double wr = 0.0, wi = 0.0;
             if (L.slot_real[sidx]) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
@@ -568,8 +570,8 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
         c->calib[1] = eps[1];
         rec_ptr = recm.data();
         rec_bytes = recm.size();
-        // no calibration envelopes: the tensor-core kernel (phase as an FP64 GEMM) is the production path
-        if (nsp == 0 && !getenv("BAJES_B200_NO_TC")) {
+        // the tensor-core kernel (phase as an FP64 GEMM) is the production path
+        if (!getenv("BAJES_B200_NO_TC")) {
             std::vector<unsigned char> rect;
             std::vector<double> basis;
             if (cfg->approx == BJ_APPROX_TAYLORF2_35PN) build_records_tile<MODEL_35>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2);
@@ -727,15 +729,17 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
     auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true, SPCAL>;
     CUDA_TRY(cudaFuncSetAttribute(fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(c1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
-    if (!SPCAL && c->d_tile_basis) {
+    if (c->d_tile_basis) {
         constexpr int RT = TileRec<MODEL>::kBasisBytes + TileRec<MODEL>::kDataBytes;
         const size_t smem_t = (size_t)kStagesT * kTileBinsT * RT + kStagesT * sizeof(uint64_t);
-        auto tkern = c->grid_df > 0.0 ? fullgrid_tile_kernel<NIFO, MODEL, SC, true> : fullgrid_tile_kernel<NIFO, MODEL, SC, false>;
+        auto tkern = c->grid_df > 0.0 ? fullgrid_tile_kernel<NIFO, MODEL, SC, true, SPCAL>
+                                      : fullgrid_tile_kernel<NIFO, MODEL, SC, false, SPCAL>;
         CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         dim3 tgrid((unsigned)(c1 - c0), (unsigned)((n_walkers + kTileWalkers - 1) / kTileWalkers));
         tkern<<<tgrid, kTileThreads, smem_t, st>>>((const unsigned char*)c->d_tile_basis, (const unsigned char*)c->d_tile_data,
                                                    (const unsigned char*)c->d_rec, RB, c->d_chunks, c->d_coef,
-                                                   c->cap_walkers, n_walkers, c->d_partial, c0, c->grid_df);
+                                                   c->cap_walkers, n_walkers, c->d_partial, c0, c->grid_df,
+                                                   c->d_coef_ex, c->dims);
         note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

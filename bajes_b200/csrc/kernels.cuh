@@ -782,8 +782,8 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 // Two static tables (SoA, so that both access patterns are free of shared-memory bank conflicts):
 //   basis[bin][K]  f64      stride 96 B (K = 12) / 224 B (K = 28): the B-fragment load of a half warp (4 bins x 4
 //                           doubles) covers all 32 banks exactly once;
-//   data[bin]      48 B     [f : f64][pair slot : f32 x2][(dr, di) : f32 x2] x 3, 8 B padding: the four bins a
-//                           quarter warp reads (2 records = 24 words apart) fall into disjoint banks.
+//   data[bin]      48 B     [f : f64][pair slot : f32 x2][(dr, di) : f32 x2] x 3 [t : f32] 4 B padding: the four bins
+//                           a quarter warp reads (2 records = 24 words apart) fall into disjoint banks.
 // Every 128-bit load serves 8 walkers here instead of 32, and shared-memory wavefronts are what this kernel runs out
 // of: with the 16-byte (dr, di, di, -dr) entries of the Horner kernels it sat at 87 % of the LSU's cycles (5.04 ms),
 // hence the 8-byte entries and the two scalar FFMAs with a negated operand in the MAC.  (A hybrid that keeps one
@@ -797,8 +797,9 @@ template <int MODEL> struct TileRec {
     static constexpr int kF = 0;
     static constexpr int kPair = 8;
     static constexpr int kData = 16;
+    static constexpr int kT = 40;            // f32: calibration interpolation fraction t(f) of the bin (0 without spcal)
 };
-static_assert(TileRec<MODEL_35>::kData + 8 * BJ_MAX_IFO <= TileRec<MODEL_35>::kDataBytes, "record too small");
+static_assert(TileRec<MODEL_35>::kData + 8 * BJ_MAX_IFO <= TileRec<MODEL_35>::kT, "record too small");
 constexpr int kTileBinsT = 128;      // bins per TMA stage
 constexpr int kStagesT = 3;
 constexpr int kTileThreads = 256;
@@ -837,10 +838,16 @@ struct TileWalker {
 // (<= 2^-33 turns per bin, <= 1.2e-8 rad at the step's ends) is antisymmetric about the anchor and leaves no phase
 // bias.  This replaces one DFMA (which competes with the DMMAs for the FP64 pipe) and the load of f per bin and
 // detector by two integer adds.
-template <int NIFO, int MODEL, int SC, bool GUARD, bool IRAMP>
+//
+// SPCAL (calibration envelopes, detector.py:517-519): inside a chunk cal_i(f) = c0_i + (c1_i - c0_i) t(f) with constant
+// node values, so  sum_k cal_i X_k = c0_i sum_k X_k + (c1_i - c0_i) sum_k t_k X_k : a second accumulator fed with
+// Q t instead of Q (one FMUL per bin + one FFMA2 per detector and bin); the node values enter once per chunk, in
+// FP64, when the kernel stores its partial sums.
+template <int NIFO, int MODEL, int SC, bool GUARD, bool IRAMP, bool SPCAL>
 __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basis, const unsigned char* __restrict__ base,
                                           const double (&afrag)[TileRec<MODEL>::kSteps], const TileWalker<NIFO>& w,
-                                          int g, int t, int limit, double df16, unsigned long long (&acc)[NIFO]) {
+                                          int g, int t, int limit, double df16, unsigned long long (&acc)[NIFO],
+                                          unsigned long long (&acc1)[NIFO]) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes;
     // ---- phase: D[m][h] = turns (+ magic) of walker g at bin 8m + 2t + h ----
@@ -886,6 +893,8 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
             const unsigned char* rb = base + (size_t)(8 * m + 2 * t + h) * RB;
             double f = 0.0;
             if constexpr (!IRAMP) f = *reinterpret_cast<const double*>(rb + R::kF);
+            float qt = 0.0f;
+            if constexpr (SPCAL) qt = Qf[m][h] * *reinterpret_cast<const float*>(rb + R::kT);
             unsigned long long dd[NIFO];
             if constexpr (NIFO >= 2) {
                 const ulonglong2 d01 = *reinterpret_cast<const ulonglong2*>(rb + R::kData);
@@ -911,7 +920,15 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
                     // acc += Q [(dr, di) c + (di, -dr) s]: Q enters once, on the accumulate
                     scaled_phasor_f32<SC>(b, 1.0f, cq, sq);
                     unpack2(mul2(dd[i], pack2(cq, cq)), ar, ai);
-                    acc[i] = fma2(pack2(fmaf(di, sq, ar), fmaf(-dr, sq, ai)), pack2(Qf[m][h], Qf[m][h]), acc[i]);
+                    const unsigned long long term = pack2(fmaf(di, sq, ar), fmaf(-dr, sq, ai));
+                    acc[i] = fma2(term, pack2(Qf[m][h], Qf[m][h]), acc[i]);
+                    if constexpr (SPCAL) acc1[i] = fma2(term, pack2(qt, qt), acc1[i]);
+                } else if constexpr (SPCAL) {
+                    scaled_phasor_f32<SC>(b, 1.0f, cq, sq);          // (the half-turn sign rides on the unit amplitude)
+                    unpack2(mul2(dd[i], pack2(cq, cq)), ar, ai);
+                    const unsigned long long term = pack2(fmaf(di, sq, ar), fmaf(-dr, sq, ai));
+                    acc[i] = fma2(term, pack2(Qf[m][h], Qf[m][h]), acc[i]);
+                    acc1[i] = fma2(term, pack2(qt, qt), acc1[i]);
                 } else {
                     // (dr + i di) Q (c - i s) = (dr, di) cq + (di, -dr) sq
                     scaled_phasor_f32<SC>(b, Qf[m][h], cq, sq);
@@ -923,7 +940,7 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
     }
 }
 
-template <int NIFO, int MODEL, int SC, bool IRAMP>
+template <int NIFO, int MODEL, int SC, bool IRAMP, bool SPCAL>
 __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const unsigned char* __restrict__ tab_basis,
                                                                   const unsigned char* __restrict__ tab_data,
                                                                   const unsigned char* __restrict__ rec_ul,
@@ -931,7 +948,8 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
                                                                   const ChunkDesc* __restrict__ chunks,
                                                                   const double* __restrict__ coef, long stride,
                                                                   long n_walkers, double* __restrict__ partial,
-                                                                  int chunk0, double df) {
+                                                                  int chunk0, double df,
+                                                                  const double* __restrict__ coef_ex, ExtrasDims dims) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes, BB = R::kBasisBytes;
     constexpr int kStageBytes = kTileBinsT * (BB + RB);
@@ -968,10 +986,10 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
     }
     const double df16 = 16.0 * df;
 
-    double zr[NIFO], zi[NIFO];
-    unsigned long long acc[NIFO];
+    double zr[NIFO], zi[NIFO], yr[NIFO], yi[NIFO];            // y: the t-weighted sums (SPCAL)
+    unsigned long long acc[NIFO], acc1[NIFO];
 #pragma unroll
-    for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; acc[i] = 0ull; }
+    for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; yr[i] = 0.0; yi[i] = 0.0; acc[i] = 0ull; acc1[i] = 0ull; }
 
     const int chunk_id = chunk0 + (int)blockIdx.x;
     const ChunkDesc chunk = chunks[chunk_id];
@@ -1007,6 +1025,12 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
             zr[i] = fma((double)re, corr, zr[i]);
             zi[i] = fma((double)im, corr, zi[i]);
             acc[i] = 0ull;
+            if constexpr (SPCAL) {
+                unpack2(acc1[i], re, im);
+                yr[i] = fma((double)re, corr, yr[i]);
+                yi[i] = fma((double)im, corr, yi[i]);
+                acc1[i] = 0ull;
+            }
         }
     };
 
@@ -1032,15 +1056,16 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
         const int n_steps = nb / kStepBins;
 #pragma unroll 1
         for (int st = 0; st < n_steps; ++st) {
-            tile_step<NIFO, MODEL, SC, false, IRAMP>(tbasis + (size_t)st * kStepBins * BB, tdata + (size_t)st * kStepBins * RB,
-                                                     afrag, w, g, t, kStepBins, df16, acc);
+            tile_step<NIFO, MODEL, SC, false, IRAMP, SPCAL>(tbasis + (size_t)st * kStepBins * BB,
+                                                            tdata + (size_t)st * kStepBins * RB, afrag, w, g, t,
+                                                            kStepBins, df16, acc, acc1);
             if (st & 1) flush();                 // FP32 sums of 16 bins per lane
         }
         if (n_steps & 1) flush();
         if (n_steps * kStepBins < nb) {
-            tile_step<NIFO, MODEL, SC, true, IRAMP>(tbasis + (size_t)n_steps * kStepBins * BB,
-                                                    tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
-                                                    nb - n_steps * kStepBins, df16, acc);
+            tile_step<NIFO, MODEL, SC, true, IRAMP, SPCAL>(tbasis + (size_t)n_steps * kStepBins * BB,
+                                                           tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
+                                                           nb - n_steps * kStepBins, df16, acc, acc1);
             flush();
         }
         __syncthreads();
@@ -1050,6 +1075,20 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
         }
     }
 
+    if constexpr (SPCAL) {
+        // calibration envelope of the chunk's segment, exact FP64 node values: z <- c0 z + (c1 - c0) y
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            const double c0r = coef_ex[ex_cal_slot(dims, i, chunk.seg, 0) * stride + wl];
+            const double c0i = coef_ex[ex_cal_slot(dims, i, chunk.seg, 1) * stride + wl];
+            const double dr = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 0) * stride + wl] - c0r;
+            const double di = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 1) * stride + wl] - c0i;
+            const double nr = c0r * zr[i] - c0i * zi[i] + dr * yr[i] - di * yi[i];
+            const double ni = c0r * zi[i] + c0i * zr[i] + dr * yi[i] + di * yr[i];
+            zr[i] = nr;
+            zi[i] = ni;
+        }
+    }
     // the four lanes of a walker hold disjoint bins: fixed-order butterfly, lane t = 0 stores
 #pragma unroll
     for (int i = 0; i < NIFO; ++i) {
