@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 // t = lane % 4) holds walker g and bins {8m + 2t, 8m + 2t + 1}, m = 0..3: ONE walker per lane (coefficients and
 // accumulators as in the kernels above), 8 bins per step, an (even, odd) pair per n-tile for the packed FP32
 // amplitude.  The four lanes of a walker are reduced by two shuffles at the end of the kernel.  A CTA = 8 warps = 64
-// walkers streams the chunk through a 3-stage TMA ring of 128 bins.
+// walkers streams the chunk through a 3-stage TMA ring of 256 bins.
 // Two static tables (SoA, so that both access patterns are free of shared-memory bank conflicts):
 //   basis[bin][K]  f64      stride 96 B (K = 12) / 224 B (K = 28): the B-fragment load of a half warp (4 bins x 4
 //                           doubles) covers all 32 banks exactly once;
@@ -800,8 +800,14 @@ template <int MODEL> struct TileRec {
     static constexpr int kT = 40;            // f32: calibration interpolation fraction t(f) of the bin (0 without spcal)
 };
 static_assert(TileRec<MODEL_35>::kData + 8 * BJ_MAX_IFO <= TileRec<MODEL_35>::kT, "record too small");
-constexpr int kTileBinsT = 128;      // bins per TMA stage
-constexpr int kStagesT = 3;
+#ifndef BJ_TILE_BINS
+#define BJ_TILE_BINS 256
+#endif
+#ifndef BJ_TILE_STAGES
+#define BJ_TILE_STAGES 3
+#endif
+constexpr int kTileBinsT = BJ_TILE_BINS;      // bins per TMA stage (fewer CTA-wide barriers than 128: -5 %)
+constexpr int kStagesT = BJ_TILE_STAGES;
 constexpr int kTileThreads = 256;
 constexpr int kTileWalkers = 64;     // 8 per warp
 constexpr int kStepBins = 32;
@@ -1040,9 +1046,10 @@ __global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const un
         const unsigned char* tdata = tbasis + (size_t)kTileBinsT * BB;
         const int nb = min(kTileBinsT, nb_total - tl * kTileBinsT);
         {
-            // smooth systematic factor of the FP32 amplitude series at the tile's first bin (see
-            // fullgrid_mixed_kernel); (u, L) of that bin come from the pair-format table
-            const double2 h0 = *reinterpret_cast<const double2*>(rec_ul + (size_t)(bin0 + (long)tl * kTileBinsT) * rec_ul_stride);
+            // smooth systematic factor of the FP32 amplitude series (see fullgrid_mixed_kernel), evaluated at the
+            // tile's CENTRE bin so that its drift over the tile cancels to first order; (u, L) of that bin come from
+            // the pair-format table
+            const double2 h0 = *reinterpret_cast<const double2*>(rec_ul + (size_t)(bin0 + (long)tl * kTileBinsT + nb / 2) * rec_ul_stride);
             const double q_exact = amp_series_f64(h0.x, h0.y, coef, stride, wl);
             double tq = fma((double)w.q6l, h0.y, (double)w.q[4]);
             tq = fma((double)w.q[5], h0.x, tq);
