@@ -808,8 +808,11 @@ static_assert(TileRec<MODEL_35>::kData + 8 * BJ_MAX_IFO <= TileRec<MODEL_35>::kT
 #endif
 constexpr int kTileBinsT = BJ_TILE_BINS;      // bins per TMA stage (fewer CTA-wide barriers than 128: -5 %)
 constexpr int kStagesT = BJ_TILE_STAGES;
-constexpr int kTileThreads = 256;
-constexpr int kTileWalkers = 64;     // 8 per warp
+#ifndef BJ_TILE_THREADS
+#define BJ_TILE_THREADS 256
+#endif
+constexpr int kTileThreads = BJ_TILE_THREADS;
+constexpr int kTileWalkers = kTileThreads / 4;     // 8 per warp
 constexpr int kStepBins = 32;
 
 // coefficient slot of basis function n (-1: zero padding); the host builds B in the same order (capi.cu)
@@ -947,7 +950,7 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
 }
 
 template <int NIFO, int MODEL, int SC, bool IRAMP, bool SPCAL>
-__global__ void __launch_bounds__(kTileThreads, 2) fullgrid_tile_kernel(const unsigned char* __restrict__ tab_basis,
+__global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_tile_kernel(const unsigned char* __restrict__ tab_basis,
                                                                   const unsigned char* __restrict__ tab_data,
                                                                   const unsigned char* __restrict__ rec_ul,
                                                                   int rec_ul_stride,
