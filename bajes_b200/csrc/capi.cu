@@ -731,7 +731,7 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
     dim3 grid((unsigned)(c1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
     if (c->d_tile_basis) {
         constexpr int RT = TileRec<MODEL>::kBasisBytes + TileRec<MODEL>::kDataBytes;
-        const size_t smem_t = (size_t)kStagesT * kTileBinsT * RT + kStagesT * sizeof(uint64_t);
+        const size_t smem_t = (size_t)kStagesT * TileRec<MODEL>::kTileBins * RT + kStagesT * sizeof(uint64_t);
         auto tkern = c->grid_df > 0.0 ? fullgrid_tile_kernel<NIFO, MODEL, SC, true, SPCAL>
                                       : fullgrid_tile_kernel<NIFO, MODEL, SC, false, SPCAL>;
         CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));

@@ -789,6 +789,14 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 // hence the 8-byte entries and the two scalar FFMAs with a negated operand in the MAC.  (A hybrid that keeps one
 // walker per thread and transposes the accumulator fragments through shared memory was measured too: 5.49 ms,
 // against 5.59 ms for the Horner kernel; 4096 walkers x 521 729 bins x 3 detectors.)
+#ifndef BJ_TILE_BINS
+#define BJ_TILE_BINS 256
+#endif
+#ifndef BJ_TILE_STAGES
+#define BJ_TILE_STAGES 3
+#endif
+constexpr int kTileBinsT = BJ_TILE_BINS;      // bins per TMA stage (fewer CTA-wide barriers than 128: -5 %)
+constexpr int kStagesT = BJ_TILE_STAGES;
 template <int MODEL> struct TileRec {
     static constexpr int K = (MODEL == MODEL_35) ? 12 : 28;
     static constexpr int kSteps = K / 4;
@@ -798,16 +806,11 @@ template <int MODEL> struct TileRec {
     static constexpr int kPair = 8;
     static constexpr int kData = 16;
     static constexpr int kT = 40;            // f32: calibration interpolation fraction t(f) of the bin (0 without spcal)
+    // bins per TMA stage: as many as two resident CTAs allow (fewer CTA-wide barriers: 256 instead of 128 is -5 %)
+    static constexpr int kTileBins = (MODEL == MODEL_35) ? kTileBinsT : kTileBinsT / 2;
 };
 static_assert(TileRec<MODEL_35>::kData + 8 * BJ_MAX_IFO <= TileRec<MODEL_35>::kT, "record too small");
-#ifndef BJ_TILE_BINS
-#define BJ_TILE_BINS 256
-#endif
-#ifndef BJ_TILE_STAGES
-#define BJ_TILE_STAGES 3
-#endif
-constexpr int kTileBinsT = BJ_TILE_BINS;      // bins per TMA stage (fewer CTA-wide barriers than 128: -5 %)
-constexpr int kStagesT = BJ_TILE_STAGES;
+
 #ifndef BJ_TILE_THREADS
 #define BJ_TILE_THREADS 256
 #endif
@@ -961,9 +964,9 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
                                                                   const double* __restrict__ coef_ex, ExtrasDims dims) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes, BB = R::kBasisBytes;
-    constexpr int kStageBytes = kTileBinsT * (BB + RB);
+    constexpr int kStageBytes = R::kTileBins * (BB + RB);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* stages = smem_raw;                    // per stage: [kTileBinsT x BB basis][kTileBinsT x RB data]
+    unsigned char* stages = smem_raw;                    // per stage: [R::kTileBins x BB basis][R::kTileBins x RB data]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStagesT * kStageBytes);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1004,7 +1007,7 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
     const ChunkDesc chunk = chunks[chunk_id];
     const long bin0 = chunk.start;
     const int nb_total = chunk.len;
-    const int n_tiles = (nb_total + kTileBinsT - 1) / kTileBinsT;
+    const int n_tiles = (nb_total + R::kTileBins - 1) / R::kTileBins;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -1014,12 +1017,12 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
     __syncthreads();
 
     auto issue = [&](int tile, int slot) {
-        const int nb = min(kTileBinsT, nb_total - tile * kTileBinsT);
-        const long first = bin0 + (long)tile * kTileBinsT;
+        const int nb = min(R::kTileBins, nb_total - tile * R::kTileBins);
+        const long first = bin0 + (long)tile * R::kTileBins;
         unsigned char* dst = stages + (size_t)slot * kStageBytes;
         mbar_expect_tx(&full[slot], (uint32_t)nb * (BB + RB));
         tma_bulk_g2s(dst, tab_basis + first * BB, (uint32_t)nb * BB, &full[slot]);
-        tma_bulk_g2s(dst + (size_t)kTileBinsT * BB, tab_data + first * RB, (uint32_t)nb * RB, &full[slot]);
+        tma_bulk_g2s(dst + (size_t)R::kTileBins * BB, tab_data + first * RB, (uint32_t)nb * RB, &full[slot]);
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStagesT && s < n_tiles; ++s) issue(s, s);
@@ -1046,13 +1049,13 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
     for (int tl = 0; tl < n_tiles; ++tl) {
         const int slot = tl % kStagesT;
         const unsigned char* tbasis = stages + (size_t)slot * kStageBytes;
-        const unsigned char* tdata = tbasis + (size_t)kTileBinsT * BB;
-        const int nb = min(kTileBinsT, nb_total - tl * kTileBinsT);
+        const unsigned char* tdata = tbasis + (size_t)R::kTileBins * BB;
+        const int nb = min(R::kTileBins, nb_total - tl * R::kTileBins);
         {
             // smooth systematic factor of the FP32 amplitude series (see fullgrid_mixed_kernel), evaluated at the
             // tile's CENTRE bin so that its drift over the tile cancels to first order; (u, L) of that bin come from
             // the pair-format table
-            const double2 h0 = *reinterpret_cast<const double2*>(rec_ul + (size_t)(bin0 + (long)tl * kTileBinsT + nb / 2) * rec_ul_stride);
+            const double2 h0 = *reinterpret_cast<const double2*>(rec_ul + (size_t)(bin0 + (long)tl * R::kTileBins + nb / 2) * rec_ul_stride);
             const double q_exact = amp_series_f64(h0.x, h0.y, coef, stride, wl);
             double tq = fma((double)w.q6l, h0.y, (double)w.q[4]);
             tq = fma((double)w.q[5], h0.x, tq);
