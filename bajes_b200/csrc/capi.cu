@@ -257,7 +257,10 @@ static int build_layout(Layout& L, long n, const double* freqs, const bj_extras*
     // chunk size depends on the table ONLY, so the reduction tree (and every output bit) is independent of how many
     // walkers a call or a rank evaluates
     const long total = (long)L.slot_bin.size();
-    long per = (total + 127) / 128;
+#ifndef BJ_TARGET_CHUNKS
+#define BJ_TARGET_CHUNKS 128
+#endif
+    long per = (total + BJ_TARGET_CHUNKS - 1) / BJ_TARGET_CHUNKS;
     per = ((per + kTileBins - 1) / kTileBins) * kTileBins;
     if (per < 256) per = 256;
     L.per = (int)per;
