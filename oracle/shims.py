@@ -49,6 +49,24 @@ def install() -> None:
             setattr(np, alias, target)
     if "trapz" not in np.__dict__:
         np.trapz = np.trapezoid
+    # inf/sampler/proposal.py:116 (and the other proposals): ``q, fact = np.transpose(q_f)`` on a ragged list of
+    # (array, float) pairs -- an implicit object array before NumPy 1.24, a ValueError since
+    if not getattr(np.transpose, "_bajes_shim", False):
+        _transpose = np.transpose
+
+        def transpose(a, axes=None):
+            try:
+                return _transpose(a, axes)
+            except ValueError:
+                rows = list(a)
+                out = np.empty((len(rows[0]), len(rows)), dtype=object)
+                for i, r in enumerate(rows):
+                    for j, v in enumerate(r):
+                        out[j, i] = v
+                return out
+
+        transpose._bajes_shim = True
+        np.transpose = transpose
 
     # bajes/obs/utils/cosmo.py:9  ``from scipy.misc import derivative``
     try:
