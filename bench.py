@@ -414,6 +414,12 @@ def main():
                 other: {"instr_per_unit": lines[other][0], "achieved": units_per_launch * lines[other][0] / k_s / 1e9,
                         "peak": lines[other][1] / 1e9, "unit": lines[other][2],
                         "frac": units_per_launch * lines[other][0] / k_s / lines[other][1]},
+                # the phase GEMM alone, in the units of a tensor-core roofline: K FMAs per walker*bin on DMMA.8x8x4 against
+                # the FP64 rate measured on this GPU (DMMA and DFMA share it: scripts/ubench_dmma.cu)
+                "tensor": ({"achieved": units_per_launch * 2 * (12 if cfg["approx"] == "TaylorF2_3.5PN" else 28) / k_s / 1e12,
+                            "peak": 2 * peak_dfma / 1e12, "unit": "TFLOP/s (FP64, DMMA)",
+                            "frac": units_per_launch * (12 if cfg["approx"] == "TaylorF2_3.5PN" else 28) / k_s / peak_dfma}
+                           if tensor_core else None),
                 "hbm": {"achieved": alg_bytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / k_s / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
