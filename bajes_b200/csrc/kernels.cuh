@@ -99,7 +99,8 @@ __device__ __forceinline__ void scaled_phasor(int32_t b, double Q, float Qf, dou
     if constexpr (SC == BJ_SINCOS_POLY32) {
         int32_t rem;
         asm("bfe.s32 %0, %1, 0, 31;" : "=r"(rem) : "r"(b));            // SGXT: nearest-half-turn remainder
-        const uint32_t flip = (uint32_t)(b ^ (b + b)) & 0x80000000u;    // parity of the half turn
+        const uint32_t ub = (uint32_t)b;
+        const uint32_t flip = (ub ^ (ub + ub)) & 0x80000000u;           // parity of the half turn
         const float qs = __uint_as_float(__float_as_uint(Qf) ^ flip);
         const float z = __int2float_rn(rem) * 4.656612873077393e-10f;   // 2^-31
         const float z2 = z * z;
@@ -145,7 +146,8 @@ __device__ __forceinline__ void scaled_phasor_f32(int32_t b, float Qf, float& cq
     if constexpr (SC == BJ_SINCOS_POLY32) {
         int32_t rem;
         asm("bfe.s32 %0, %1, 0, 31;" : "=r"(rem) : "r"(b));            // SGXT: nearest-half-turn remainder
-        const uint32_t flip = (uint32_t)(b ^ (b + b)) & 0x80000000u;    // parity of the half turn
+        const uint32_t ub = (uint32_t)b;
+        const uint32_t flip = (ub ^ (ub + ub)) & 0x80000000u;           // parity of the half turn
         const float qs = __uint_as_float(__float_as_uint(Qf) ^ flip);
         const float z = __int2float_rn(rem) * 4.656612873077393e-10f;   // 2^-31
         const float z2 = z * z;
@@ -839,7 +841,7 @@ template <int NIFO>
 struct TileWalker {
     double tau[NIFO];
     float q[6], q6l;
-    int d1[NIFO], d7[NIFO];     // uniform grids: one-bin step of the time-delay ramp, df tau_i, in 2^-32 turns (and x 7)
+    uint32_t d1[NIFO], d7[NIFO];   // uniform grids: one-bin step of the time-delay ramp, df tau_i, in 2^-32 turns (and x 7); binary angles wrap mod 2^32
 };
 
 // one step: 8 walkers x 32 bins per warp.  `limit` = number of valid bins of the step (32 except at the ragged end
@@ -891,11 +893,11 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
         unpack2(q, Qf[m][0], Qf[m][1]);
     }
     // ---- per bin and detector: ramp, phasor, packed complex MAC ----
-    int e[NIFO];
+    uint32_t e[NIFO];
     if constexpr (IRAMP) {
         const double fc = *reinterpret_cast<const double*>(base + R::kF) + df16;     // bin 16 of the step
 #pragma unroll
-        for (int i = 0; i < NIFO; ++i) e[i] = __double2loint(fma(fc, w.tau[i], kMagic)) + (2 * t - 16) * w.d1[i];
+        for (int i = 0; i < NIFO; ++i) e[i] = (uint32_t)__double2loint(fma(fc, w.tau[i], kMagic)) + (uint32_t)(2 * t - 16) * w.d1[i];
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
@@ -921,7 +923,7 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
                 float cq, sq;
                 int32_t b;
                 if constexpr (IRAMP) {
-                    b = __double2loint(D[m][h]) + e[i];
+                    b = (int32_t)((uint32_t)__double2loint(D[m][h]) + e[i]);
                     e[i] += h == 0 ? w.d1[i] : w.d7[i];           // next bin of this lane: + 1, then + 7
                 } else {
                     b = __double2loint(fma(f, w.tau[i], D[m][h]));
@@ -993,8 +995,8 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
 #pragma unroll
     for (int i = 0; i < NIFO; ++i) {
         w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
-        w.d1[i] = __double2loint(fma(df, w.tau[i], kMagic));
-        w.d7[i] = 7 * w.d1[i];
+        w.d1[i] = (uint32_t)__double2loint(fma(df, w.tau[i], kMagic));
+        w.d7[i] = 7u * w.d1[i];
     }
     const double df16 = 16.0 * df;
 
