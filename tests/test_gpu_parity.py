@@ -184,6 +184,21 @@ def test_c2_full_size_properties(c2_full):
         assert abs((l1[r] + lp[r]) + hh) <= 2 * harness.tolerance(l1[r]) + 1e-6 * hh
 
 
+@pytest.mark.parametrize("approx", ["TaylorF2_3.5PN", "TaylorF2_5.5PN_7.5PNTides"])
+def test_c2_full_size_production_kernel_vs_fp64_kernel(c2_full, approx):
+    """8192 walkers (posterior-scale and prior-scale boxes) x 521 729 bins: the tensor-core mixed-precision kernel
+    against the all-FP64 validation kernel, itself pinned to the reference on the golden subset.  Catches rare
+    parameter-dependent failures the 256 golden points could miss."""
+    cfg, gold, net = c2_full
+    names, const = _names(gold), syn.constants(cfg)
+    Xa, _ = syn.draw_walkers(cfg, 4096, 91, "narrow")
+    Xb, _ = syn.draw_walkers(cfg, 4096, 92, "wide")
+    X = np.concatenate([Xa, Xb])
+    fast = _like(cfg, gold, net=net, approx=approx).log_like_batch(X, names, const)
+    slow = _like(cfg, gold, net=net, approx=approx, sincos="fp64").log_like_batch(X, names, const)
+    _check(fast, slow, "C2 full, 8192 walkers, %s: production vs FP64 kernel" % approx)
+
+
 @pytest.mark.parametrize("sincos", ["mufu", "poly32", "fp64"])
 def test_wide_phase_path_subsolar_mass(sincos):
     """Sub-solar-mass binaries accumulate > 2^19 turns of phase, beyond the range of the binary-angle trick: the
