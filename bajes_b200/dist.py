@@ -46,6 +46,18 @@ class ShardedEvaluator:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else torch.device("cpu")
         self.local_eval_device = local_eval_device
+        self._pin_x = None          # pinned staging of the sampler rank (CUDA only): X in, gathered logL out
+        self._pin_out = None
+
+    def _pinned(self, name, numel):
+        """A persistent pinned host buffer of at least ``numel`` doubles (CUDA devices only; None on CPU)."""
+        if self.device.type != "cuda":
+            return None
+        buf = getattr(self, name)
+        if buf is None or buf.numel() < numel:
+            buf = self.torch.empty(max(numel, 1), dtype=self.torch.float64).pin_memory()
+            setattr(self, name, buf)
+        return buf
 
     def evaluate(self, X: Optional[np.ndarray]) -> np.ndarray:
         torch, dist = self.torch, self.dist
@@ -60,7 +72,14 @@ class ShardedEvaluator:
         if W < 0:                       # shutdown signal for the worker loop
             return None
         if self.rank == self.src:
-            xt = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(self.device)
+            xh = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64))
+            pin = self._pinned("_pin_x", xh.numel())
+            if pin is not None:                      # pageable -> pinned -> device: the H2D copy runs at PCIe speed
+                stage = pin[:xh.numel()].view(xh.shape)
+                stage.copy_(xh)
+                xt = stage.to(self.device, non_blocking=True)
+            else:
+                xt = xh.to(self.device)
         else:
             xt = torch.empty((W, self.ndim), dtype=torch.float64, device=self.device)
         dist.broadcast(xt, src=self.src, group=self.group)
@@ -77,7 +96,14 @@ class ShardedEvaluator:
             send[:len(out)] = torch.as_tensor(out).to(self.device)
         recv = torch.empty(chunk * self.world, dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(recv, send, group=self.group)
-        recv = recv.cpu().numpy().reshape(self.world, chunk)
+        pin = self._pinned("_pin_out", recv.numel()) if self.rank == self.src else None
+        if pin is not None:
+            host = pin[:recv.numel()]
+            host.copy_(recv, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            recv = host.numpy().reshape(self.world, chunk)
+        else:
+            recv = recv.cpu().numpy().reshape(self.world, chunk)
         return np.concatenate([recv[r, :hi[r] - lo[r]] for r in range(self.world)])
 
 
@@ -131,7 +157,14 @@ class FrequencySplitEvaluator:
         if W < 0:
             return None
         if self.rank == self.src:
-            xt = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(self.device)
+            xh = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64))
+            pin = self._pinned("_pin_x", xh.numel())
+            if pin is not None:                      # pageable -> pinned -> device: the H2D copy runs at PCIe speed
+                stage = pin[:xh.numel()].view(xh.shape)
+                stage.copy_(xh)
+                xt = stage.to(self.device, non_blocking=True)
+            else:
+                xt = xh.to(self.device)
         else:
             xt = torch.empty((W, self.ndim), dtype=torch.float64, device=self.device)
         if self.world > 1:
