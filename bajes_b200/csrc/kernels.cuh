@@ -499,6 +499,27 @@ __device__ __forceinline__ double amp_series_f64(double u, double L, const doubl
     return fma(u * u, t, 1.0);
 }
 
+// Systematic factor of the FP32 amplitude series at (u, L): the series with the exact coefficients over the series with
+// the float-rounded coefficients q[], BOTH evaluated in FP64 (no rounding noise enters).  It is ~1 + 3e-8 x (condition
+// number of the series) and varies smoothly with frequency, so it rides on the FP32 -> FP64 flush of the bins around
+// (u, L).  Next to a zero of the series -- the 3.5PN amplitude changes sign near v ~ 1, i.e. at the top of the band
+// for heavy binaries, where bajes applies no ISCO cut -- the ratio is meaningless (and the bins carry no weight):
+// it is then dropped rather than applied to the neighbouring bins.
+__device__ __forceinline__ double amp_series_correction(const float (&q)[6], float q6l, double u, double L,
+                                                        const double* __restrict__ coef, long stride, long w) {
+    const double q_exact = amp_series_f64(u, L, coef, stride, w);
+    double t = fma((double)q6l, L, (double)q[4]);
+    t = fma((double)q[5], u, t);
+    t = fma(t, u, (double)q[3]);
+    t = fma(t, u, (double)q[2]);
+    t = fma(t, u, (double)q[1]);
+    t = fma(t, u, (double)q[0]);
+    // 1 + (exact - rounded) / rounded: the difference is ~1e-7, so an FP32 reciprocal is plenty for the quotient
+    const double q_rounded = fma(u * u, t, 1.0);
+    const double c = (double)((float)(q_exact - q_rounded) * __frcp_rn((float)q_rounded));
+    return fabs(c) < 1e-4 ? 1.0 + c : 1.0;
+}
+
 // calibration envelope of the chunk's segment, FP32 packed (re, im): cal(t) = c0 + dc * t, t in the record
 template <int NIFO>
 struct Spcal32 {
@@ -721,18 +742,8 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
         const unsigned char* tile = stages + (size_t)slot * kTileBins * RB;
         const int nb = min(kTileBins, nb_total - t * kTileBins);
         {
-            // exact series vs the series with float-rounded coefficients, BOTH in FP64 arithmetic at the tile's
-            // first bin: the ratio is the smooth systematic factor (no rounding noise enters)
-            const double2 h0 = *reinterpret_cast<const double2*>(tile);
-            const double q_exact = amp_series_f64(h0.x, h0.y, coef, stride, wl);
-            double t = fma((double)w.q6l, h0.y, (double)w.q[4]);
-            t = fma((double)w.q[5], h0.x, t);
-            t = fma(t, h0.x, (double)w.q[3]);
-            t = fma(t, h0.x, (double)w.q[2]);
-            t = fma(t, h0.x, (double)w.q[1]);
-            t = fma(t, h0.x, (double)w.q[0]);
-            const double q_rounded = fma(h0.x * h0.x, t, 1.0);
-            corr = q_exact / q_rounded;
+            const double2 h0 = *reinterpret_cast<const double2*>(tile);          // the tile's first bin
+            corr = amp_series_correction(w.q, w.q6l, h0.x, h0.y, coef, stride, wl);
         }
         const int n_blocks = nb / kBlockBins;
 #pragma unroll 1
@@ -1053,19 +1064,15 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
         const unsigned char* tbasis = stages + (size_t)slot * kStageBytes;
         const unsigned char* tdata = tbasis + (size_t)R::kTileBins * BB;
         const int nb = min(R::kTileBins, nb_total - tl * R::kTileBins);
-        {
-            // smooth systematic factor of the FP32 amplitude series (see fullgrid_mixed_kernel), evaluated at the
-            // tile's CENTRE bin so that its drift over the tile cancels to first order; (u, L) of that bin come from
-            // the pair-format table
-            const double2 h0 = *reinterpret_cast<const double2*>(rec_ul + (size_t)(bin0 + (long)tl * R::kTileBins + nb / 2) * rec_ul_stride);
-            const double q_exact = amp_series_f64(h0.x, h0.y, coef, stride, wl);
-            double tq = fma((double)w.q6l, h0.y, (double)w.q[4]);
-            tq = fma((double)w.q[5], h0.x, tq);
-            tq = fma(tq, h0.x, (double)w.q[3]);
-            tq = fma(tq, h0.x, (double)w.q[2]);
-            tq = fma(tq, h0.x, (double)w.q[1]);
-            tq = fma(tq, h0.x, (double)w.q[0]);
-            corr = q_exact / fma(h0.x * h0.x, tq, 1.0);
+        // systematic factor of the FP32 amplitude series (amp_series_correction), one value per PAIR of 32-bin steps,
+        // taken at the pair's centre bin: lane t of a walker's quad evaluates pair t of the
+        // stage, the step loop fetches it by shuffle.  (u, L) of a bin come from the pair-format table.
+        static_assert(R::kTileBins <= 8 * kStepBins, "one correction value per lane covers at most 4 step pairs");
+        double corr_mine = 1.0;
+        if (2 * t * kStepBins < nb) {
+            const long centre = bin0 + (long)tl * R::kTileBins + min((2 * t + 1) * kStepBins, nb - 1);
+            const double2 h0 = *reinterpret_cast<const double2*>(rec_ul + (size_t)centre * rec_ul_stride);
+            corr_mine = amp_series_correction(w.q, w.q6l, h0.x, h0.y, coef, stride, wl);
         }
         mbar_wait(&full[slot], (uint32_t)((tl / kStagesT) & 1));
         const int n_steps = nb / kStepBins;
@@ -1074,13 +1081,16 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
             tile_step<NIFO, MODEL, SC, false, IRAMP, SPCAL>(tbasis + (size_t)st * kStepBins * BB,
                                                             tdata + (size_t)st * kStepBins * RB, afrag, w, g, t,
                                                             kStepBins, df16, acc, acc1);
-            if (st & 1) flush();                 // FP32 sums of 16 bins per lane
+            // FP32 sums of 8 bins per lane go to FP64 (16 would save 1.5 % and double the worst-case rounding noise:
+            // 1 walker in 50 000 then leaves the tolerance)
+            corr = __shfl_sync(0xffffffffu, corr_mine, (lane & ~3) | (st >> 1));
+            flush();
         }
-        if (n_steps & 1) flush();
         if (n_steps * kStepBins < nb) {
             tile_step<NIFO, MODEL, SC, true, IRAMP, SPCAL>(tbasis + (size_t)n_steps * kStepBins * BB,
                                                            tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
                                                            nb - n_steps * kStepBins, df16, acc, acc1);
+            corr = __shfl_sync(0xffffffffu, corr_mine, (lane & ~3) | (n_steps >> 1));
             flush();
         }
         __syncthreads();

@@ -157,14 +157,7 @@ class FrequencySplitEvaluator:
         if W < 0:
             return None
         if self.rank == self.src:
-            xh = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64))
-            pin = self._pinned("_pin_x", xh.numel())
-            if pin is not None:                      # pageable -> pinned -> device: the H2D copy runs at PCIe speed
-                stage = pin[:xh.numel()].view(xh.shape)
-                stage.copy_(xh)
-                xt = stage.to(self.device, non_blocking=True)
-            else:
-                xt = xh.to(self.device)
+            xt = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(self.device)
         else:
             xt = torch.empty((W, self.ndim), dtype=torch.float64, device=self.device)
         if self.world > 1:

@@ -389,3 +389,23 @@ def test_kernel_variants_vs_reference_golden(env, approx, monkeypatch):
     _check(got, gold["logl_%s_marg0" % approx][:n], "C2_small %s %s" % (approx, env or "default"))
     threads = like.engine.last_launch_info()[2]
     assert threads == (128 if "BAJES_B200_NO_TC" in env else 256)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2_small"])
+@pytest.mark.parametrize("sincos", ["mufu", "poly32"])
+def test_hundred_thousand_walkers_vs_fp64_kernel(name, sincos):
+    """100 003 walkers (posterior-scale + prior-scale boxes) against the all-FP64 validation kernel.  At this count the
+    rare parameter combinations show up -- e.g. heavy binaries whose 3.5PN amplitude series changes sign inside the
+    band (bajes applies no ISCO cut): the per-stage amplitude correction used to blow up there (500 x the tolerance
+    for 1 walker in 20 000) -- and so does the worst case of the FP32 rounding noise."""
+    cfg = syn.CONFIGS[name]
+    cl = syn.product_classes()
+    net = syn.build_network(cfg, cl)
+    W = 100003
+    Xa, names = syn.draw_walkers(cfg, W // 2, 11, "narrow")
+    Xb, _ = syn.draw_walkers(cfg, W - W // 2, 12, "wide")
+    X = np.concatenate([Xa, Xb])
+    const = syn.constants(cfg)
+    slow = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], sincos="fp64").log_like_batch(X, names, const)
+    fast = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], sincos=sincos).log_like_batch(X, names, const)
+    _check(fast, slow, "%s, 100 003 walkers, %s vs FP64 kernel" % (name, sincos), frac=0.8)
