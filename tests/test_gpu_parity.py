@@ -409,3 +409,52 @@ def test_hundred_thousand_walkers_vs_fp64_kernel(name, sincos):
     slow = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], sincos="fp64").log_like_batch(X, names, const)
     fast = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], sincos=sincos).log_like_batch(X, names, const)
     _check(fast, slow, "%s, 100 003 walkers, %s vs FP64 kernel" % (name, sincos), frac=0.8)
+
+
+# ------------------------------------------------------------------------------------------------------
+# many points against the oracle port evaluated live on the host (the golden files hold a few dozen points each)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("marg", [False, True])
+def test_roq_many_points_vs_port(marg):
+    from test_oracle_golden import _roq_port
+    gold = load_golden("roq_small.npz")
+    cfg, net, roq = _roq_port(gold)
+    port_like = harness.port_likelihood(cfg, marg_phi_ref=marg, roq=roq, net=net)
+    ifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"],
+                        marg_phi_ref=marg, roq=roq)
+    Xa, names = syn.draw_walkers(cfg, 1500, 31, "narrow")
+    Xb, _ = syn.draw_walkers(cfg, 1500, 32, "wide")
+    X = np.concatenate([Xa, Xb])
+    # keep the time shifts inside the tabulated tc range most of the time, leave some outside (-> -inf)
+    it = names.index("time_shift")
+    t_lo, t_hi = gold["t_bounds"]
+    X[:, it] = np.random.default_rng(33).uniform(t_lo - 0.06, t_hi + 0.06, len(X))
+    const = syn.constants(cfg)
+    with np.errstate(all="ignore"):
+        ref = harness.eval_batch(port_like, X, names, const)
+    ref = np.where(np.isfinite(ref), ref, -np.inf)
+    got = like.log_like_batch(X, names, const)
+    assert np.isfinite(ref).sum() > 1000 and np.isneginf(ref).sum() > 10
+    _check(got, ref, "ROQ, 3000 points, marg=%s" % marg)
+
+
+@pytest.mark.parametrize("mphi", [False, True])
+def test_time_marginalised_many_points_vs_port(mphi):
+    from oracle import bajes_port as port
+    cfg = syn.CONFIGS["C1"]
+    cl = harness.port_classes()
+    net = syn.build_network(cfg, cl)
+    ref_like = port.GWLikelihoodPort(net[0], net[1], net[2], net[3], net[4], cfg["srate"], cfg["seglen"], cfg["approx"],
+                                     marg_time_shift=True, marg_phi_ref=mphi)
+    ifos, datas, dets, noises, f = product_network_from_port(cfg, syn.build_network(cfg, cl))
+    like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"],
+                        marg_time_shift=True, marg_phi_ref=mphi)
+    Xa, names = syn.draw_walkers(cfg, 600, 41, "narrow")
+    Xb, _ = syn.draw_walkers(cfg, 600, 42, "wide")
+    X = np.concatenate([Xa, Xb])
+    const = syn.constants(cfg)
+    with np.errstate(all="ignore"):
+        ref = harness.eval_batch(ref_like, X, names, const)
+    got = like.log_like_batch(X, names, const)
+    _check(got, ref, "time-marginalised C1, 1200 points, mphi=%s" % mphi)
