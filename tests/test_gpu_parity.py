@@ -274,13 +274,13 @@ def test_relbin_vs_port_restatement(marg):
                                marg_phi_ref=marg)
     assert like.Nbin == ref.Nbin and np.array_equal(like.fbin_ind, ref.fbin_ind)
     np.testing.assert_allclose(like.sdat, ref.sdat, rtol=1e-8, atol=1e-9 * np.max(np.abs(ref.sdat)))
-    xa, names = syn.draw_walkers(cfg, 96, 41, "narrow")
-    xb, _ = syn.draw_walkers(cfg, 32, 42, "wide")
+    xa, names = syn.draw_walkers(cfg, 1500, 41, "narrow")
+    xb, _ = syn.draw_walkers(cfg, 500, 42, "wide")
     X = np.concatenate([xa, xb])
     const = syn.constants(cfg)
     got = like.log_like_batch(X, names, const)
     want = harness.eval_batch(ref, X, names, const)
-    _check(got, want, "relbin marg=%s" % marg)
+    _check(got, want, "relbin, 2000 points, marg=%s" % marg)
     p = {k: float(v) for k, v in zip(names, X[3])}
     p.update(const)
     assert like.log_like(dict(p)) == got[3]
