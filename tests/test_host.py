@@ -236,3 +236,28 @@ def test_relbin_setup_matches_port():
     a = compute_sdat(fb, fbin1, ind1, psds, datas, h0s)
     b = port.relbin_summary_data(fb, fbin2, ind2, psds, datas, h0s)
     np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12 * np.max(np.abs(b)))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """``bench.py --impl reference`` (the CPU arm: oracle port on the host cores) runs without a GPU and prints ONE JSON
+    line with the keys of the benchmark contract; with RANK != 0 it exits without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-points", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "walker*bins/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("likelihood evals/sec") and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
