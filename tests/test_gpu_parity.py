@@ -458,3 +458,24 @@ def test_time_marginalised_many_points_vs_port(mphi):
         ref = harness.eval_batch(ref_like, X, names, const)
     got = like.log_like_batch(X, names, const)
     _check(got, ref, "time-marginalised C1, 1200 points, mphi=%s" % mphi)
+
+
+@pytest.mark.parametrize("kind,upd", [
+    ("C2_small", dict(seglen=4.0)), ("C2_small", dict(f_min=10.0)), ("C2_small", dict(ifos=["H1"])),
+    ("C2_small", dict(f_min=23.3, f_max=1777.7)), ("C2_small", dict(seglen=256.0, f_max=1024.0, srate=2048.0)),
+    ("C1", dict(seglen=2.0, f_max=512.0, srate=1024.0)), ("C1", dict(seglen=8.0, f_min=10.0))])
+def test_data_configurations_vs_fp64_kernel(kind, upd):
+    """Segment lengths from 2 to 256 s, bands from 10 Hz, off-grid band edges, one to three detectors: 20 011 walkers
+    each, production kernel against the all-FP64 validation kernel."""
+    cfg = dict(syn.CONFIGS[kind])
+    cfg.update(upd)
+    cl = syn.product_classes()
+    net = syn.build_network(cfg, cl)
+    W = 20011
+    Xa, names = syn.draw_walkers(cfg, W // 2, 51, "narrow")
+    Xb, _ = syn.draw_walkers(cfg, W - W // 2, 52, "wide")
+    X = np.concatenate([Xa, Xb])
+    const = syn.constants(cfg)
+    slow = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], sincos="fp64").log_like_batch(X, names, const)
+    fast = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"]).log_like_batch(X, names, const)
+    _check(fast, slow, "%s %s, 20 011 walkers vs FP64 kernel" % (kind, upd))
