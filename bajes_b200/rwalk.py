@@ -70,16 +70,40 @@ def unitcheck(U, nonbounded=None):
     return ok
 
 
-class _Chain(object):
-    """Recorded part of one chain: the accepted points and the chain length at which each was appended."""
-    __slots__ = ("pts", "pos")
+class _Chains(object):
+    """Recorded part of all chains: per chain the accepted points and the chain length at which each was appended
+    (between two accepts the chain repeats its last entry, so that is all there is to store).  Array-backed: appending
+    the accepts of one proposal round is a handful of fancy-indexed assignments, whatever the number of chains."""
 
-    def __init__(self):
-        self.pts, self.pos = [], []
+    def __init__(self, m, n, cap=32):
+        self.m, self.n, self.cap = m, n, cap
+        self.u = np.empty((m, cap, n))
+        self.v = np.empty((m, cap, n))
+        self.l = np.empty((m, cap))
+        self.pos = np.zeros((m, cap), dtype=np.int64)
+        self.count = np.zeros(m, dtype=np.int64)
 
-    def at(self, idx):
-        j = int(np.searchsorted(self.pos, idx, side="right")) - 1
-        return self.pts[j]
+    def _grow(self):
+        for name in ("u", "v", "l", "pos"):
+            old = getattr(self, name)
+            new = np.zeros((self.m, 2 * self.cap) + old.shape[2:], dtype=old.dtype)
+            new[:, :self.cap] = old
+            setattr(self, name, new)
+        self.cap *= 2
+
+    def append(self, idx, u, v, l, pos):
+        if len(idx) == 0:
+            return
+        k = self.count[idx]
+        if k.max() >= self.cap:
+            self._grow()
+        self.u[idx, k], self.v[idx, k], self.l[idx, k], self.pos[idx, k] = u, v, l, pos
+        self.count[idx] = k + 1
+
+    def at(self, c, step):
+        """Entry ``step`` of chain ``c``: the last accept appended at or before it."""
+        j = int(np.searchsorted(self.pos[c, :self.count[c]], step, side="right")) - 1
+        return self.u[c, j], self.v[c, j], self.l[c, j]
 
 
 class LockstepRandomWalk(object):
@@ -161,7 +185,7 @@ class LockstepRandomWalk(object):
         nlist = np.zeros(m, dtype=np.int64)
         act = np.full(m, np.inf)
         active = np.ones(m, dtype=bool)
-        chains = [_Chain() for _ in range(m)]
+        chains = _Chains(m, n)
         old_act = float(self.walks)
 
         while True:
@@ -201,9 +225,7 @@ class LockstepRandomWalk(object):
                 a_idx = good[acc]
                 u[a_idx], v[a_idx], logl[a_idx] = u_prop[ok][acc], v_prop[acc], l_prop[acc]
                 accept[a_idx] += 1
-                for c in a_idx:
-                    chains[c].pts.append((u[c].copy(), v[c].copy(), float(logl[c])))
-                    chains[c].pos.append(int(nlist[c]))
+                chains.append(a_idx, u[a_idx], v[a_idx], logl[a_idx], nlist[a_idx])
                 nlist[a_idx] += 1
                 r_idx = good[~acc]
                 reject[r_idx] += 1
@@ -222,7 +244,7 @@ class LockstepRandomWalk(object):
             lo = int(0.5 * self.nact * act[c]) if np.isfinite(act[c]) else None
             if lo is not None and lo < nlist[c]:
                 pick = states[c].randint(lo, nlist[c]) if self.draws == "chain" else int(self._rng.integers(lo, nlist[c]))
-                out_u[c], out_v[c], out_l[c] = chains[c].at(pick)
+                out_u[c], out_v[c], out_l[c] = chains.at(c, pick)
             else:
                 fresh.append(c)
         if fresh:
