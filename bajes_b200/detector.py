@@ -115,12 +115,24 @@ class Detector(object):
         dphase = (gps_time - self.reference_time) / self.sday * (2.0 * np.pi)
         return (self.gmst_reference + dphase) % (2.0 * np.pi)
 
-    def time_delay_from_earth_center(self, right_ascension, declination, t_gps):
-        """Scalar geometry helper (detector.py:318-357); the batched path computes this on the device."""
+    def time_delay_from_location(self, other_location, right_ascension, declination, t_gps):
+        """``t_here - t_there`` for a signal from (ra, dec) (detector.py:334-357); scalar geometry helper."""
         ang = self.gmst_estimate(t_gps) - right_ascension
         cd = np.cos(declination)
         ehat = np.array([cd * np.cos(ang), cd * -np.sin(ang), np.sin(declination)])
-        return (np.zeros(3) - self.location).dot(ehat) / CLIGHT_SI
+        return (np.asarray(other_location, dtype=float) - self.location).dot(ehat) / CLIGHT_SI
+
+    def time_delay_from_earth_center(self, right_ascension, declination, t_gps):
+        """detector.py:318-332; the batched path computes this on the device."""
+        return self.time_delay_from_location(np.zeros(3), right_ascension, declination, t_gps)
+
+    def time_delay_from_detector(self, other_detector, right_ascension, declination, t_gps):
+        """detector.py:359-376."""
+        return self.time_delay_from_location(other_detector.location, right_ascension, declination, t_gps)
+
+    def optimal_orientation(self, t_gps):
+        """(ra, dec) overhead of the detector at ``t_gps`` (detector.py:378-392)."""
+        return self.longitude + (self.gmst_estimate(t_gps) % (2.0 * np.pi)), self.latitude
 
     def antenna_pattern(self, right_ascension, declination, polarization, t_gps):
         """Scalar geometry helper (detector.py:268-316); the batched path computes this on the device."""

@@ -59,3 +59,32 @@ def test_golden_c1_is_reproducible_from_the_reference():
     got = harness.eval_batch(ref, gold["X"][:16], names, syn.constants(cfg))
     np.testing.assert_allclose(got, gold["logl_marg0"][:16], rtol=0, atol=1e-9)
     np.testing.assert_allclose([ref.dets[i].gmst_reference for i in cfg["ifos"]], gold["gmst_reference"])
+
+
+def test_detector_mirror_geometry_matches_the_reference_methods():
+    """The scalar geometry helpers the post-processing scripts call on ``Detector`` (detector.py:246-392): same numbers
+    from the product's mirror class and from the unmodified reference class, fed the same GMST reference."""
+    from bajes_b200 import synthetic as syn
+    from bajes_b200.detector import Detector
+    cl = harness.reference_classes()
+    rng = np.random.default_rng(4)
+    for ifo in ("H1", "L1", "V1"):
+        ref = cl.Detector(ifo, syn.T_GPS)
+        mine = Detector(ifo, syn.T_GPS)
+        mine.gmst_reference, mine.sday = ref.gmst_reference, ref.sday
+        other = cl.Detector("V1" if ifo != "V1" else "H1", syn.T_GPS)
+        for _ in range(20):
+            ra, dec, psi = rng.uniform(0, 2 * np.pi), np.arcsin(rng.uniform(-1, 1)), rng.uniform(0, np.pi)
+            t = syn.T_GPS + rng.uniform(-100, 100)
+            assert mine.gmst_estimate(t) == ref.gmst_estimate(t)
+            assert np.isclose(mine.time_delay_from_earth_center(ra, dec, t), ref.time_delay_from_earth_center(ra, dec, t),
+                              rtol=1e-13, atol=1e-18)
+            assert np.isclose(mine.time_delay_from_detector(other, ra, dec, t),
+                              ref.time_delay_from_detector(other, ra, dec, t), rtol=1e-13, atol=1e-18)
+            loc = rng.uniform(-6e6, 6e6, 3)
+            assert np.isclose(mine.time_delay_from_location(loc, ra, dec, t), ref.time_delay_from_location(loc, ra, dec, t),
+                              rtol=1e-13, atol=1e-18)
+            assert np.allclose(mine.antenna_pattern(ra, dec, psi, t), ref.antenna_pattern(ra, dec, psi, t), rtol=1e-12,
+                               atol=1e-15)
+            assert np.allclose(mine.optimal_orientation(t), ref.optimal_orientation(t), rtol=1e-14)
+        assert np.isclose(mine.light_travel_time_to_detector(other), ref.light_travel_time_to_detector(other), rtol=1e-14)
