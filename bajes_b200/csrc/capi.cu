@@ -84,6 +84,10 @@ struct bj_ctx {
     void* d_rec = nullptr;
     void* d_tile_basis = nullptr; // tables of the tensor-core kernel; null: Horner kernels only
     double grid_df = 0.0;         // bin spacing if the in-band grid is uniform (integer time-delay ramps), else 0
+    bool rot = false;             // tile tables in the rotation layout (kernels.cuh: tile_step_rot)
+    int n_precise = 0;            // chunks [0, n_precise): the FP64 window (heaviest bins), evaluated by fullgrid_kernel
+    double* d_rec64 = nullptr;    // FP64 records of the window's slots [prec_lo, prec_hi)
+    long prec_lo = 0, prec_hi = 0;
     void* d_tile_data = nullptr;
     double* d_freqs = nullptr;
     double* d_gram = nullptr;
@@ -161,6 +165,7 @@ static int init_common(bj_ctx* c, const bj_config* cfg) {
     c->cfg.dh_fix_im = 0.0;
     c->cfg.f_lo = 0.0;
     c->cfg.f_hi = 0.0;
+    c->cfg.grid_df = 0.0;
     memset(&c->dims, 0, sizeof(c->dims));
     for (int i = 0; i < BJ_MAX_IFO; ++i) c->cfg.det[i] = cfg->det[i];
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -213,9 +218,17 @@ struct Layout {
     std::vector<int> cell_band, cell_seg;
     std::vector<ChunkDesc> chunks;
     int per = 0;
+    int n_precise = 0;               // chunks [0, n_precise) of the list: the window evaluated in FP64
+    long prec_lo = 0, prec_hi = 0;   // its slot range
 };
 
-static int build_layout(Layout& L, long n, const double* freqs, const bj_extras* ex) {
+// binweight[k] ~ share of bin k in <h|h> of an inspiral (sum_i f^(-7/3) / S_i).  The shortest run of consecutive slots
+// that holds the fraction prec_share of the sum of SQUARED weights (the bins whose terms are signal-dominated at high SNR,
+// where FP32 rounding does not average down), at most prec_frac of the table, is cut into small chunks that a launch of
+// the FP64 window kernel evaluates.  For the design PSDs of H1/L1/V1 a share of 0.9 is the band 20-87 Hz: 1.6 % of the
+// bins of a 128 s segment sampled to 4096 Hz.
+static int build_layout(Layout& L, long n, const double* freqs, const bj_extras* ex, const std::vector<double>* binweight,
+                        double prec_share, double prec_frac) {
     const int nsp = ex ? ex->nspcal : 0, nw = ex ? ex->nweights : 0;
     std::vector<int> band(n, 0), seg(n, 0);
     std::vector<double> tt(n, 0.0);
@@ -264,21 +277,59 @@ static int build_layout(Layout& L, long n, const double* freqs, const bj_extras*
     per = ((per + kTileBins - 1) / kTileBins) * kTileBins;
     if (per < 256) per = 256;
     L.per = (int)per;
+    // the precise window [prec_lo, prec_hi) in slot space (multiples of 256 slots)
+    L.prec_lo = L.prec_hi = 0;
+    if (binweight && prec_frac > 0.0 && prec_share > 0.0 && total > 512) {
+        std::vector<double> cum(total + 1, 0.0);
+        for (long sidx = 0; sidx < total; ++sidx) {
+            const double w = L.slot_real[sidx] ? (*binweight)[L.slot_bin[sidx]] : 0.0;
+            cum[sidx + 1] = cum[sidx] + (std::isfinite(w) ? w * w : 0.0);
+        }
+        // shortest window with the requested share (two pointers), then rounded up to whole 256-slot chunks and capped
+        const double want = std::fmin(prec_share, 1.0) * cum[total];
+        long best_len = total, best_lo = 0, j = 0;
+        for (long a = 0; a < total; a += 2) {
+            while (j < total && cum[j] - cum[a] < want) ++j;
+            if (cum[j] - cum[a] < want) break;
+            if (j - a < best_len) { best_len = j - a; best_lo = a; }
+        }
+        long win = ((best_len + 255) / 256) * 256;
+        const long cap = (long)std::ceil(prec_frac * (double)total / 256.0) * 256;
+        if (win > cap) {                 // capped: the window of that length with the largest share
+            win = cap;
+            best_lo = 0;
+            for (long a = 0; a + win <= total; a += 2)
+                if (cum[a + win] - cum[a] > cum[best_lo + win] - cum[best_lo]) best_lo = a;
+        }
+        if (win > total) win = total & ~1L;
+        if (best_lo + win > total) best_lo = (total - win) & ~1L;
+        L.prec_lo = best_lo;
+        L.prec_hi = best_lo + win;
+    }
+    std::vector<ChunkDesc> fast;
     long s0 = 0;
     while (s0 < total) {
         const int cell = L.slot_cell[s0];
         long s1 = s0;
         while (s1 < total && L.slot_cell[s1] == cell) ++s1;
-        for (long a = s0; a < s1; a += per) {
-            ChunkDesc cd;
-            cd.start = (int)a;
-            cd.len = (int)std::min(per, s1 - a);
-            cd.band = L.cell_band[cell];
-            cd.seg = L.cell_seg[cell];
-            L.chunks.push_back(cd);
+        // pieces of this cell: before / inside / after the precise window
+        const long cut[4] = {s0, std::min(std::max(L.prec_lo, s0), s1), std::min(std::max(L.prec_hi, s0), s1), s1};
+        for (int piece = 0; piece < 3; ++piece) {
+            const bool precise = piece == 1;
+            const long step = precise ? 256 : per;
+            for (long a = cut[piece]; a < cut[piece + 1]; a += step) {
+                ChunkDesc cd;
+                cd.start = (int)a;
+                cd.len = (int)std::min(step, cut[piece + 1] - a);
+                cd.band = L.cell_band[cell];
+                cd.seg = L.cell_seg[cell];
+                (precise ? L.chunks : fast).push_back(cd);
+            }
         }
         s0 = s1;
     }
+    L.n_precise = (int)L.chunks.size();
+    L.chunks.insert(L.chunks.end(), fast.begin(), fast.end());
     return 0;
 }
 
@@ -337,6 +388,30 @@ static void build_records(std::vector<double>& rec, const Layout& L, const doubl
         if (!L.slot_real[sidx]) continue;
         for (int i = 0; i < NIFO; ++i)
             data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], r[4 + 2 * i], r[5 + 2 * i]);
+    }
+}
+
+// all-FP64 records of the precise window [lo, hi), data weights times the complex factor (sr + i si) that the epilogue's
+// common <d|h> correction (table scale, calibrated phasor bias) will undo again
+template <int NIFO>
+static void build_records_window(std::vector<double>& rec, const Layout& L, long lo, long hi, const double* freqs,
+                                 const double* const* data_ri, const double* const* psd, double seglen, double sr,
+                                 double si) {
+    constexpr int RS = Rec<NIFO>::kDoubles;
+    rec.assign((size_t)(hi - lo) * RS, 0.0);
+    const double four_over_t = 4.0 / seglen;
+    for (long sidx = lo; sidx < hi; ++sidx) {
+        const long k = L.slot_bin[sidx];
+        const BinStatics b = bin_statics(freqs[k], seglen);
+        double* r = &rec[(size_t)(sidx - lo) * RS];
+        r[0] = b.u; r[1] = b.L; r[2] = b.w5; r[3] = b.f;
+        if (!L.slot_real[sidx]) continue;
+        for (int i = 0; i < NIFO; ++i) {
+            double wr, wi;
+            data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            r[4 + 2 * i] = wr * sr - wi * si;
+            r[5 + 2 * i] = wr * si + wi * sr;
+        }
     }
 }
 
@@ -400,7 +475,7 @@ static int build_records_mixed(std::vector<unsigned char>& rec, const Layout& L,
 template <int MODEL>
 static void build_records_tile(std::vector<double>& tab_basis, std::vector<unsigned char>& rec, const Layout& L,
                                const double* freqs, const double* const* data_ri, const double* const* psd,
-                               double seglen, int nifo, int e2) {
+                               double seglen, int nifo, int e2, bool rot) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes;
     const size_t n = L.slot_bin.size();
@@ -439,11 +514,19 @@ static void build_records_tile(std::vector<double>& tab_basis, std::vector<unsig
         memcpy(r + R::kPair, hf, 8);
         const float tcal = (float)L.slot_t[sidx];
         memcpy(r + R::kT, &tcal, 4);
+        float dri[BJ_MAX_IFO][2];
         for (int i = 0; i < nifo; ++i) {
             double wr = 0.0, wi = 0.0;
             if (L.slot_real[sidx]) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
-            const float d2[2] = {(float)(wr * sc), (float)(wi * sc)};
-            memcpy(r + R::kData + 8 * i, d2, 8);
+            dri[i][0] = (float)(wr * sc);
+            dri[i][1] = (float)(wi * sc);
+        }
+        if (rot && nifo == 3) {
+            // rotation layout: (dr0, di0), (dr1, dr2), (di1, di2) -- the two rotated detectors share FFMA2 lanes
+            const float d6[6] = {dri[0][0], dri[0][1], dri[1][0], dri[2][0], dri[1][1], dri[2][1]};
+            memcpy(r + R::kData, d6, 24);
+        } else {
+            for (int i = 0; i < nifo; ++i) memcpy(r + R::kData + 8 * i, dri[i], 8);
         }
     }
 }
@@ -519,7 +602,23 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
     }
 
     Layout L;
-    if (build_layout(L, n_bins, freqs, ex)) { bj_destroy(c); return fail(BJ_ERR_INVALID, "len_weights do not cover the band"); }
+    {
+        // share of each bin in <h|h> of an inspiral; the precise window only exists in the mixed-precision modes
+        std::vector<double> bw((size_t)n_bins, 0.0);
+        for (int64_t k = 0; k < n_bins; ++k) {
+            double w = 0.0;
+            for (int i = 0; i < cfg->n_ifo; ++i) w += 1.0 / psd[i][k];
+            bw[k] = w * std::pow(freqs[k], -7.0 / 3.0);
+        }
+        double share = 0.9, frac = 0.08;
+        if (const char* ev = getenv("BAJES_B200_PRECISE_SHARE")) share = atof(ev);
+        if (const char* ev = getenv("BAJES_B200_PRECISE_FRAC")) frac = atof(ev);
+        if (cfg->sincos == BJ_SINCOS_FP64 || (ex && ex->marg_time_shift) || getenv("BAJES_B200_NO_TC")) frac = 0.0;
+        if (build_layout(L, n_bins, freqs, ex, &bw, share, frac)) { bj_destroy(c); return fail(BJ_ERR_INVALID, "len_weights do not cover the band"); }
+    }
+    c->n_precise = L.n_precise;
+    c->prec_lo = L.prec_lo;
+    c->prec_hi = L.prec_hi;
     c->n_cells = (int)L.cell_band.size();
     c->n_chunks = (int)L.chunks.size();
     c->bins_per_chunk = L.per;
@@ -573,12 +672,38 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
         c->calib[1] = eps[1];
         rec_ptr = recm.data();
         rec_bytes = recm.size();
+        if (c->n_precise > 0) {
+            // the epilogue multiplies every chunk sum by 2^e / (ar + i ai): pre-multiply the FP64 window by its inverse
+            std::vector<double> rec64;
+            const double inv = std::ldexp(1.0, -e2);
+            switch (cfg->n_ifo) {
+                case 1: build_records_window<1>(rec64, L, L.prec_lo, L.prec_hi, freqs, data_ri, psd, cfg->seglen, ar * inv, ai * inv); break;
+                case 2: build_records_window<2>(rec64, L, L.prec_lo, L.prec_hi, freqs, data_ri, psd, cfg->seglen, ar * inv, ai * inv); break;
+                default: build_records_window<3>(rec64, L, L.prec_lo, L.prec_hi, freqs, data_ri, psd, cfg->seglen, ar * inv, ai * inv); break;
+            }
+            cudaError_t e64 = upload(&c->d_rec64, rec64);
+            if (e64 != cudaSuccess) {
+                bj_destroy(c);
+                return fail(BJ_ERR_CUDA, "uploading the FP64 window failed: %s", cudaGetErrorString(e64));
+            }
+        }
         // the tensor-core kernel (phase as an FP64 GEMM) is the production path
         if (!getenv("BAJES_B200_NO_TC")) {
+            // uniform in-band grid (every FFT grid bajes produces): integer time-delay ramps, and one phasor per bin
+            // rotated to the other detectors
+            if (n_bins >= 2 && !getenv("BAJES_B200_NO_IRAMP")) {
+                const double df = (freqs[n_bins - 1] - freqs[0]) / (double)(n_bins - 1);
+                bool uniform = df > 0.0;
+                for (int64_t k = 0; k < n_bins && uniform; ++k)
+                    uniform = std::fabs(freqs[k] - (freqs[0] + (double)k * df)) <= 1e-7 * df;
+                if (uniform) c->grid_df = df;
+            }
+            c->rot = c->grid_df > 0.0 && cfg->n_ifo >= 2 && !getenv("BAJES_B200_NO_ROT");
+            if (c->rot) c->cfg.grid_df = c->grid_df;
             std::vector<unsigned char> rect;
             std::vector<double> basis;
-            if (cfg->approx == BJ_APPROX_TAYLORF2_35PN) build_records_tile<MODEL_35>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2);
-            else                                        build_records_tile<MODEL_GENERIC>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2);
+            if (cfg->approx == BJ_APPROX_TAYLORF2_35PN) build_records_tile<MODEL_35>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2, c->rot);
+            else                                        build_records_tile<MODEL_GENERIC>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2, c->rot);
             cudaError_t et = cudaMalloc(&c->d_tile_data, rect.size());
             if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_data, rect.data(), rect.size(), cudaMemcpyHostToDevice);
             if (et == cudaSuccess) et = cudaMalloc(&c->d_tile_basis, basis.size() * sizeof(double));
@@ -586,14 +711,6 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
             if (et != cudaSuccess) {
                 bj_destroy(c);
                 return fail(BJ_ERR_CUDA, "uploading the tensor-core tables failed: %s", cudaGetErrorString(et));
-            }
-            // uniform in-band grid (every FFT grid bajes produces): integer time-delay ramps
-            if (n_bins >= 2 && !getenv("BAJES_B200_NO_IRAMP")) {
-                const double df = (freqs[n_bins - 1] - freqs[0]) / (double)(n_bins - 1);
-                bool uniform = df > 0.0;
-                for (int64_t k = 0; k < n_bins && uniform; ++k)
-                    uniform = std::fabs(freqs[k] - (freqs[0] + (double)k * df)) <= 1e-7 * df;
-                if (uniform) c->grid_df = df;
             }
         }
     }
@@ -629,6 +746,7 @@ extern "C" int bj_destroy(bj_ctx* c) {
     cudaFree(c->d_rec);
     cudaFree(c->d_tile_basis);
     cudaFree(c->d_tile_data);
+    cudaFree(c->d_rec64);
     cudaFree(c->d_freqs);
     cudaFree(c->d_gram);
     cudaFree(c->d_chunks);
@@ -727,6 +845,29 @@ static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st, int 
 template <int NIFO, int MODEL, int SC, bool SPCAL>
 static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
     constexpr int RB = RecM<NIFO>::kBytes;
+    if (c0 < c->n_precise) {
+        // the heaviest bins in FP64 (chunks of 256 records; the table pointer is offset so that chunk.start indexes it)
+        constexpr int RS = Rec<NIFO>::kDoubles;
+        const int p1 = c1 < c->n_precise ? c1 : c->n_precise;
+        const size_t smem64 = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
+        dim3 pgrid((unsigned)(p1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
+        if (c->grid_df > 0.0 && !getenv("BAJES_B200_WINDOW_GENERIC")) {
+            auto pk = fullgrid_window_kernel<NIFO, MODEL, SPCAL>;
+            CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+            pk<<<pgrid, kThreads, smem64, st>>>(c->d_rec64 - (size_t)c->prec_lo * RS, c->d_chunks, c->d_coef,
+                                                c->cap_walkers, n_walkers, c->d_partial, c->d_coef_ex, c->dims,
+                                                c->d_spcal_freqs, c0, c->grid_df);
+        } else {
+            auto pk = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, SPCAL>;
+            CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+            pk<<<pgrid, kThreads, smem64, st>>>(c->d_rec64 - (size_t)c->prec_lo * RS, c->d_chunks, c->d_coef,
+                                                c->cap_walkers, n_walkers, c->d_partial, c->d_coef_ex, c->dims,
+                                                c->d_spcal_freqs, c0);
+        }
+        CUDA_TRY(cudaGetLastError());
+        c0 = p1;
+        if (c0 >= c1) return BJ_OK;
+    }
     const size_t smem = (size_t)kStages * kTileBins * RB + kStages * sizeof(uint64_t);
     auto kern = fullgrid_mixed_kernel<NIFO, MODEL, SC, false, SPCAL>;
     auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true, SPCAL>;
@@ -735,8 +876,11 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
     if (c->d_tile_basis) {
         constexpr int RT = TileRec<MODEL>::kBasisBytes + TileRec<MODEL>::kDataBytes;
         const size_t smem_t = (size_t)kStagesT * TileRec<MODEL>::kTileBins * RT + kStagesT * sizeof(uint64_t);
-        auto tkern = c->grid_df > 0.0 ? fullgrid_tile_kernel<NIFO, MODEL, SC, true, SPCAL>
-                                      : fullgrid_tile_kernel<NIFO, MODEL, SC, false, SPCAL>;
+        auto tkern = c->grid_df > 0.0 ? fullgrid_tile_kernel<NIFO, MODEL, SC, true, SPCAL, false>
+                                      : fullgrid_tile_kernel<NIFO, MODEL, SC, false, SPCAL, false>;
+        if constexpr (NIFO >= 2) {
+            if (c->rot) tkern = fullgrid_tile_kernel<NIFO, MODEL, SC, true, SPCAL, true>;
+        }
         CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         dim3 tgrid((unsigned)(c1 - c0), (unsigned)((n_walkers + kTileWalkers - 1) / kTileWalkers));
         tkern<<<tgrid, kTileThreads, smem_t, st>>>((const unsigned char*)c->d_tile_basis, (const unsigned char*)c->d_tile_data,

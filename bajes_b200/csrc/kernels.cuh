@@ -86,6 +86,13 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
     return d;
 }
 
+__device__ __forceinline__ unsigned long long neg2(unsigned long long a) {
+    // folds into the operand-negate modifier of FFMA2
+    unsigned long long d;
+    asm("{.reg .f32 lo, hi; mov.b64 {lo, hi}, %1; neg.f32 lo, lo; neg.f32 hi, hi; mov.b64 %0, {lo, hi};}" : "=l"(d) : "l"(a));
+    return d;
+}
+
 // ---- Q e^{-i theta} from a 32-bit binary angle (turns * 2^32, two's complement) ---------------------
 // Returns cq = Q cos(theta), sq = Q sin(theta) as doubles.
 //   POLY32 : theta = pi z + pi n with z = sext31(b) 2^-31 in [-1/2, 1/2); sin(pi z)/z and cos(pi z) are
@@ -167,11 +174,19 @@ __device__ __forceinline__ void scaled_phasor_f32(int32_t b, float Qf, float& cq
         sq = sf;
         cq = cf;
     } else {
+#ifdef BJ_DIAG_EXACT_PHASOR
+        // diagnostic build (scripts/diag_tail.py): FP64 sin/cos rounded once -- isolates the phasor error from the rest
+        double sd, cd;
+        sincospi(2.0 * ((double)b * 2.3283064365386963e-10), &sd, &cd);
+        sq = (float)sd * Qf;
+        cq = (float)cd * Qf;
+#else
         const float x = __int2float_rn(b) * 1.4629180792671596e-9f;
         float sf, cf;
         __sincosf(x, &sf, &cf);
         sq = sf * Qf;
         cq = cf * Qf;
+#endif
     }
 }
 
@@ -433,6 +448,213 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
 #pragma unroll 1
         for (; b + 2 <= nb; b += 2) process_bins<NIFO, MODEL, SC, 2, SPCAL>(tile + b * RS, w, sp, zr, zi);
         if (b < nb) process_bins<NIFO, MODEL, SC, 1, SPCAL>(tile + b * RS, w, sp, zr, zi);
+        __syncthreads();
+        if (threadIdx.x == 0 && t + kStages < n_tiles) {
+            fence_proxy_async();
+            issue(t + kStages, slot);
+        }
+    }
+
+    if (wi < n_walkers) {
+        double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            out[(2 * i + 0) * stride] = zr[i];
+            out[(2 * i + 1) * stride] = zi[i];
+        }
+    }
+}
+
+// ---- the FP64 window kernel ----------------------------------------------------------------------------------------
+// The production path evaluates the bins that carry most of the signal power -- where, at high SNR, the terms of <d|h>
+// are coherent and FP32 rounding does not average down -- in FP64 (capi.cu: build_layout, the "precise window": a few
+// per cent of the table, cut into chunks of 256 records).  Same structure as fullgrid_kernel (one thread = one walker,
+// TMA ring of FP64 records), but built for speed on a uniform grid:
+//   * ONE sin/cos per bin (detector 0), from the exactly reduced angle with FP64 polynomials on [-pi/4, pi/4];
+//   * the other detectors by FP64 rotation e^{-2 pi i f (tau_i - tau_0)}, advanced bin to bin by a complex multiplication
+//     (re-anchored exactly at every 64-bin tile: the recurrence never runs longer than that).
+// sin(x), cos(x) for |x| <= pi/4: Taylor polynomials of degree 13 / 12 (truncation error < 1e-14)
+__device__ __forceinline__ void sincos_turns_f64(double turns, double& s, double& c) {
+    const double r = turns - rint(turns);              // [-1/2, 1/2]
+    const double q = rint(4.0 * r);
+    const double x = fma(q, -0.25, r) * kTwoPi;        // |x| <= pi/4
+    const double x2 = x * x;
+    double sp = 1.6059043836821613e-10;                // 1/13!
+    sp = fma(sp, x2, -2.5052108385441720e-08);
+    sp = fma(sp, x2, 2.7557319223985893e-06);
+    sp = fma(sp, x2, -1.9841269841269841e-04);
+    sp = fma(sp, x2, 8.3333333333333332e-03);
+    sp = fma(sp, x2, -1.6666666666666666e-01);
+    sp = fma(sp * x2, x, x);
+    double cp = 2.0876756987868100e-09;                // 1/12!
+    cp = fma(cp, x2, -2.7557319223985888e-07);
+    cp = fma(cp, x2, 2.4801587301587302e-05);
+    cp = fma(cp, x2, -1.3888888888888889e-03);
+    cp = fma(cp, x2, 4.1666666666666664e-02);
+    cp = fma(cp, x2, -0.5);
+    cp = fma(cp, x2, 1.0);
+    const int qi = (int)q & 3;
+    const double s0 = (qi & 1) ? cp : sp, c0 = (qi & 1) ? sp : cp;
+    s = (qi & 2) ? -s0 : s0;
+    c = (qi == 1 || qi == 2) ? -c0 : c0;
+}
+
+template <int NIFO, int MODEL, bool SPCAL>
+__global__ void __launch_bounds__(kThreads, 2) fullgrid_window_kernel(const double* __restrict__ rec,
+                                                                      const ChunkDesc* __restrict__ chunks,
+                                                                      const double* __restrict__ coef, long stride,
+                                                                      long n_walkers, double* __restrict__ partial,
+                                                                      const double* __restrict__ coef_ex, ExtrasDims dims,
+                                                                      const double* __restrict__ spcal_freqs, int chunk0,
+                                                                      double df) {
+    constexpr int RS = Rec<NIFO>::kDoubles;
+    constexpr int NR = NIFO > 1 ? NIFO - 1 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileBins * RS * 8);
+
+    const long wi = (long)blockIdx.y * kThreads + threadIdx.x;
+    const long wl = wi < n_walkers ? wi : n_walkers - 1;
+
+    WalkerRegs<NIFO, MODEL> w;
+#pragma unroll
+    for (int j = 0; j < WalkerRegs<NIFO, MODEL>::NA; ++j) w.a[j] = coef[(C_A0 + j) * stride + wl];
+    w.a10 = coef[(C_A0 + 10) * stride + wl];
+    w.a12 = coef[(C_A0 + 12) * stride + wl];
+#pragma unroll
+    for (int j = 0; j < WalkerRegs<NIFO, MODEL>::NBQ; ++j) w.bq[j] = coef[(C_B0 + j) * stride + wl];
+    w.c8 = coef[C_C8 * stride + wl];
+    w.k0m = coef[C_K0 * stride + wl];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) w.q[j] = coef[(C_Q2 + j) * stride + wl];
+    w.q6l = coef[C_Q6L * stride + wl];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
+    // one-bin rotation of detector r + 1 against detector 0: e^{-2 pi i df (tau_i - tau_0)}
+    double dtau[NR], r1c[NR], r1s[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        dtau[r] = NIFO > 1 ? w.tau[(r + 1) % NIFO] - w.tau[0] : 0.0;
+        const double t = df * dtau[r];
+        sincos_turns_f64(t, r1s[r], r1c[r]);
+    }
+
+    double zr[NIFO], zi[NIFO];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; }
+
+    const int chunk_id = chunk0 + (int)blockIdx.x;
+    const ChunkDesc chunk = chunks[chunk_id];
+    const long bin0 = chunk.start;
+    const int nb_total = chunk.len;
+    const int n_tiles = (nb_total + kTileBins - 1) / kTileBins;
+    Spcal64<NIFO> sp;
+    if constexpr (SPCAL) {
+        sp.f0 = spcal_freqs[chunk.seg];
+        sp.inv_width = 1.0 / (spcal_freqs[chunk.seg + 1] - sp.f0);
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
+            sp.c0r[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg, 0) * stride + wl];
+            sp.c0i[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg, 1) * stride + wl];
+            sp.dcr[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 0) * stride + wl] - sp.c0r[i];
+            sp.dci[i] = coef_ex[ex_cal_slot(dims, i, chunk.seg + 1, 1) * stride + wl] - sp.c0i[i];
+        }
+    }
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int slot) {
+        const int nb = min(kTileBins, nb_total - tile * kTileBins);
+        const uint32_t bytes = (uint32_t)nb * RS * 8;
+        mbar_expect_tx(&full[slot], bytes);
+        tma_bulk_g2s(stages + (size_t)slot * kTileBins * RS, rec + (bin0 + (long)tile * kTileBins) * RS, bytes,
+                     &full[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages && s < n_tiles; ++s) issue(s, s);
+    }
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int slot = t % kStages;
+        mbar_wait(&full[slot], (uint32_t)((t / kStages) & 1));
+        const double* tile = stages + (size_t)slot * kTileBins * RS;
+        const int nb = min(kTileBins, nb_total - t * kTileBins);
+        // exact anchors of the rotations at the tile's first bin
+        double rc[NR], rs[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            double sn, cs;
+            sincos_turns_f64(tile[3] * dtau[r], sn, cs);
+            rc[r] = cs;
+            rs[r] = sn;                                  // R = rc - i rs
+        }
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            const double* rb = tile + (size_t)b * RS;
+            const double2 h0 = *reinterpret_cast<const double2*>(rb);
+            const double2 h1 = *reinterpret_cast<const double2*>(rb + 2);
+            const double u = h0.x, L = h0.y, w5 = h1.x, f = h1.y, u2 = u * u;
+            double ph;
+            if constexpr (MODEL == MODEL_35) {
+                double p = fma(w.a12, u2, w.a10);
+                p = fma(p, u2 * u, w.a[7]);
+#pragma unroll
+                for (int k = 6; k >= 2; --k) p = fma(p, u, w.a[k]);
+                p = fma(p, u2, w.a[0]);
+                const double bl = fma(w.bq[1], u, w.bq[0]);
+                ph = fma(w5, p, fma(L, bl, w.k0m));
+            } else {
+                double p = w.a[15], bl = w.bq[6];
+#pragma unroll
+                for (int k = 14; k >= 0; --k) p = fma(p, u, w.a[k]);
+#pragma unroll
+                for (int k = 5; k >= 0; --k) bl = fma(bl, u, w.bq[k]);
+                bl = fma(L, w.c8 * (u2 * u), bl);
+                ph = fma(w5, p, fma(L, bl, w.k0m));
+            }
+            double qq = fma(w.q6l, L, w.q[4]);
+            qq = fma(w.q[5], u, qq);
+#pragma unroll
+            for (int k = 3; k >= 0; --k) qq = fma(qq, u, w.q[k]);
+            const double Q = fma(u2, qq, 1.0);
+            double sn, cs;
+            sincos_turns_f64(fma(f, w.tau[0], ph), sn, cs);
+            const double pc = Q * cs, ps = Q * sn;       // Q e^{-i theta_0} = pc - i ps
+#pragma unroll
+            for (int i = 0; i < NIFO; ++i) {
+                double cq = pc, sq = ps;
+                if (i > 0) {
+                    // (pc - i ps)(rc - i rs)
+                    cq = pc * rc[i - 1] - ps * rs[i - 1];
+                    sq = ps * rc[i - 1] + pc * rs[i - 1];
+                }
+                if constexpr (SPCAL) {
+                    const double tt = fmin(fmax((f - sp.f0) * sp.inv_width, 0.0), 1.0);
+                    const double calr = fma(sp.dcr[i], tt, sp.c0r[i]), cali = fma(sp.dci[i], tt, sp.c0i[i]);
+                    const double c2 = cq * calr + sq * cali, s2 = sq * calr - cq * cali;
+                    cq = c2;
+                    sq = s2;
+                }
+                const double2 d = *reinterpret_cast<const double2*>(rb + 4 + 2 * i);
+                zr[i] = fma(d.x, cq, zr[i]);
+                zr[i] = fma(d.y, sq, zr[i]);
+                zi[i] = fma(d.y, cq, zi[i]);
+                zi[i] = fma(-d.x, sq, zi[i]);
+            }
+            // advance the rotations by one bin
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const double nc = rc[r] * r1c[r] - rs[r] * r1s[r];
+                const double ns = rs[r] * r1c[r] + rc[r] * r1s[r];
+                rc[r] = nc;
+                rs[r] = ns;
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0 && t + kStages < n_tiles) {
             fence_proxy_async();
@@ -766,7 +988,9 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
         }
     }
 
-    if (wi < n_walkers) {
+    // the fix-up pass replaces the sums of the flagged walkers only: every walker is written by exactly one path, so
+    // its bits do not depend on which other walkers share its tile
+    if (wi < n_walkers && (!ROBUST || coef[C_VALID * stride + wi] == 2.0)) {
         double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
@@ -965,7 +1189,152 @@ __device__ __forceinline__ void tile_step(const unsigned char* __restrict__ basi
     }
 }
 
-template <int NIFO, int MODEL, int SC, bool IRAMP, bool SPCAL>
+// ---- ROT: one phasor per bin, the other detectors by rotation ------------------------------------------------
+// The phase of detector i differs from detector 0's by 2 pi f (tau_i - tau_0) only, and on a uniform grid the bins of a
+// lane sit at fixed offsets j - 12.5, j in {0, 1, 8, 9, 16, 17, 24, 25}, from the lane's centre f_c:
+//     e^{-i theta_i,k} = e^{-i theta_0,k} . e^{-i (j - 12.5) eps_i} . E_i,      eps_i = 2 pi df (tau_i - tau_0),
+//     E_i = e^{-2 pi i f_c (tau_i - tau_0)}.
+// The offsets come in +- pairs {3.5, 4.5, 11.5, 12.5}: four (cos - 1, sin) constants per detector and walker (prologue,
+// FP64, rounded once; cos enters as 1 + rho so that its rounding error is ~1e-12).  Per bin, ONE phasor P = Q e^{-i theta_0}
+// (MUFU or polynomial) is rotated to the other detectors with exact-angle FP32 rotations (no recurrence: every term
+// sees two roundings, relative to itself), and E_i -- advanced per step in FP64 by e^{-i 32 eps_i} from an FP64 anchor
+// per chunk -- multiplies the 8-bin FP32 sums on their way into the FP64 accumulators.  2 instead of 2 NIFO MUFU per bin;
+// with three detectors the two rotated ones are packed into FFMA2 lanes (data table: (dr1, dr2), (di1, di2)).
+template <int NIFO>
+struct TileRot {
+    static constexpr int NR = NIFO > 1 ? NIFO - 1 : 1;
+    unsigned long long rho[4], sn[4];      // NR == 2: (detector 1, detector 2) packed; NR == 1: low half
+    double er[NR], ei[NR];                 // E_i of the current step
+    double rr[NR], ri[NR];                 // e^{-i 32 eps_i}
+};
+
+// accumulators: acc0 = (re, im) of detector 0; NR == 2: accR = (re1, re2), accI = (im1, im2); NR == 1: accR = (re1, im1).
+// The *_t twins take the calibration-weighted terms (SPCAL).
+template <int NIFO, int MODEL, int SC, bool GUARD, bool SPCAL>
+__device__ __forceinline__ void tile_step_rot(const unsigned char* __restrict__ basis, const unsigned char* __restrict__ base,
+                                              const double (&afrag)[TileRec<MODEL>::kSteps], const TileWalker<NIFO>& w,
+                                              const TileRot<NIFO>& rot, int g, int t, int limit, double df16,
+                                              unsigned long long& acc0, unsigned long long& accR, unsigned long long& accI,
+                                              unsigned long long& acc0_t, unsigned long long& accR_t,
+                                              unsigned long long& accI_t) {
+    using R = TileRec<MODEL>;
+    constexpr int RB = R::kDataBytes;
+    constexpr int NR = NIFO - 1;
+    static_assert(NIFO >= 2 && NIFO <= 3, "rotation path: two or three detectors");
+    double D[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { D[m][0] = 0.0; D[m][1] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < R::kSteps; ++s) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const double b = *reinterpret_cast<const double*>(basis + (size_t)(8 * m + g) * R::kBasisBytes + (4 * s + t) * 8);
+            dmma884(D[m], afrag[s], b);
+        }
+    }
+    float Qf[4][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const unsigned char* re = base + (size_t)(8 * m + 2 * t) * RB;
+        const unsigned long long up = *reinterpret_cast<const unsigned long long*>(re + R::kPair);
+        const unsigned long long lp = *reinterpret_cast<const unsigned long long*>(re + RB + R::kPair);
+        unsigned long long q = fma2(pack2(w.q6l, w.q6l), lp, pack2(w.q[4], w.q[4]));
+        q = fma2(pack2(w.q[5], w.q[5]), up, q);
+        q = fma2(q, up, pack2(w.q[3], w.q[3]));
+        q = fma2(q, up, pack2(w.q[2], w.q[2]));
+        q = fma2(q, up, pack2(w.q[1], w.q[1]));
+        q = fma2(q, up, pack2(w.q[0], w.q[0]));
+        q = fma2(mul2(up, up), q, pack2(1.0f, 1.0f));
+        unpack2(q, Qf[m][0], Qf[m][1]);
+    }
+    // detector 0's time-delay ramp in binary angles, anchored at the step's centre (see tile_step)
+    const double fc = *reinterpret_cast<const double*>(base + R::kF) + df16;
+    uint32_t e0 = (uint32_t)__double2loint(fma(fc, w.tau[0], kMagic)) + (uint32_t)(2 * t - 16) * w.d1[0];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (GUARD && 8 * m + 2 * t >= limit) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned char* rb = base + (size_t)(8 * m + 2 * t + h) * RB;
+            // offset of this bin from the lane's centre: j - 12.5 with j = 8 m + h
+            constexpr int kIdx[4][2] = {{3, 2}, {1, 0}, {0, 1}, {2, 3}};
+            const int idx = kIdx[m][h];
+            const bool pos = m >= 2;                             // sign of the offset
+            const int32_t b = (int32_t)((uint32_t)__double2loint(D[m][h]) + e0);
+            e0 += h == 0 ? w.d1[0] : w.d7[0];
+            float qt = 0.0f;
+            if constexpr (SPCAL) qt = Qf[m][h] * *reinterpret_cast<const float*>(rb + R::kT);
+            // the one phasor of this bin: (pc, ps) = Q (cos, sin) theta_0   (unit amplitude with SPCAL: Q and Q t enter on
+            // the accumulate)
+            float pc, ps;
+            scaled_phasor_f32<SC>(b, SPCAL ? 1.0f : Qf[m][h], pc, ps);
+            // ---- detector 0 ----
+            {
+                const unsigned long long d0 = *reinterpret_cast<const unsigned long long*>(rb + R::kData);
+                float dr, di, ar, ai;
+                unpack2(d0, dr, di);
+                if constexpr (SPCAL) {
+                    unpack2(mul2(d0, pack2(pc, pc)), ar, ai);
+                    const unsigned long long term = pack2(fmaf(di, ps, ar), fmaf(-dr, ps, ai));
+                    acc0 = fma2(term, pack2(Qf[m][h], Qf[m][h]), acc0);
+                    acc0_t = fma2(term, pack2(qt, qt), acc0_t);
+                } else {
+                    unpack2(fma2(d0, pack2(pc, pc), acc0), ar, ai);
+                    acc0 = pack2(fmaf(di, ps, ar), fmaf(-dr, ps, ai));
+                }
+            }
+            // ---- rotated detectors ----
+            if constexpr (NR == 2) {
+                // (c1, c2) = pc (1 + rho) -+ ps s ;  (s1, s2) = ps (1 + rho) +- pc s
+                unsigned long long cv = fma2(pack2(pc, pc), rot.rho[idx], pack2(pc, pc));
+                unsigned long long sv = fma2(pack2(ps, ps), rot.rho[idx], pack2(ps, ps));
+                if (pos) {
+                    cv = fma2(pack2(-ps, -ps), rot.sn[idx], cv);
+                    sv = fma2(pack2(pc, pc), rot.sn[idx], sv);
+                } else {
+                    cv = fma2(pack2(ps, ps), rot.sn[idx], cv);
+                    sv = fma2(pack2(-pc, -pc), rot.sn[idx], sv);
+                }
+                const unsigned long long drv = *reinterpret_cast<const unsigned long long*>(rb + R::kData + 8);   // (dr1, dr2)
+                const unsigned long long div = *reinterpret_cast<const unsigned long long*>(rb + R::kData + 16);  // (di1, di2)
+                if constexpr (SPCAL) {
+                    const unsigned long long tr = fma2(div, sv, mul2(drv, cv));
+                    const unsigned long long ti = fma2(neg2(drv), sv, mul2(div, cv));
+                    accR = fma2(tr, pack2(Qf[m][h], Qf[m][h]), accR);
+                    accI = fma2(ti, pack2(Qf[m][h], Qf[m][h]), accI);
+                    accR_t = fma2(tr, pack2(qt, qt), accR_t);
+                    accI_t = fma2(ti, pack2(qt, qt), accI_t);
+                } else {
+                    accR = fma2(drv, cv, accR);
+                    accR = fma2(div, sv, accR);
+                    accI = fma2(div, cv, accI);
+                    accI = fma2(neg2(drv), sv, accI);
+                }
+            } else {
+                float rho, sn, dum;
+                unpack2(rot.rho[idx], rho, dum);
+                unpack2(rot.sn[idx], sn, dum);
+                float c1 = fmaf(pc, rho, pc), s1 = fmaf(ps, rho, ps);
+                if (pos) { c1 = fmaf(-ps, sn, c1); s1 = fmaf(pc, sn, s1); }
+                else     { c1 = fmaf(ps, sn, c1);  s1 = fmaf(-pc, sn, s1); }
+                const unsigned long long d1 = *reinterpret_cast<const unsigned long long*>(rb + R::kData + 8);
+                float dr, di, ar, ai;
+                unpack2(d1, dr, di);
+                if constexpr (SPCAL) {
+                    unpack2(mul2(d1, pack2(c1, c1)), ar, ai);
+                    const unsigned long long term = pack2(fmaf(di, s1, ar), fmaf(-dr, s1, ai));
+                    accR = fma2(term, pack2(Qf[m][h], Qf[m][h]), accR);
+                    accR_t = fma2(term, pack2(qt, qt), accR_t);
+                } else {
+                    unpack2(fma2(d1, pack2(c1, c1), accR), ar, ai);
+                    accR = pack2(fmaf(di, s1, ar), fmaf(-dr, s1, ai));
+                }
+            }
+        }
+    }
+}
+
+template <int NIFO, int MODEL, int SC, bool IRAMP, bool SPCAL, bool ROT>
 __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_tile_kernel(const unsigned char* __restrict__ tab_basis,
                                                                   const unsigned char* __restrict__ tab_data,
                                                                   const unsigned char* __restrict__ rec_ul,
@@ -1012,7 +1381,7 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
     const double df16 = 16.0 * df;
 
     double zr[NIFO], zi[NIFO], yr[NIFO], yi[NIFO];            // y: the t-weighted sums (SPCAL)
-    unsigned long long acc[NIFO], acc1[NIFO];
+    unsigned long long acc[NIFO], acc1[NIFO];                 // ROT: acc[0] = detector 0, acc[1] = accR, acc[2] = accI
 #pragma unroll
     for (int i = 0; i < NIFO; ++i) { zr[i] = 0.0; zi[i] = 0.0; yr[i] = 0.0; yi[i] = 0.0; acc[i] = 0ull; acc1[i] = 0ull; }
 
@@ -1021,6 +1390,35 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
     const long bin0 = chunk.start;
     const int nb_total = chunk.len;
     const int n_tiles = (nb_total + R::kTileBins - 1) / R::kTileBins;
+
+    TileRot<NIFO> rot;
+    if constexpr (ROT) {
+        constexpr int NR = NIFO - 1;
+        float rf[2][8];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                rf[r][j] = r < NR ? (float)coef[(size_t)(C_ROT0 + kRotSlots * r + j) * stride + wl] : 0.0f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            rot.rho[a] = pack2(rf[0][a], rf[1][a]);
+            rot.sn[a] = pack2(rf[0][4 + a], rf[1][4 + a]);
+        }
+        // anchor of the chunk's first step at this lane's centre bin (2 t + 12.5 bins after the chunk's first bin)
+        const double f_first = *reinterpret_cast<const double*>(tab_data + (size_t)bin0 * RB + R::kF);
+        const double f_c = f_first + (2.0 * t + 12.5) * df;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            rot.rr[r] = coef[(size_t)(C_ROT0 + kRotSlots * r + 8) * stride + wl];
+            rot.ri[r] = coef[(size_t)(C_ROT0 + kRotSlots * r + 9) * stride + wl];
+            const double turns = f_c * (w.tau[r + 1] - w.tau[0]);
+            double sn, cs;
+            sincospi(2.0 * (turns - rint(turns)), &sn, &cs);
+            rot.er[r] = cs;
+            rot.ei[r] = -sn;
+        }
+    }
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -1043,18 +1441,58 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
 
     double corr = 1.0;
     auto flush = [&]() {
-#pragma unroll
-        for (int i = 0; i < NIFO; ++i) {
+        if constexpr (ROT) {
+            constexpr int NR = NIFO - 1;
             float re, im;
-            unpack2(acc[i], re, im);
-            zr[i] = fma((double)re, corr, zr[i]);
-            zi[i] = fma((double)im, corr, zi[i]);
-            acc[i] = 0ull;
+            unpack2(acc[0], re, im);
+            zr[0] = fma((double)re, corr, zr[0]);
+            zi[0] = fma((double)im, corr, zi[0]);
             if constexpr (SPCAL) {
-                unpack2(acc1[i], re, im);
-                yr[i] = fma((double)re, corr, yr[i]);
-                yi[i] = fma((double)im, corr, yi[i]);
-                acc1[i] = 0ull;
+                unpack2(acc1[0], re, im);
+                yr[0] = fma((double)re, corr, yr[0]);
+                yi[0] = fma((double)im, corr, yi[0]);
+            }
+            float sr[2], si[2], tr[2] = {0.0f, 0.0f}, ti[2] = {0.0f, 0.0f};
+            if constexpr (NR == 2) {
+                unpack2(acc[1], sr[0], sr[1]);
+                unpack2(acc[2], si[0], si[1]);
+                if constexpr (SPCAL) { unpack2(acc1[1], tr[0], tr[1]); unpack2(acc1[2], ti[0], ti[1]); }
+            } else {
+                unpack2(acc[1], sr[0], si[0]);
+                sr[1] = si[1] = 0.0f;
+                if constexpr (SPCAL) unpack2(acc1[1], tr[0], ti[0]);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                // z += corr E_r (sr + i si), then E_r advances by one step
+                const double fr = corr * rot.er[r], fi = corr * rot.ei[r];
+                zr[r + 1] = fma((double)sr[r], fr, fma(-(double)si[r], fi, zr[r + 1]));
+                zi[r + 1] = fma((double)sr[r], fi, fma((double)si[r], fr, zi[r + 1]));
+                if constexpr (SPCAL) {
+                    yr[r + 1] = fma((double)tr[r], fr, fma(-(double)ti[r], fi, yr[r + 1]));
+                    yi[r + 1] = fma((double)tr[r], fi, fma((double)ti[r], fr, yi[r + 1]));
+                }
+                const double nr = fma(rot.er[r], rot.rr[r], -rot.ei[r] * rot.ri[r]);
+                const double ni = fma(rot.er[r], rot.ri[r], rot.ei[r] * rot.rr[r]);
+                rot.er[r] = nr;
+                rot.ei[r] = ni;
+            }
+#pragma unroll
+            for (int i = 0; i < NIFO; ++i) { acc[i] = 0ull; acc1[i] = 0ull; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NIFO; ++i) {
+                float re, im;
+                unpack2(acc[i], re, im);
+                zr[i] = fma((double)re, corr, zr[i]);
+                zi[i] = fma((double)im, corr, zi[i]);
+                acc[i] = 0ull;
+                if constexpr (SPCAL) {
+                    unpack2(acc1[i], re, im);
+                    yr[i] = fma((double)re, corr, yr[i]);
+                    yi[i] = fma((double)im, corr, yi[i]);
+                    acc1[i] = 0ull;
+                }
             }
         }
     };
@@ -1078,6 +1516,12 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
         const int n_steps = nb / kStepBins;
 #pragma unroll 1
         for (int st = 0; st < n_steps; ++st) {
+            if constexpr (ROT)
+                tile_step_rot<NIFO, MODEL, SC, false, SPCAL>(tbasis + (size_t)st * kStepBins * BB,
+                                                             tdata + (size_t)st * kStepBins * RB, afrag, w, rot, g, t,
+                                                             kStepBins, df16, acc[0], acc[1], acc[NIFO - 1], acc1[0],
+                                                             acc1[1], acc1[NIFO - 1]);
+            else
             tile_step<NIFO, MODEL, SC, false, IRAMP, SPCAL>(tbasis + (size_t)st * kStepBins * BB,
                                                             tdata + (size_t)st * kStepBins * RB, afrag, w, g, t,
                                                             kStepBins, df16, acc, acc1);
@@ -1087,6 +1531,12 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
             flush();
         }
         if (n_steps * kStepBins < nb) {
+            if constexpr (ROT)
+                tile_step_rot<NIFO, MODEL, SC, true, SPCAL>(tbasis + (size_t)n_steps * kStepBins * BB,
+                                                            tdata + (size_t)n_steps * kStepBins * RB, afrag, w, rot, g, t,
+                                                            nb - n_steps * kStepBins, df16, acc[0], acc[1], acc[NIFO - 1],
+                                                            acc1[0], acc1[1], acc1[NIFO - 1]);
+            else
             tile_step<NIFO, MODEL, SC, true, IRAMP, SPCAL>(tbasis + (size_t)n_steps * kStepBins * BB,
                                                            tdata + (size_t)n_steps * kStepBins * RB, afrag, w, g, t,
                                                            nb - n_steps * kStepBins, df16, acc, acc1);

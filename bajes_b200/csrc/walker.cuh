@@ -41,8 +41,13 @@ enum : int {
     C_FP0 = 43,      // F+_i     [BJ_MAX_IFO]   (diagnostics / polarisation dump)
     C_FC0 = 46,      // Fx_i
     C_COSI = 49,
-    C_NUM = 50
+    // detector-to-detector rotations of the fused kernel (uniform grids; kernels.cuh: tile_step ROT), detector r + 1
+    // against detector 0, d = tau_{r+1} - tau_0, eps = 2 pi df d:  C_ROT0 + 10 r + {0..3} = cos(a eps) - 1,
+    // {4..7} = sin(a eps) for a = 3.5, 4.5, 11.5, 12.5 bins; {8, 9} = cos, -sin of 32 eps (advance per 32-bin step)
+    C_ROT0 = 50,
+    C_NUM = C_ROT0 + 10 * (BJ_MAX_IFO - 1)
 };
+constexpr int kRotSlots = 10;
 
 struct DeviceConfig {
     int approx;
@@ -53,6 +58,7 @@ struct DeviceConfig {
     double logZ_noise;
     double dh_fix_re, dh_fix_im;   // <d|h> correction: table scale / calibrated phasor bias (1 + 0i in fp64 mode)
     double f_lo, f_hi;             // in-band frequency range (0, 0 when the context has no full grid)
+    double grid_df;                // bin spacing of a uniform in-band grid, else 0
     bj_detector det[BJ_MAX_IFO];
 };
 
@@ -447,6 +453,26 @@ __device__ inline void walker_coefficients(const DeviceConfig& cfg, const ParamM
         out[C_FP0 + i] = fp;
         out[C_FC0 + i] = fc;
         ok = ok && isfinite(tau) && isfinite(fp) && isfinite(fc);
+    }
+    // rotation constants: the phase of detector i differs from detector 0's by 2 pi f (tau_i - tau_0) only
+    if (cfg.grid_df > 0.0) {
+        for (int i = 1; i < cfg.n_ifo; ++i) {
+            const double turns_per_bin = cfg.grid_df * (out[C_TAU0 + i] - out[C_TAU0]);
+            double* o = out + C_ROT0 + kRotSlots * (i - 1);
+            const double offs[4] = {3.5, 4.5, 11.5, 12.5};
+#pragma unroll 1
+            for (int a = 0; a < 4; ++a) {
+                double sh, ch, sn, cs;
+                sincospi(offs[a] * turns_per_bin, &sh, &ch);          // half angle: cos x - 1 = -2 sin^2(x / 2)
+                sincospi(2.0 * offs[a] * turns_per_bin, &sn, &cs);
+                o[a] = -2.0 * sh * sh;
+                o[4 + a] = sn;
+            }
+            double sn, cs;
+            sincospi(64.0 * turns_per_bin, &sn, &cs);
+            o[8] = cs;
+            o[9] = -sn;
+        }
     }
 
     // ---- validity (log_like.py:121-129): NaN/Inf anywhere in hp/hc, or hp identically zero ---
