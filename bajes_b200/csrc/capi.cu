@@ -1311,6 +1311,98 @@ extern "C" int bj_relbin_create(bj_ctx** out, const bj_config* cfg, int64_t n_ed
 }
 
 // ------------------------------------------------------------------------------------------------
+// multi-GPU result path over peer memory (include/bajes_b200.h)
+// ------------------------------------------------------------------------------------------------
+__global__ void peer_signal_kernel(long long* flags, int slot, long long value) {
+    // everything this stream wrote before (the epilogue's logL stores into the peer buffer) becomes visible system-wide
+    // before the flag does
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(flags + slot), "l"(value) : "memory");
+}
+
+__global__ void peer_wait_kernel(long long* flags, int first, int n, long long value, long long timeout_cycles) {
+    const long long t0 = clock64();
+    for (int s = first + (int)threadIdx.x; s < first + n; s += blockDim.x) {
+        long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(flags + s) : "memory");
+            if (v >= value) break;
+            if (clock64() - t0 > timeout_cycles) {
+                flags[BJ_PEER_FLAGS] = 1;                  // status word: timed out
+                break;
+            }
+            __nanosleep(200);
+        } while (true);
+    }
+    __threadfence_system();
+}
+
+extern "C" int bj_peer_create(int device, int64_t capacity_doubles, void** base_dev, unsigned char* handle64) {
+    if (!base_dev || !handle64 || capacity_doubles <= 0) return fail(BJ_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    void* p = nullptr;
+    const size_t bytes = (size_t)BJ_PEER_HEADER_BYTES + (size_t)capacity_doubles * sizeof(double);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(BJ_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *base_dev = p;
+    return BJ_OK;
+}
+
+extern "C" int bj_peer_open(int device, const unsigned char* handle64, void** base_dev) {
+    if (!base_dev || !handle64) return fail(BJ_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BJ_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle failed (no peer access between the two GPUs?): %s",
+                    cudaGetErrorString(e));
+    }
+    *base_dev = p;
+    return BJ_OK;
+}
+
+extern "C" int bj_peer_close(int device, void* base_dev, int opened_from_handle) {
+    if (!base_dev) return BJ_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    if (opened_from_handle) CUDA_TRY(cudaIpcCloseMemHandle(base_dev));
+    else                    CUDA_TRY(cudaFree(base_dev));
+    return BJ_OK;
+}
+
+extern "C" int bj_peer_signal(int device, void* base_dev, int32_t slot, int64_t value, void* stream) {
+    if (!base_dev || slot < 0 || slot >= BJ_PEER_FLAGS) return fail(BJ_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)base_dev, slot, (long long)value);
+    CUDA_TRY(cudaGetLastError());
+    return BJ_OK;
+}
+
+extern "C" int bj_peer_wait(int device, void* base_dev, int32_t first_slot, int32_t n_slots, int64_t value,
+                            double timeout_ms, void* stream) {
+    if (!base_dev || first_slot < 0 || n_slots < 0 || first_slot + n_slots > BJ_PEER_FLAGS)
+        return fail(BJ_ERR_INVALID, "bad arguments");
+    if (n_slots == 0) return BJ_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    const long long cycles = (long long)(timeout_ms * (double)(khz > 0 ? khz : 1000000));
+    peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((long long*)base_dev, first_slot, n_slots, (long long)value, cycles);
+    CUDA_TRY(cudaGetLastError());
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // issue-rate micro-benchmarks (roofline denominators for the FP64 / MUFU bound kernels)
 // ------------------------------------------------------------------------------------------------
 __global__ void peak_dfma_kernel(double* out, int iters, double seed) {

@@ -4,8 +4,9 @@ Multi-GPU evaluation: the walker batch is sharded across the ranks of a ``torch.
 (``Posterior.log_like`` is a pure function of one point; the reference farms points to workers the same
 way, bajes/pipe/utils/mpi.py:120-159), so the data path has NO collective: each walker's whole reduction
 happens on one GPU and results are bit-identical for any number of ranks.  The only communication is
-the plumbing around it -- broadcast of the [W, ndim] parameter block from the sampler rank and an
-all-gather of the W log-likelihoods (8 MB at W = 2^20: latency-, not bandwidth-bound).
+the plumbing around it -- one scatter of the [W, ndim] parameter block from the sampler rank, and the
+W log-likelihoods stored by every rank's epilogue kernel straight into the sampler rank's HBM over NVLink
+(peer memory; a gather on CPU).
 """
 from __future__ import annotations
 
@@ -22,18 +23,37 @@ def shard_bounds(n: int, world: int):
     return lo, hi
 
 
+class _RawCuda:
+    """Wraps a raw device address as a float64 vector for ``torch.as_tensor`` (CUDA array interface)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+HDR = 3                     # per-rank header of the scattered block: rows of this rank, offset of its first row, sequence
+CMD_SHUTDOWN, CMD_GROW = -1.0, -2.0
+
+
 class ShardedEvaluator:
-    """``evaluate(X)``: rank ``src`` supplies X [W, ndim]; every rank returns the full logL [W].
+    """``evaluate(X)``: rank ``src`` (the sampler) supplies X [W, ndim] and gets logL [W] back; every rank evaluates a
+    contiguous slice.  Per call there is ONE collective and, on the sampler rank, ONE host synchronisation:
 
-    ``local_eval(X_slice) -> logL_slice`` is the per-rank worker: on a GPU box it is
-    ``lambda Xs: like.log_like_batch(Xs, names, const)`` (or the device-pointer variant below); the CPU
-    tests pass any pure function.
-    """
+      out    the sampler rank packs, per rank, [rows, first row, sequence | that rank's rows] into a fixed-capacity
+             block and ONE ``scatter`` (NCCL over NVLink) delivers it -- 1/N of the batch per link instead of a
+             broadcast of all of it, and no separate size message;
+      back   no collective at all on CUDA: the sampler rank owns the result vector, the other ranks map it through a
+             CUDA IPC handle, and their epilogue kernel stores every logL straight into the sampler rank's HBM over
+             NVLink (``engine.PeerBuffer``; a system-scope flag per rank, awaited by a one-block kernel on the sampler
+             rank's stream, orders the device-to-host copy behind the remote stores).  On CPU (gloo tests) or without
+             peer access the slices come back with one ``gather``.
 
-    def __init__(self, local_eval: Callable[[np.ndarray], np.ndarray], ndim: int, group=None, device=None, src=0,
-                 local_eval_device=None):
-        """``local_eval_device(x_dev [w, ndim], out_dev [w])`` (optional, CUDA): evaluates a device-resident slice in
-        place on the current stream -- the shard then never leaves HBM between the broadcast and the all-gather."""
+    ``local_eval(X_slice) -> logL_slice`` is the per-rank host worker (CPU tests pass any pure function);
+    ``local_eval_device(x_dev [w, ndim], out_dev [w])`` evaluates a device-resident slice in place on the current
+    stream -- ``out_dev`` may be a view of the sampler rank's memory.  The capacity grows on demand (collectively).
+    The other ranks sit in ``serve()`` (the role of MPIPool.wait, bajes/pipe/utils/mpi.py:91-117)."""
+
+    def __init__(self, local_eval: Optional[Callable[[np.ndarray], np.ndarray]], ndim: int, group=None, device=None,
+                 src=0, local_eval_device=None, capacity: int = 4096, peer: Optional[bool] = None):
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -46,80 +66,161 @@ class ShardedEvaluator:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else torch.device("cpu")
         self.local_eval_device = local_eval_device
-        self._pin_x = None          # pinned staging of the sampler rank (CUDA only): X in, gathered logL out
-        self._pin_out = None
+        self.seq = 0
+        self.peer = None
+        self.want_peer = (self.device.type == "cuda" and local_eval_device is not None) if peer is None else bool(peer)
+        self.capacity = 0
+        if self.world > 1:
+            self._setup(int(capacity))
 
-    def _pinned(self, name, numel):
-        """A persistent pinned host buffer of at least ``numel`` doubles (CUDA devices only; None on CPU)."""
-        if self.device.type != "cuda":
-            return None
-        buf = getattr(self, name)
-        if buf is None or buf.numel() < numel:
-            buf = self.torch.empty(max(numel, 1), dtype=self.torch.float64).pin_memory()
-            setattr(self, name, buf)
-        return buf
-
-    def evaluate(self, X: Optional[np.ndarray]) -> np.ndarray:
+    # -- collective set-up (every rank, same capacity) ------------------------------------------------------------
+    def _setup(self, capacity: int):
         torch, dist = self.torch, self.dist
-        if self.world == 1:
-            return np.asarray(self.local_eval(np.ascontiguousarray(X, dtype=np.float64)))
-        # 1. batch size, then the parameter block, from the sampler rank
-        n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.capacity = int(capacity)
+        self.cap_rank = -(-self.capacity // self.world)
+        self.slot = HDR + self.cap_rank * self.ndim
+        self.recv = torch.empty(self.slot, dtype=torch.float64, device=self.device)
+        cuda = self.device.type == "cuda"
         if self.rank == self.src:
-            n[0] = -1 if X is None else len(X)
-        dist.broadcast(n, src=self.src, group=self.group)
-        W = int(n.item())
-        if W < 0:                       # shutdown signal for the worker loop
-            return None
-        if self.rank == self.src:
-            xh = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64))
-            pin = self._pinned("_pin_x", xh.numel())
-            if pin is not None:                      # pageable -> pinned -> device: the H2D copy runs at PCIe speed
-                stage = pin[:xh.numel()].view(xh.shape)
-                stage.copy_(xh)
-                xt = stage.to(self.device, non_blocking=True)
+            self.stage = torch.empty((self.world, self.slot), dtype=torch.float64, pin_memory=cuda)
+            self.send = self.stage if not cuda else torch.empty((self.world, self.slot), dtype=torch.float64,
+                                                                 device=self.device)
+            self.host_out = torch.empty(2 + self.capacity, dtype=torch.float64, pin_memory=cuda)
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+        self.out_view = None
+        if self.want_peer:
+            from . import engine
+            ok = torch.ones(1, dtype=torch.int32, device=self.device)
+            handle = [None]
+            try:
+                if self.rank == self.src:
+                    self.peer = engine.PeerBuffer.create(self.device.index, self.capacity)
+                    handle[0] = self.peer.handle
+            except Exception:
+                ok.zero_()
+            dist.broadcast_object_list(handle, src=self.src, group=self.group)
+            if self.rank != self.src:
+                try:
+                    self.peer = engine.PeerBuffer.open(self.device.index, handle[0], self.capacity)
+                except Exception:
+                    ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:                      # some pair of GPUs has no peer access: gather instead
+                if self.peer is not None:
+                    self.peer.close()
+                self.peer = None
             else:
-                xt = xh.to(self.device)
-        else:
-            xt = torch.empty((W, self.ndim), dtype=torch.float64, device=self.device)
-        dist.broadcast(xt, src=self.src, group=self.group)
-        # 2. each rank evaluates its contiguous slice (no data-path collective)
-        lo, hi = shard_bounds(W, self.world)
-        mine = xt[lo[self.rank]:hi[self.rank]]
-        # 3. all-gather (padded to equal chunks so one collective suffices)
-        chunk = max(h - l for l, h in zip(lo, hi))
-        send = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
-        if self.local_eval_device is not None and mine.shape[0] > 0:
-            self.local_eval_device(mine.contiguous(), send[:mine.shape[0]])
-        else:
-            out = np.asarray(self.local_eval(mine.cpu().numpy()), dtype=np.float64)
-            send[:len(out)] = torch.as_tensor(out).to(self.device)
-        recv = torch.empty(chunk * self.world, dtype=torch.float64, device=self.device)
-        dist.all_gather_into_tensor(recv, send, group=self.group)
-        pin = self._pinned("_pin_out", recv.numel()) if self.rank == self.src else None
-        if pin is not None:
-            host = pin[:recv.numel()]
-            host.copy_(recv, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            recv = host.numpy().reshape(self.world, chunk)
-        else:
-            recv = recv.cpu().numpy().reshape(self.world, chunk)
-        return np.concatenate([recv[r, :hi[r] - lo[r]] for r in range(self.world)])
+                # [status, pad, logL...] as a tensor (the flags sit in front of it)
+                from .engine import PEER_FLAGS
+                self.out_all = torch.as_tensor(_RawCuda(self.peer.base + PEER_FLAGS * 8, 2 + self.capacity),
+                                               device=self.device)
+                self.out_view = self.out_all[2:]
+        if self.peer is None:
+            self.ret = torch.empty(self.cap_rank, dtype=torch.float64, device=self.device)
+            self.ret_all = ([torch.empty(self.cap_rank, dtype=torch.float64, device=self.device)
+                             for _ in range(self.world)] if self.rank == self.src else None)
 
+    # -- one batch ----------------------------------------------------------------------------------------------------
+    def _scatter(self):
+        self.dist.scatter(self.recv, scatter_list=list(self.send.unbind(0)) if self.rank == self.src else None,
+                          src=self.src, group=self.group)
+
+    def _command(self, cmd: float, arg: float = 0.0):
+        """sampler rank: a header-only block for every rank (shutdown / grow)"""
+        self.stage[:, 0] = cmd
+        self.stage[:, 1] = arg
+        if self.send is not self.stage:
+            self.send[:, :HDR].copy_(self.stage[:, :HDR], non_blocking=True)
+        self._scatter()
+
+    def _local(self, n: int, lo: int):
+        """evaluate rows [lo, lo + n) of the batch, which sit in self.recv, and deliver them"""
+        torch = self.torch
+        rows = self.recv[HDR:HDR + n * self.ndim].view(n, self.ndim)
+        if self.peer is not None:
+            if n > 0:
+                self.local_eval_device(rows, self.out_view[lo:lo + n])
+            if self.rank != self.src:
+                self.peer.signal(self.rank, self.seq, torch.cuda.current_stream(self.device).cuda_stream)
+            return
+        if n > 0:
+            if self.local_eval_device is not None:
+                self.local_eval_device(rows, self.ret[:n])
+            else:
+                out = np.asarray(self.local_eval(rows.cpu().numpy()), dtype=np.float64)
+                self.ret[:n] = torch.as_tensor(out).to(self.device)
+        self.dist.gather(self.ret, gather_list=self.ret_all, dst=self.src, group=self.group)
+
+    def evaluate(self, X: np.ndarray) -> np.ndarray:
+        torch = self.torch
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if self.world == 1:
+            return np.asarray(self.local_eval(X))
+        assert self.rank == self.src, "evaluate() is the sampler rank's call; the other ranks run serve()"
+        W = len(X)
+        if W > self.capacity:
+            new_cap = max(W, 2 * self.capacity)
+            self._command(CMD_GROW, float(new_cap))
+            self._setup(new_cap)
+        self.seq += 1
+        lo, hi = shard_bounds(W, self.world)
+        st = self.stage.numpy()
+        for r in range(self.world):
+            n = hi[r] - lo[r]
+            st[r, 0], st[r, 1], st[r, 2] = n, lo[r], self.seq
+            st[r, HDR:HDR + n * self.ndim] = X[lo[r]:hi[r]].reshape(-1)
+        if self.send is not self.stage:
+            used = HDR + max(h - l for l, h in zip(lo, hi)) * self.ndim
+            if used * 4 >= self.slot * 3:
+                self.send.copy_(self.stage, non_blocking=True)                    # one H2D copy
+            else:
+                self.send[:, :used].copy_(self.stage[:, :used], non_blocking=True)
+        self._scatter()
+        self._local(hi[self.src] - lo[self.src], lo[self.src])
+        if self.peer is not None:
+            stream = torch.cuda.current_stream(self.device)
+            others = [r for r in range(self.world) if r != self.src]
+            # flags are indexed by rank; the sampler's own slot is never awaited
+            first, last = min(others), max(others)
+            if self.src > first and self.src < last:
+                self.peer.wait(first, self.src - first, self.seq, stream=stream.cuda_stream)
+                self.peer.wait(self.src + 1, last - self.src, self.seq, stream=stream.cuda_stream)
+            else:
+                self.peer.wait(first, last - first + 1, self.seq, stream=stream.cuda_stream)
+            self.host_out[:2 + W].copy_(self.out_all[:2 + W], non_blocking=True)
+            stream.synchronize()
+            if int(self.host_out[:1].view(torch.int64)[0]) != 0:
+                raise RuntimeError("a rank did not deliver its slice of the batch in time (peer-memory result path)")
+            return self.host_out[2:2 + W].numpy().copy()
+        out = np.empty(W)
+        for r in range(self.world):
+            out[lo[r]:hi[r]] = self.ret_all[r][:hi[r] - lo[r]].cpu().numpy()
+        return out
 
     def serve(self):
-        """Worker loop of the non-sampler ranks (the role of MPIPool.wait, bajes/pipe/utils/mpi.py:91-117):
-        take part in every evaluate() of the sampler rank until it calls shutdown()."""
+        """Worker loop of the other ranks: take part in every evaluate() of the sampler rank until its shutdown()."""
         assert self.rank != self.src
         n_calls = 0
-        while self.evaluate(None) is not None:
+        while True:
+            self._scatter()
+            hdr = self.recv[:HDR].cpu().numpy()
+            if hdr[0] == CMD_SHUTDOWN:
+                return n_calls
+            if hdr[0] == CMD_GROW:
+                self._setup(int(hdr[1]))
+                continue
+            self.seq = int(hdr[2])
+            self._local(int(hdr[0]), int(hdr[1]))
             n_calls += 1
-        return n_calls
 
     def shutdown(self):
         """Sampler rank: release the workers."""
         if self.world > 1 and self.rank == self.src:
-            self.evaluate(None)
+            self._command(CMD_SHUTDOWN)
+        if self.peer is not None:
+            self.torch.cuda.synchronize(self.device)
 
 
 class FrequencySplitEvaluator:

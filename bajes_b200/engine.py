@@ -125,6 +125,11 @@ EXPORTS = {
                                    C.POINTER(bj_param_map), _DP, _DP]),
     "bj_roq_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(bj_config), C.POINTER(bj_roq_tables)]),
     "bj_relbin_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(bj_config), C.c_int64, _DP, _DPP, _DP]),
+    "bj_peer_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "bj_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "bj_peer_close": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
+    "bj_peer_signal": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "bj_peer_wait": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_void_p]),
     "bj_measure_peak": (C.c_int, [C.c_int, C.c_int, _DP]),
     "bj_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bj_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
@@ -184,6 +189,53 @@ def measure_peak(which: str, device: int = 0) -> float:
     out = C.c_double()
     _check(lib, lib.bj_measure_peak(device, {"dfma": 0, "mufu": 1}[which], C.byref(out)), "bj_measure_peak")
     return out.value
+
+
+PEER_FLAGS = 64
+PEER_HEADER_BYTES = (PEER_FLAGS + 2) * 8
+
+
+class PeerBuffer:
+    """The sampler rank's result buffer, written by every rank's epilogue kernel over NVLink
+    (include/bajes_b200.h: bj_peer_*).  ``create`` on the owner, ``open`` with its 64-byte handle elsewhere."""
+
+    def __init__(self, device: int, base: int, opened: bool, capacity: int, handle: bytes = b""):
+        self.device, self.base, self.opened, self.capacity, self.handle = device, base, opened, capacity, handle
+
+    @classmethod
+    def create(cls, device: int, capacity: int) -> "PeerBuffer":
+        lib = load_library()
+        base = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _check(lib, lib.bj_peer_create(device, capacity, C.byref(base), handle), "bj_peer_create")
+        return cls(device, base.value, False, capacity, handle.raw)
+
+    @classmethod
+    def open(cls, device: int, handle: bytes, capacity: int) -> "PeerBuffer":
+        lib = load_library()
+        base = C.c_void_p()
+        _check(lib, lib.bj_peer_open(device, handle, C.byref(base)), "bj_peer_open")
+        return cls(device, base.value, True, capacity, handle)
+
+    @property
+    def data_ptr(self) -> int:
+        """device address of logL[0]"""
+        return self.base + PEER_HEADER_BYTES
+
+    def signal(self, slot: int, value: int, stream: int = 0) -> None:
+        lib = load_library()
+        _check(lib, lib.bj_peer_signal(self.device, C.c_void_p(self.base), slot, value, C.c_void_p(stream or None)),
+               "bj_peer_signal")
+
+    def wait(self, first: int, n: int, value: int, timeout_ms: float = 5000.0, stream: int = 0) -> None:
+        lib = load_library()
+        _check(lib, lib.bj_peer_wait(self.device, C.c_void_p(self.base), first, n, value, float(timeout_ms),
+                                     C.c_void_p(stream or None)), "bj_peer_wait")
+
+    def close(self) -> None:
+        if self.base:
+            load_library().bj_peer_close(self.device, C.c_void_p(self.base), 1 if self.opened else 0)
+            self.base = 0
 
 
 def _as_f64(a) -> np.ndarray:

@@ -21,9 +21,24 @@ def compute_linear_weights(tc, df, interpolant, data, psd, freqs):
     return 4.0 * df * (interpolant.T @ vec)
 
 
-def linear_weights_matrix(tcs, df, interpolant, data, psd, freqs, block=256):
-    """[N_L, N_tc] matrix of omega_j(tc) (roq.py:862-865), evaluated as blocked GEMMs."""
+def linear_weights_matrix(tcs, df, interpolant, data, psd, freqs, block=256, device=None):
+    """[N_L, N_tc] matrix of omega_j(tc) (roq.py:862-865), evaluated as blocked GEMMs.  With ``device`` (a CUDA
+    device) the phase matrix and the complex128 GEMMs run there (set-up only; the same sums in another order:
+    agreement with the host path ~1e-15 relative)."""
     base = np.conj(data) / psd
+    if device is not None:
+        import torch
+        dev = torch.device(device)
+        f_d = torch.as_tensor(np.asarray(freqs, dtype=np.float64), device=dev)
+        base_d = torch.as_tensor(base, device=dev)
+        bt_d = torch.as_tensor(np.ascontiguousarray(interpolant.T).astype(np.complex128), device=dev)
+        t_d = torch.as_tensor(np.asarray(tcs, dtype=np.float64), device=dev)
+        out_d = torch.empty((interpolant.shape[1], len(tcs)), dtype=torch.complex128, device=dev)
+        blk = 1024
+        for s in range(0, len(tcs), blk):
+            ang = -2.0 * np.pi * torch.outer(f_d, t_d[s:s + blk])
+            out_d[:, s:s + blk] = 4.0 * df * (bt_d @ (base_d[:, None] * torch.polar(torch.ones_like(ang), ang)))
+        return out_d.cpu().numpy()
     out = np.empty((interpolant.shape[1], len(tcs)), dtype=np.complex128)
     bt = np.ascontiguousarray(interpolant.T)
     for s in range(0, len(tcs), block):
@@ -48,7 +63,7 @@ def load_jenpyroq(path):
     return meta, lin_f, quad_f, lin_b, quad_b
 
 
-def initialise_roq_for_inference(path, approx, f_min, f_max, df, freqs_full, psd, data_f, tcs):
+def initialise_roq_for_inference(path, approx, f_min, f_max, df, freqs_full, psd, data_f, tcs, device=None):
     """roq.py:817-872: returns linear / quadratic node frequencies, the cubic interpolant of the linear
     weights over ``tcs`` and the quadratic weights."""
     from scipy.interpolate import interp1d
@@ -59,13 +74,13 @@ def initialise_roq_for_inference(path, approx, f_min, f_max, df, freqs_full, psd
             meta = None
     if meta is None:
         data_f, psd, freqs_full = data_f[:-1], psd[:-1], freqs_full[:-1]   # legacy PyROQ layout (roq.py:844-849)
-    matrix = linear_weights_matrix(tcs, df, lin_b, data_f, psd, freqs_full)
+    matrix = linear_weights_matrix(tcs, df, lin_b, data_f, psd, freqs_full, device=device)
     omega = interp1d(tcs, matrix, kind="cubic", bounds_error=False, fill_value=-np.inf)
     psi = 4.0 * df * quad_b.T @ (1.0 / psd)
     return lin_f, quad_f, omega, psi
 
 
-def initialize_roq(roq_path, time_points, freqs_full, data_f, psd, f_min, f_max, seglen, prior, approx):
+def initialize_roq(roq_path, time_points, freqs_full, data_f, psd, f_min, f_max, seglen, prior, approx, device=None):
     """bajes/pipe/__init__.py:661-716: tc grid from the time_shift prior (+-30 ms), weights, joined node
     axis and the index masks."""
     if "time_shift" not in prior.const:
@@ -75,16 +90,16 @@ def initialize_roq(roq_path, time_points, freqs_full, data_f, psd, f_min, f_max,
         t_low = t_high = prior.const["time_shift"]
     tcs = np.linspace(seglen / 2.0 + t_low - 0.030, seglen / 2.0 + t_high + 0.030, time_points)
     lin_f, quad_f, omega, psi = initialise_roq_for_inference(roq_path, approx, f_min, f_max, 1.0 / seglen,
-                                                             freqs_full, psd, data_f, tcs)
+                                                             freqs_full, psd, data_f, tcs, device=device)
     joined = np.sort(np.array(list(set(np.concatenate((quad_f, lin_f))))))
     mask_lin = [i for i in range(len(joined)) if joined[i] in lin_f]
     mask_qua = [i for i in range(len(joined)) if joined[i] in quad_f]
     return joined, mask_qua, mask_lin, psi, omega
 
 
-def build_roq_dict(roq_path, time_points, ifos, datas, noises, freqs, f_min, f_max, seglen, prior, approx):
+def build_roq_dict(roq_path, time_points, ifos, datas, noises, freqs, f_min, f_max, seglen, prior, approx, device=None):
     """The ``roq`` argument of GWLikelihood as assembled in bajes/pipe/__init__.py:753-783
-    (PSD WITHOUT the window factor, :763)."""
+    (PSD WITHOUT the window factor, :763).  ``device``: evaluate the weight matrices on that CUDA device."""
     roq = {ifo: {} for ifo in ifos}
     joined = m_psi = m_om = None
     for ifo in ifos:
@@ -93,7 +108,7 @@ def build_roq_dict(roq_path, time_points, ifos, datas, noises, freqs, f_min, f_m
         d = datas[ifo].freq_series[mask]
         psd = noises[ifo].interp_psd_pad(f_full)
         joined, m_psi, m_om, psi, omega = initialize_roq(roq_path, time_points, f_full, d, psd, f_min, f_max,
-                                                         seglen, prior, approx)
+                                                         seglen, prior, approx, device=device)
         roq[ifo]["omega_weights_interp"] = omega
         roq[ifo]["psi_weights"] = psi
     roq["freqs_join"] = joined

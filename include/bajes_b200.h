@@ -229,6 +229,25 @@ int bj_relbin_create(bj_ctx** out, const bj_config* cfg, int64_t n_edges, const 
                      const double* const* h0_ri, const double* sdat_ri);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU result path over peer memory (one process per GPU; replaces the gather of the per-point results to the
+ * sampler rank, the "results in requested order" step of MPIPool.map, pipe/utils/mpi.py:120-159).
+ * The sampler rank owns ONE device buffer [flags: 64 x int64][status: int64][pad][logL: capacity doubles]; the other
+ * ranks map it with a CUDA IPC handle and pass `peer_base + offset` as out_logl_dev of bj_loglike_device: the
+ * epilogue kernel then stores every logL straight into the sampler rank's HBM over NVLink.  bj_peer_signal (stream-
+ * ordered, after the epilogue) publishes `value` in flags[slot] with a system-scope release; bj_peer_wait on the
+ * sampler rank's stream spins (bounded by timeout_ms; status word = 1 on time-out) until flags[first..first+n) have
+ * all reached `value`.  No collective and no host synchronisation on the return path.
+ * ------------------------------------------------------------------------------------------ */
+#define BJ_PEER_FLAGS 64
+#define BJ_PEER_HEADER_BYTES ((BJ_PEER_FLAGS + 2) * 8)
+int bj_peer_create(int device, int64_t capacity_doubles, void** base_dev, unsigned char* handle64);
+int bj_peer_open(int device, const unsigned char* handle64, void** base_dev);
+int bj_peer_close(int device, void* base_dev, int opened_from_handle);
+int bj_peer_signal(int device, void* base_dev, int32_t slot, int64_t value, void* stream);
+int bj_peer_wait(int device, void* base_dev, int32_t first_slot, int32_t n_slots, int64_t value, double timeout_ms,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): issue-rate micro-benchmarks used as roofline denominators.
  * which: 0 = FP64 FMA (instr/s), 1 = MUFU sin+cos (instr/s).  Result in *out (thread-instr/s).
  * ------------------------------------------------------------------------------------------ */

@@ -242,8 +242,55 @@ def gen_rwalk():
     np.savez_compressed(os.path.join(GOLDEN, "rwalk.npz"), **out)
 
 
+RELBIN_CFG = dict(ifos=["H1", "L1", "V1"], seglen=8.0, srate=4096.0, f_min=20.0, f_max=2048.0,
+                  approx="TaylorF2_3.5PN", source="bns", n_walkers=64, seed=4204)
+
+
+def gen_relbin():
+    """Relative-binning SET-UP pinned to reference code.  ``bajes/pipe/utils/binning.py`` cannot be imported as shipped
+    (it imports ``bajes.pipe.likelihood`` and ``bajes.utils``, which do not exist: SURVEY.md F5); with two empty stub
+    parent modules registered its two pure set-up functions ``setup_bins`` (:22-49) and ``compute_sdat`` (:52-101) run
+    UNMODIFIED.  Inputs: the seeded synthetic network built with the reference classes, the fiducial waveform from the
+    reference's own Waveform + Detector.project_fdwave on the masked band (the documented repair: h0 lives on the same
+    axis as the detector data).  The per-point ``log_like`` of that module stays unrunnable, so logL parity for this
+    likelihood remains unpinned; bins and summary data are not."""
+    import types
+    shims.import_reference()
+    for name, attrs in (("bajes.pipe.likelihood", {"Likelihood": type("Likelihood", (), {})}),
+                        ("bajes.utils", {"erase_init_wrapper": lambda f: f, "list_2_dict": lambda *a, **k: {}})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    import importlib
+    binning = importlib.import_module("bajes.pipe.utils.binning")
+    cfg = RELBIN_CFG
+    cl = harness.reference_classes()
+    ifos, datas, dets, noises, f = syn.build_network(cfg, cl)
+    fid = syn.injection_params(cfg)
+    mask = datas[ifos[0]].mask
+    fband = np.asarray(f)[mask]
+    wave = cl.Waveform(fband, cfg["srate"], cfg["seglen"], cfg["approx"])
+    hphc = wave.compute_hphc(dict(fid))
+    psds, sfts, h0s = [], [], []
+    for ifo in ifos:
+        dets[ifo].store_measurement(datas[ifo], noises[ifo])
+        psds.append(np.asarray(dets[ifo].psd))
+        sfts.append(np.asarray(dets[ifo].data))
+        h0s.append(np.asarray(dets[ifo].project_fdwave(hphc, dict(fid), "freq")))
+    out = {}
+    for tag, chi, eps in (("default", 1.0, 0.5), ("fine", 1.0, 0.1)):
+        nbin, fbin, fbin_ind = binning.setup_bins(fband, cfg["f_min"], cfg["f_max"], chi=chi, eps=eps)
+        sdat = binning.compute_sdat(fband, fbin, fbin_ind, len(ifos), psds, sfts, h0s)
+        out.update({"nbin_" + tag: nbin, "fbin_" + tag: fbin, "fbin_ind_" + tag: fbin_ind, "sdat_" + tag: sdat,
+                    "chi_eps_" + tag: np.array([chi, eps])})
+        print("  relbin %-8s chi=%g eps=%g  Nbin=%d  |A0| max %.3g" % (tag, chi, eps, nbin, np.abs(sdat[0]).max()))
+    np.savez_compressed(os.path.join(GOLDEN, "relbin_setup.npz"), h0=np.array(h0s), **out, **_det_constants(dets, ifos))
+
+
 def main(argv):
-    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq", "extras", "tmarg", "rwalk"}
+    what = set(argv) or {"asd", "c1", "c2_small", "c2", "roq", "extras", "tmarg", "rwalk", "relbin"}
     os.makedirs(GOLDEN, exist_ok=True)
     if "asd" in what:
         write_design_asd()
@@ -264,6 +311,8 @@ def main(argv):
         gen_tmarg()
     if "rwalk" in what:
         gen_rwalk()
+    if "relbin" in what:
+        gen_relbin()
 
 
 if __name__ == "__main__":

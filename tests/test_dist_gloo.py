@@ -1,6 +1,6 @@
 """
-world_size-2 gloo test (CPU) of the multi-GPU host logic: broadcast of the parameter block, contiguous
-walker shards, all-gather of logL in input order; N-rank result == 1-rank result bit for bit.
+world_size-2 gloo test (CPU) of the multi-GPU host logic: one scatter of the parameter block (header + rows per rank),
+contiguous walker shards, results back in input order; N-rank result == 1-rank result bit for bit.
 """
 import os
 import socket
@@ -23,28 +23,38 @@ def _fake_logl(X):
     return np.sin(X).sum(axis=1) + 1e-3 * X[:, 0] * X[:, -1]
 
 
-def _worker(rank, world, port, n, q):
+def _worker(rank, world, port, n, q, capacity, device_fn):
     sys.path.insert(0, ROOT)
+    import torch
     import torch.distributed as dist
     from bajes_b200.dist import ShardedEvaluator
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
-        ev = ShardedEvaluator(_fake_logl, ndim=5)
-        rng = np.random.default_rng(0)
-        X = rng.normal(size=(n, 5))
-        out = ev.evaluate(X if rank == 0 else None)      # only the sampler rank holds the points
-        q.put((rank, out))
+        def eval_dev(x, out):          # the device-pointer worker signature, on CPU tensors
+            out.copy_(torch.as_tensor(_fake_logl(x.numpy())))
+
+        ev = ShardedEvaluator(_fake_logl, ndim=5, capacity=capacity, local_eval_device=eval_dev if device_fn else None)
+        if rank == 0:                  # only the sampler rank holds the points
+            rng = np.random.default_rng(0)
+            X = rng.normal(size=(n, 5))
+            out = ev.evaluate(X)
+            ev.shutdown()
+            q.put((rank, out))
+        else:
+            q.put((rank, ev.serve()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [1, 7, 64, 1001])
-def test_sharded_evaluator_world2(n):
+@pytest.mark.parametrize("n,capacity,device_fn", [(1, 4096, False), (7, 4096, True), (64, 64, False), (1001, 8, False),
+                                                  (1001, 2048, True)])
+def test_sharded_evaluator_world2(n, capacity, device_fn):
+    """one scatter out (header + rows per rank), one gather back; capacity grows collectively when a batch exceeds it"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q, capacity, device_fn)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=120) for _ in range(2))
@@ -53,7 +63,7 @@ def test_sharded_evaluator_world2(n):
         assert p.exitcode == 0
     X = np.random.default_rng(0).normal(size=(n, 5))
     ref = _fake_logl(X)
-    assert np.array_equal(res[0], ref) and np.array_equal(res[1], ref)
+    assert np.array_equal(res[0], ref) and res[1] == 1
 
 
 def test_shard_bounds_cover_and_balance():

@@ -11,7 +11,7 @@ import pytest
 from bajes_b200 import GWLikelihood, Waveform, synthetic as syn
 from oracle import harness
 
-from conftest import load_golden, port_network, product_network_from_port
+from conftest import load_golden, port_network, product_network_from_port, roq_product
 
 pytestmark = pytest.mark.gpu
 
@@ -241,10 +241,9 @@ def test_zero_noise_injection_peak():
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("marg", [False, True])
 def test_roq_vs_reference_golden(marg):
-    from test_oracle_golden import _roq_port
+    # the roq dict comes from the PRODUCT set-up (bajes_b200.roq.build_roq_dict), not from the oracle's
     gold = load_golden("roq_small.npz")
-    cfg, net, roq = _roq_port(gold)
-    ifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    cfg, net, (ifos, datas, dets, noises, f), roq = roq_product(gold)
     like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"],
                         marg_phi_ref=marg, roq=roq)
     got = like.log_like_batch(gold["X"], _names(gold), syn.constants(cfg))
@@ -435,9 +434,10 @@ def test_roq_many_points_vs_port(marg):
     gold = load_golden("roq_small.npz")
     cfg, net, roq = _roq_port(gold)
     port_like = harness.port_likelihood(cfg, marg_phi_ref=marg, roq=roq, net=net)
-    ifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    # product side: its own set-up, with the weight matrices evaluated on the GPU
+    _, _, (ifos, datas, dets, noises, f), roq_p = roq_product(gold, device="cuda:0")
     like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"],
-                        marg_phi_ref=marg, roq=roq)
+                        marg_phi_ref=marg, roq=roq_p)
     Xa, names = syn.draw_walkers(cfg, 1500, 31, "narrow")
     Xb, _ = syn.draw_walkers(cfg, 1500, 32, "wide")
     X = np.concatenate([Xa, Xb])

@@ -261,3 +261,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
+
+
+# ------------------------------------------------------------------------------------------------------
+# product ROQ set-up (bajes_b200/roq.py) pinned to the reference golden vectors
+# ------------------------------------------------------------------------------------------------------
+def test_product_roq_setup_matches_reference_golden():
+    """bajes_b200.roq.build_roq_dict (mirror of pipe/utils/roq.py:808-872 and pipe/__init__.py:661-716) against the
+    psi weights, the omega weights at mid-grid and the logL golden vectors the UNMODIFIED reference produced
+    (oracle/make_golden.py roq): same JenpyROQ files on disk, same data, same tc grid."""
+    from conftest import load_golden, roq_product
+    from test_oracle_golden import _roq_port
+    from bajes_b200.roq import spline_tables
+    gold = load_golden("roq_small.npz")
+    cfg, net, pnet, roq = roq_product(gold)
+    _, _, roq_port = _roq_port(gold)
+    assert list(roq["mask_psi"]) == list(roq_port["mask_psi"]) and list(roq["mask_omega"]) == list(roq_port["mask_omega"])
+    np.testing.assert_array_equal(roq["freqs_join"], roq_port["freqs_join"])
+    for i, ifo in enumerate(cfg["ifos"]):
+        np.testing.assert_allclose(roq[ifo]["psi_weights"], gold["psi"][i], rtol=1e-12)
+        mid = roq[ifo]["omega_weights_interp"](cfg["seglen"] / 2 + 1e-3)
+        np.testing.assert_allclose(mid, gold["omega_mid"][i], rtol=1e-9, atol=1e-11 * np.max(np.abs(gold["omega_mid"][i])))
+        t, c, lo, hi = spline_tables(roq[ifo]["omega_weights_interp"])
+        assert len(t) == c.shape[0] + 4 and c.shape[1] == len(roq["mask_omega"])
+        assert lo == pytest.approx(cfg["seglen"] / 2 + gold["t_bounds"][0] - 0.030)
+        assert hi == pytest.approx(cfg["seglen"] / 2 + gold["t_bounds"][1] + 0.030)
+    # out of the tabulated range the reference's interpolant returns -inf (roq.py:866)
+    assert np.all(np.isneginf(np.real(roq[cfg["ifos"][0]]["omega_weights_interp"](hi + 1.0))))

@@ -164,3 +164,43 @@ def test_time_marginalised_likelihood(name, mphi):
     with np.errstate(all="ignore"):
         got = harness.eval_batch(like, gold["X_" + name], names, syn.constants(cfg))
     _assert_close(got, gold["logl_%s_mphi%d" % (name, int(mphi))], "tmarg %s mphi=%s" % (name, mphi))
+
+
+# ------------------------------------------------------------------------------------------------------
+# relative-binning SET-UP: bins and summary data from the unmodified reference functions
+# (binning.py:22-101 under two stub parent modules, oracle/make_golden.py relbin)
+# ------------------------------------------------------------------------------------------------------
+def _relbin_inputs(gold):
+    from oracle.make_golden import RELBIN_CFG as cfg
+    net = port_network(cfg, gold)
+    ifos, datas, dets, noises, f = net
+    mask = datas[ifos[0]].mask
+    fband = np.asarray(f)[mask]
+    psds, sfts = [], []
+    for ifo in ifos:
+        dets[ifo].store_measurement(datas[ifo], noises[ifo])
+        psds.append(np.asarray(dets[ifo].psd))
+        sfts.append(np.asarray(dets[ifo].data))
+    return cfg, fband, psds, sfts, [h for h in gold["h0"]]
+
+
+@pytest.mark.parametrize("tag", ["default", "fine"])
+@pytest.mark.parametrize("side", ["port", "product"])
+def test_relbin_setup_vs_reference_golden(tag, side):
+    """Bin edges bit for bit, summary data A0/A1/B0/B1 to 1e-8, for the oracle restatement AND for the product's
+    host set-up (bajes_b200/binning.py), against what the reference's own setup_bins / compute_sdat returned."""
+    gold = load_golden("relbin_setup.npz")
+    cfg, fband, psds, sfts, h0s = _relbin_inputs(gold)
+    chi, eps = gold["chi_eps_" + tag]
+    if side == "port":
+        nbin, fbin, ind = port.relbin_setup_bins(fband, cfg["f_min"], cfg["f_max"], chi=chi, eps=eps)
+        sdat = port.relbin_summary_data(fband, fbin, ind, psds, sfts, h0s)
+    else:
+        from bajes_b200 import binning
+        nbin, fbin, ind = binning.setup_bins(fband, cfg["f_min"], cfg["f_max"], chi=chi, eps=eps)
+        sdat = binning.compute_sdat(fband, fbin, ind, psds, sfts, h0s)
+    assert nbin == int(gold["nbin_" + tag])
+    np.testing.assert_array_equal(ind, gold["fbin_ind_" + tag])
+    np.testing.assert_array_equal(fbin, gold["fbin_" + tag])
+    ref = gold["sdat_" + tag]
+    np.testing.assert_allclose(sdat, ref, rtol=1e-8, atol=1e-10 * np.max(np.abs(ref)))
