@@ -108,8 +108,10 @@ struct bj_ctx {
     double2* d_tm = nullptr;
     double* d_tm_R = nullptr;
     long cap_tm_R = 0;
-    int tm_plan = 0;
+    int tm_plan = 0;              // plan of tm_batch rows
     bool tm_plan_ok = false;
+    int tm_plan_small = 0;        // plan of tm_small rows (calls with few walkers: a sampler's single points)
+    long tm_small = 0;
     // ROQ / relbin static tables
     RoqDevice roq;
     RelbinDevice relbin;
@@ -758,6 +760,7 @@ extern "C" int bj_destroy(bj_ctx* c) {
     cudaFree(c->d_tm);
     cudaFree(c->d_tm_R);
     if (c->tm_plan_ok) g_cufft.Destroy(c->tm_plan);
+    if (c->tm_small > 0) g_cufft.Destroy(c->tm_plan_small);
     cudaFree(c->d_coef);
     cudaFree(c->d_partial);
     cudaFree(c->d_x);
@@ -990,18 +993,36 @@ static int run_timemarg(bj_ctx* c, long n_walkers, cudaStream_t st, double* out_
         CUDA_TRY(cudaMalloc(&c->d_tm_R, (size_t)n_walkers * sizeof(double)));
         c->cap_tm_R = n_walkers;
     }
-    if (g_cufft.SetStream(c->tm_plan, st) != 0) return fail(BJ_ERR_CUDA, "cufftSetStream failed");
     for (long w0 = 0; w0 < n_walkers; w0 += c->tm_batch) {
         const long n_sub = std::min(c->tm_batch, n_walkers - w0);
-        // the plan always transforms tm_batch rows; rows beyond n_sub are zero and ignored
-        CUDA_TRY(cudaMemsetAsync(c->d_tm, 0, (size_t)c->tm_batch * c->tm_n_full * sizeof(double2), st));
+        // a batched plan transforms a fixed number of rows: the full sub-batch, or -- for calls with few walkers -- a
+        // second, small plan (next power of two; rebuilt when it does not fit), so that one point does not pay for 1024
+        int plan = c->tm_plan;
+        long rows = c->tm_batch;
+        if (n_sub * 4 <= c->tm_batch) {
+            long want = 1;
+            while (want < n_sub) want *= 2;
+            if (c->tm_small != want) {
+                if (c->tm_small > 0) g_cufft.Destroy(c->tm_plan_small);
+                c->tm_small = 0;
+                int n = (int)c->tm_n_full;
+                if (g_cufft.PlanMany(&c->tm_plan_small, 1, &n, nullptr, 1, n, nullptr, 1, n, kCufftZ2Z, (int)want) != 0)
+                    return fail(BJ_ERR_CUDA, "cufftPlanMany(n=%d, batch=%ld) failed", n, want);
+                c->tm_small = want;
+            }
+            plan = c->tm_plan_small;
+            rows = want;
+        }
+        if (g_cufft.SetStream(plan, st) != 0) return fail(BJ_ERR_CUDA, "cufftSetStream failed");
+        // rows beyond n_sub are zero and ignored
+        CUDA_TRY(cudaMemsetAsync(c->d_tm, 0, (size_t)rows * c->tm_n_full * sizeof(double2), st));
         switch (c->cfg.n_ifo) {
             case 1: launch_tm_integrand_m<1>(c, w0, n_sub, st); break;
             case 2: launch_tm_integrand_m<2>(c, w0, n_sub, st); break;
             default: launch_tm_integrand_m<3>(c, w0, n_sub, st); break;
         }
         CUDA_TRY(cudaGetLastError());
-        if (g_cufft.ExecZ2Z(c->tm_plan, c->d_tm, c->d_tm, kCufftForward) != 0) return fail(BJ_ERR_CUDA, "cufftExecZ2Z failed");
+        if (g_cufft.ExecZ2Z(plan, c->d_tm, c->d_tm, kCufftForward) != 0) return fail(BJ_ERR_CUDA, "cufftExecZ2Z failed");
         timemarg_reduce_kernel<<<(unsigned)n_sub, 256, 0, st>>>(c->d_tm, c->tm_n_full, c->cfg.marg_phi_ref, w0, c->d_tm_R);
         CUDA_TRY(cudaGetLastError());
     }
@@ -1052,6 +1073,14 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev[1], st));
     if (c->kind == KIND_FULLGRID && c->tm) {
+        if (out_parts_dev) {
+            // per-detector <d|h>, <h|h> (Detector.compute_inner_products) do not depend on the marginalisation: one pass
+            // of the fused kernels fills them (its logL is overwritten by the marginalised one below)
+            rc = launch_fullgrid(c, n_walkers, st, 0, c->n_chunks);
+            if (rc) return rc;
+            rc = launch_epilogue(c, n_walkers, st, out_logl_dev, out_parts_dev, 0, 0, c->n_chunks, nullptr);
+            if (rc) return rc;
+        }
         rc = run_timemarg(c, n_walkers, st, out_logl_dev);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[2], st));
@@ -1099,6 +1128,7 @@ extern "C" int bj_partial_device(bj_ctx* c, const double* x_dev, int64_t n_walke
                                  int32_t chunk_end, double* out_sums_dev, void* stream) {
     if (!c) return fail(BJ_ERR_INVALID, "null context");
     if (c->kind != KIND_FULLGRID) return fail(BJ_ERR_UNSUPPORTED, "only the full-grid likelihood can be split in frequency");
+    if (c->tm) return fail(BJ_ERR_UNSUPPORTED, "the time-marginalised likelihood needs the whole spectrum of a walker on one GPU: it cannot be split in frequency");
     if (n_walkers <= 0 || ndim <= 0 || !x_dev || !out_sums_dev) return fail(BJ_ERR_INVALID, "bad batch arguments");
     if (chunk_begin < 0 || chunk_end > c->n_chunks || chunk_begin > chunk_end)
         return fail(BJ_ERR_INVALID, "chunk range [%d, %d) outside [0, %d)", chunk_begin, chunk_end, c->n_chunks);
@@ -1129,6 +1159,7 @@ extern "C" int bj_finish_device(bj_ctx* c, const double* sums_dev, int64_t n_wal
                                 double* out_parts_dev, void* stream) {
     if (!c) return fail(BJ_ERR_INVALID, "null context");
     if (c->kind != KIND_FULLGRID) return fail(BJ_ERR_UNSUPPORTED, "only the full-grid likelihood can be split in frequency");
+    if (c->tm) return fail(BJ_ERR_UNSUPPORTED, "the time-marginalised likelihood cannot be split in frequency");
     if (n_walkers <= 0 || !sums_dev || !out_logl_dev) return fail(BJ_ERR_INVALID, "bad arguments");
     if (n_walkers > c->cap_walkers) return fail(BJ_ERR_INVALID, "bj_finish_device must follow bj_partial_device on the same batch");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1394,8 +1425,13 @@ extern "C" int bj_peer_wait(int device, void* base_dev, int32_t first_slot, int3
         return fail(BJ_ERR_INVALID, "bad arguments");
     if (n_slots == 0) return BJ_OK;
     CUDA_TRY(cudaSetDevice(device));
-    int khz = 0;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    // the clock-rate attribute is a slow driver query (~1 ms): once per device
+    static int khz_cache[64] = {0};
+    int khz = device < 64 ? khz_cache[device] : 0;
+    if (khz == 0) {
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        if (device < 64) khz_cache[device] = khz;
+    }
     const long long cycles = (long long)(timeout_ms * (double)(khz > 0 ? khz : 1000000));
     peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((long long*)base_dev, first_slot, n_slots, (long long)value, cycles);
     CUDA_TRY(cudaGetLastError());

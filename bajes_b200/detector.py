@@ -184,9 +184,18 @@ class Detector(object):
         return self._need_owner().project_fdwave(params)[self.ifo]
 
     def compute_inner_products(self, hphc, params, tag="freq", psd_weight_factor=False, roq=None):
-        """(dh, hh, dd[, psd_factor]) with ``dh`` the SUMMED <d|h> (detector.py:496-544; the per-bin integrand
-        array of the non-ROQ branch is only needed for time marginalisation, which is not fused)."""
+        """(dh, hh, dd[, psd_factor]) as detector.py:496-544, with ``dh`` the SUMMED <d|h> (the reference returns the
+        per-bin integrand in the non-ROQ branch because its caller sums it or Fourier-transforms it for the time
+        marginalisation; here both happen on the device).  With PSD weights ``dd`` is recomputed with ``psd * weights``
+        and ``psd_factor = sum(log(weights))`` (detector.py:524-531), consistent with the weighted dh / hh the engine
+        returns."""
         dh, hh = self._need_owner().inner_products(params)[self.ifo]
+        dd, w = self._dd, 0.0
+        if self.nweights:
+            weights = np.concatenate([np.full(int(n), float(params["weight{}_{}".format(b, self.ifo)]))
+                                      for b, n in enumerate(self.len_weights)])          # detector.py:22-23
+            w = float(np.log(weights).sum())
+            dd = (4.0 / self.seglen) * float(np.sum(np.abs(self.data) ** 2.0 / (self.psd * weights)))
         if psd_weight_factor:
-            return dh, hh, self._dd, 0.0
-        return dh, hh, self._dd
+            return dh, hh, dd, w
+        return dh, hh, dd

@@ -4,9 +4,9 @@ Multi-GPU evaluation: the walker batch is sharded across the ranks of a ``torch.
 (``Posterior.log_like`` is a pure function of one point; the reference farms points to workers the same
 way, bajes/pipe/utils/mpi.py:120-159), so the data path has NO collective: each walker's whole reduction
 happens on one GPU and results are bit-identical for any number of ranks.  The only communication is
-the plumbing around it -- one scatter of the [W, ndim] parameter block from the sampler rank, and the
-W log-likelihoods stored by every rank's epilogue kernel straight into the sampler rank's HBM over NVLink
-(peer memory; a gather on CPU).
+the plumbing around it -- and on CUDA that plumbing is peer memory: the parameter block is read by every rank's
+prologue kernel, and the W log-likelihoods are stored by every rank's epilogue kernel, straight out of / into the
+sampler rank's HBM over NVLink (one scatter + one gather on CPU or without peer access).
 """
 from __future__ import annotations
 
@@ -30,27 +30,51 @@ class _RawCuda:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
+class _PtrView:
+    """A float64 array at a raw device address with the two things a device worker needs from its arguments:
+    ``data_ptr()`` and ``shape``.  Used for the sampler rank's buffer as mapped into the OTHER ranks' address space
+    (torch would attribute that memory to the sampler rank's device)."""
+
+    def __init__(self, ptr: int, n: int, shape=None):
+        self.ptr, self.n = int(ptr), int(n)
+        self.shape = tuple(shape) if shape is not None else (self.n,)
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+    def __len__(self):
+        return self.shape[0]
+
+
 HDR = 3                     # per-rank header of the scattered block: rows of this rank, offset of its first row, sequence
-CMD_SHUTDOWN, CMD_GROW = -1.0, -2.0
+CMD_RUN, CMD_SHUTDOWN, CMD_GROW = 0.0, -1.0, -2.0
+X_FLAG0 = 32                # flag slots 32 + r: "rank r's rows of X are in the sampler rank's HBM" (slots r: "rank r is done")
 
 
 class ShardedEvaluator:
     """``evaluate(X)``: rank ``src`` (the sampler) supplies X [W, ndim] and gets logL [W] back; every rank evaluates a
-    contiguous slice.  Per call there is ONE collective and, on the sampler rank, ONE host synchronisation:
+    contiguous slice.  Two transports:
 
-      out    the sampler rank packs, per rank, [rows, first row, sequence | that rank's rows] into a fixed-capacity
-             block and ONE ``scatter`` (NCCL over NVLink) delivers it -- 1/N of the batch per link instead of a
-             broadcast of all of it, and no separate size message;
-      back   no collective at all on CUDA: the sampler rank owns the result vector, the other ranks map it through a
-             CUDA IPC handle, and their epilogue kernel stores every logL straight into the sampler rank's HBM over
-             NVLink (``engine.PeerBuffer``; a system-scope flag per rank, awaited by a one-block kernel on the sampler
-             rank's stream, orders the device-to-host copy behind the remote stores).  On CPU (gloo tests) or without
-             peer access the slices come back with one ``gather``.
+    **peer memory** (CUDA, the default when every GPU can map the sampler rank's memory): NO collective per call.
+    The sampler rank owns one device buffer [flags | logL | X]; the other ranks map it through a CUDA IPC handle.
+      out    the sampler rank writes the per-rank (rows, first row) table to a small host shared-memory block and
+             enqueues ONE host-to-device copy of X into its buffer followed by a flag store; the other ranks' host loops
+             see the new sequence number, enqueue a one-block kernel that waits for that flag (a remote read over
+             NVLink) and then their likelihood kernels, whose prologue reads its rows of X straight out of the sampler
+             rank's HBM;
+      back   every rank's epilogue kernel stores its logL straight into the sampler rank's HBM, then publishes a
+             system-scope flag; a one-block kernel on the sampler rank's stream waits for all flags, the device-to-
+             host copy follows in stream order.  One host synchronisation on the sampler rank, none elsewhere.
+    Walkers are independent, so this IS the whole exchange of the path: compute and "collective" are the same kernels.
+
+    **collective** (CPU / gloo tests, or GPUs without peer access): one ``scatter`` of fixed-capacity per-rank blocks
+    [rows, first row, sequence | rows of X] and one ``gather`` of the results.
 
     ``local_eval(X_slice) -> logL_slice`` is the per-rank host worker (CPU tests pass any pure function);
     ``local_eval_device(x_dev [w, ndim], out_dev [w])`` evaluates a device-resident slice in place on the current
-    stream -- ``out_dev`` may be a view of the sampler rank's memory.  The capacity grows on demand (collectively).
-    The other ranks sit in ``serve()`` (the role of MPIPool.wait, bajes/pipe/utils/mpi.py:91-117)."""
+    stream; both arguments only need ``data_ptr()`` and ``shape`` -- they may be views of the sampler rank's memory.
+    The capacity grows on demand (collectively).  The other ranks sit in ``serve()`` (the role of MPIPool.wait,
+    bajes/pipe/utils/mpi.py:91-117)."""
 
     def __init__(self, local_eval: Optional[Callable[[np.ndarray], np.ndarray]], ndim: int, group=None, device=None,
                  src=0, local_eval_device=None, capacity: int = 4096, peer: Optional[bool] = None):
@@ -68,83 +92,186 @@ class ShardedEvaluator:
         self.local_eval_device = local_eval_device
         self.seq = 0
         self.peer = None
+        self.shm = None
         self.want_peer = (self.device.type == "cuda" and local_eval_device is not None) if peer is None else bool(peer)
         self.capacity = 0
         if self.world > 1:
+            assert self.world <= X_FLAG0
             self._setup(int(capacity))
 
     # -- collective set-up (every rank, same capacity) ------------------------------------------------------------
+    def _release(self):
+        if self.peer is not None:
+            self.torch.cuda.synchronize(self.device)
+            # the importers unmap before the owner frees
+            if self.rank == self.src:
+                self.dist.barrier(group=self.group)
+            self.peer.close()
+            if self.rank != self.src:
+                self.dist.barrier(group=self.group)
+            self.peer = None
+        if self.shm is not None:
+            self.hdr = None
+            self.shm.close()
+            if self.rank == self.src:
+                self.shm.unlink()
+            self.shm = None
+
     def _setup(self, capacity: int):
         torch, dist = self.torch, self.dist
+        self._release()
         self.capacity = int(capacity)
+        cuda = self.device.type == "cuda"
+        if self.want_peer:
+            from multiprocessing import shared_memory
+            from . import engine
+            ok = torch.ones(1, dtype=torch.int32, device=self.device)
+            info = [None]
+            try:
+                if self.rank == self.src:
+                    self.peer = engine.PeerBuffer.create(self.device.index, self.capacity * (1 + self.ndim))
+                    self.shm = shared_memory.SharedMemory(create=True, size=8 * 4 * self.world)
+                    info[0] = (self.peer.handle, self.shm.name)
+            except Exception:
+                ok.zero_()
+            dist.broadcast_object_list(info, src=self.src, group=self.group)
+            if self.rank != self.src:
+                try:
+                    self.peer = engine.PeerBuffer.open(self.device.index, info[0][0], self.capacity * (1 + self.ndim))
+                    self.shm = shared_memory.SharedMemory(name=info[0][1])
+                    try:                                 # the owner unlinks it; keep this process's tracker out of it
+                        from multiprocessing import resource_tracker
+                        resource_tracker.unregister(self.shm._name, "shared_memory")
+                    except Exception:
+                        pass
+                except Exception:
+                    ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:                      # some pair of GPUs has no peer access: collectives instead
+                self._release()
+            else:
+                from .engine import PEER_FLAGS
+                # host header, one row per rank: sequence, rows, first row, command
+                self.hdr = np.ndarray((self.world, 4), dtype=np.float64, buffer=self.shm.buf)
+                if self.rank == self.src:
+                    self.hdr[:] = 0.0
+                    self.out_all = torch.as_tensor(_RawCuda(self.peer.base + PEER_FLAGS * 8, 2 + self.capacity),
+                                                   device=self.device)         # [status, pad, logL...]
+                    self.x_all = torch.as_tensor(_RawCuda(self.peer.data_ptr + 8 * self.capacity,
+                                                          self.capacity * self.ndim), device=self.device)
+                    self.x_pin = torch.empty(self.capacity * self.ndim, dtype=torch.float64, pin_memory=True)
+                    self.host_out = torch.empty(2 + self.capacity, dtype=torch.float64, pin_memory=True)
+                self.seq = 0
+                dist.barrier(group=self.group)           # the header is zeroed before anyone polls it
+                return
+        # collective transport
         self.cap_rank = -(-self.capacity // self.world)
         self.slot = HDR + self.cap_rank * self.ndim
         self.recv = torch.empty(self.slot, dtype=torch.float64, device=self.device)
-        cuda = self.device.type == "cuda"
         if self.rank == self.src:
             self.stage = torch.empty((self.world, self.slot), dtype=torch.float64, pin_memory=cuda)
             self.send = self.stage if not cuda else torch.empty((self.world, self.slot), dtype=torch.float64,
                                                                  device=self.device)
-            self.host_out = torch.empty(2 + self.capacity, dtype=torch.float64, pin_memory=cuda)
-        if self.peer is not None:
-            self.peer.close()
-            self.peer = None
-        self.out_view = None
-        if self.want_peer:
-            from . import engine
-            ok = torch.ones(1, dtype=torch.int32, device=self.device)
-            handle = [None]
-            try:
-                if self.rank == self.src:
-                    self.peer = engine.PeerBuffer.create(self.device.index, self.capacity)
-                    handle[0] = self.peer.handle
-            except Exception:
-                ok.zero_()
-            dist.broadcast_object_list(handle, src=self.src, group=self.group)
-            if self.rank != self.src:
-                try:
-                    self.peer = engine.PeerBuffer.open(self.device.index, handle[0], self.capacity)
-                except Exception:
-                    ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-            if int(ok.item()) == 0:                      # some pair of GPUs has no peer access: gather instead
-                if self.peer is not None:
-                    self.peer.close()
-                self.peer = None
-            else:
-                # [status, pad, logL...] as a tensor (the flags sit in front of it)
-                from .engine import PEER_FLAGS
-                self.out_all = torch.as_tensor(_RawCuda(self.peer.base + PEER_FLAGS * 8, 2 + self.capacity),
-                                               device=self.device)
-                self.out_view = self.out_all[2:]
-        if self.peer is None:
-            self.ret = torch.empty(self.cap_rank, dtype=torch.float64, device=self.device)
-            self.ret_all = ([torch.empty(self.cap_rank, dtype=torch.float64, device=self.device)
-                             for _ in range(self.world)] if self.rank == self.src else None)
+        self.ret = torch.empty(self.cap_rank, dtype=torch.float64, device=self.device)
+        self.ret_all = ([torch.empty(self.cap_rank, dtype=torch.float64, device=self.device)
+                         for _ in range(self.world)] if self.rank == self.src else None)
 
-    # -- one batch ----------------------------------------------------------------------------------------------------
+    # -- peer-memory transport ----------------------------------------------------------------------------------------
+    def _peer_local(self, n: int, lo: int):
+        """this rank's rows [lo, lo + n): X and logL both live in the sampler rank's buffer"""
+        if n > 0:
+            x = _PtrView(self.peer.data_ptr + 8 * (self.capacity + lo * self.ndim), n * self.ndim, (n, self.ndim))
+            self.local_eval_device(x, _PtrView(self.peer.data_ptr + 8 * lo, n, (n,)))
+
+    def _peer_evaluate(self, X) -> np.ndarray:
+        torch = self.torch
+        W = len(X)
+        self.seq += 1
+        lo, hi = shard_bounds(W, self.world)
+        stream = torch.cuda.current_stream(self.device)
+        # the header first: the other ranks enqueue their kernels behind a wait on THEIR slice's flag while it travels
+        for r in range(self.world):
+            self.hdr[r, 1], self.hdr[r, 2], self.hdr[r, 3] = hi[r] - lo[r], lo[r], CMD_RUN
+        self.hdr[:, 0] = self.seq                        # published last
+        # X into the sampler rank's HBM, slice by slice (the other ranks' first, each followed by its flag), staged through
+        # pinned memory in pieces so that the host copy of one piece overlaps the DMA of the previous one
+        pinned_src = X if (isinstance(X, torch.Tensor) and X.is_pinned()) else None
+        flat = None if pinned_src is not None else X.reshape(-1)
+        stage = self.x_pin.numpy()
+        piece = 1 << 18                                   # doubles per piece (2 MiB)
+        for r in [q for q in range(self.world) if q != self.src] + [self.src]:
+            a, b = lo[r] * self.ndim, hi[r] * self.ndim
+            if pinned_src is not None:
+                self.x_all[a:b].copy_(pinned_src.view(-1)[a:b], non_blocking=True)
+            else:
+                for p0 in range(a, b, piece):
+                    p1 = min(b, p0 + piece)
+                    stage[p0:p1] = flat[p0:p1]
+                    self.x_all[p0:p1].copy_(self.x_pin[p0:p1], non_blocking=True)
+            self.peer.signal(X_FLAG0 + r, self.seq, stream.cuda_stream)
+        self._peer_local(hi[self.src] - lo[self.src], lo[self.src])
+        others = [r for r in range(self.world) if r != self.src]
+        first, last = min(others), max(others)
+        if first < self.src < last:
+            self.peer.wait(first, self.src - first, self.seq, stream=stream.cuda_stream)
+            self.peer.wait(self.src + 1, last - self.src, self.seq, stream=stream.cuda_stream)
+        else:
+            self.peer.wait(first, last - first + 1, self.seq, stream=stream.cuda_stream)
+        self.host_out[:2 + W].copy_(self.out_all[:2 + W], non_blocking=True)
+        stream.synchronize()
+        if int(self.host_out[:1].view(torch.int64)[0]) != 0:
+            raise RuntimeError("a rank did not deliver its slice of the batch in time (peer-memory result path)")
+        return self.host_out[2:2 + W].numpy().copy()
+
+    def _peer_command(self, cmd: float, arg: float = 0.0):
+        self.seq += 1
+        self.hdr[:, 1], self.hdr[:, 2], self.hdr[:, 3] = arg, 0.0, cmd
+        self.hdr[:, 0] = self.seq
+
+    def _peer_serve(self):
+        import time
+        torch = self.torch
+        stream = torch.cuda.current_stream(self.device)
+        n_calls, idle = 0, 0
+        while True:
+            seq = self.hdr[self.rank, 0]
+            if seq == self.seq:
+                idle += 1
+                if idle > 20000:                         # a sampler thinking on the host: stop burning a core
+                    time.sleep(0.0002)
+                continue
+            idle = 0
+            self.seq = int(seq)
+            n, lo, cmd = int(self.hdr[self.rank, 1]), int(self.hdr[self.rank, 2]), self.hdr[self.rank, 3]
+            if cmd == CMD_SHUTDOWN:
+                return n_calls, None
+            if cmd == CMD_GROW:
+                return n_calls, n
+            # the parameter block is in the sampler rank's HBM once its flag carries this sequence number
+            self.peer.wait(X_FLAG0 + self.rank, 1, self.seq, stream=stream.cuda_stream)
+            self._peer_local(n, lo)
+            self.peer.signal(self.rank, self.seq, stream.cuda_stream)
+            n_calls += 1
+
+    # -- collective transport -----------------------------------------------------------------------------------------
     def _scatter(self):
         self.dist.scatter(self.recv, scatter_list=list(self.send.unbind(0)) if self.rank == self.src else None,
                           src=self.src, group=self.group)
 
     def _command(self, cmd: float, arg: float = 0.0):
         """sampler rank: a header-only block for every rank (shutdown / grow)"""
+        if self.peer is not None:
+            return self._peer_command(cmd, arg)
         self.stage[:, 0] = cmd
         self.stage[:, 1] = arg
         if self.send is not self.stage:
             self.send[:, :HDR].copy_(self.stage[:, :HDR], non_blocking=True)
         self._scatter()
 
-    def _local(self, n: int, lo: int):
-        """evaluate rows [lo, lo + n) of the batch, which sit in self.recv, and deliver them"""
+    def _local(self, n: int):
+        """evaluate the n rows that sit in self.recv and hand them to the gather"""
         torch = self.torch
         rows = self.recv[HDR:HDR + n * self.ndim].view(n, self.ndim)
-        if self.peer is not None:
-            if n > 0:
-                self.local_eval_device(rows, self.out_view[lo:lo + n])
-            if self.rank != self.src:
-                self.peer.signal(self.rank, self.seq, torch.cuda.current_stream(self.device).cuda_stream)
-            return
         if n > 0:
             if self.local_eval_device is not None:
                 self.local_eval_device(rows, self.ret[:n])
@@ -153,9 +280,11 @@ class ShardedEvaluator:
                 self.ret[:n] = torch.as_tensor(out).to(self.device)
         self.dist.gather(self.ret, gather_list=self.ret_all, dst=self.src, group=self.group)
 
-    def evaluate(self, X: np.ndarray) -> np.ndarray:
-        torch = self.torch
-        X = np.ascontiguousarray(X, dtype=np.float64)
+    def evaluate(self, X) -> np.ndarray:
+        """X: float64 [W, ndim], a NumPy array or (peer transport) a pinned torch tensor, which skips the staging copy"""
+        if not (self.peer is not None and isinstance(X, self.torch.Tensor) and X.is_pinned()
+                and X.dtype == self.torch.float64 and X.is_contiguous()):
+            X = np.ascontiguousarray(X.numpy() if isinstance(X, self.torch.Tensor) else X, dtype=np.float64)
         if self.world == 1:
             return np.asarray(self.local_eval(X))
         assert self.rank == self.src, "evaluate() is the sampler rank's call; the other ranks run serve()"
@@ -164,6 +293,8 @@ class ShardedEvaluator:
             new_cap = max(W, 2 * self.capacity)
             self._command(CMD_GROW, float(new_cap))
             self._setup(new_cap)
+        if self.peer is not None:
+            return self._peer_evaluate(X)
         self.seq += 1
         lo, hi = shard_bounds(W, self.world)
         st = self.stage.numpy()
@@ -178,22 +309,7 @@ class ShardedEvaluator:
             else:
                 self.send[:, :used].copy_(self.stage[:, :used], non_blocking=True)
         self._scatter()
-        self._local(hi[self.src] - lo[self.src], lo[self.src])
-        if self.peer is not None:
-            stream = torch.cuda.current_stream(self.device)
-            others = [r for r in range(self.world) if r != self.src]
-            # flags are indexed by rank; the sampler's own slot is never awaited
-            first, last = min(others), max(others)
-            if self.src > first and self.src < last:
-                self.peer.wait(first, self.src - first, self.seq, stream=stream.cuda_stream)
-                self.peer.wait(self.src + 1, last - self.src, self.seq, stream=stream.cuda_stream)
-            else:
-                self.peer.wait(first, last - first + 1, self.seq, stream=stream.cuda_stream)
-            self.host_out[:2 + W].copy_(self.out_all[:2 + W], non_blocking=True)
-            stream.synchronize()
-            if int(self.host_out[:1].view(torch.int64)[0]) != 0:
-                raise RuntimeError("a rank did not deliver its slice of the batch in time (peer-memory result path)")
-            return self.host_out[2:2 + W].numpy().copy()
+        self._local(hi[self.src] - lo[self.src])
         out = np.empty(W)
         for r in range(self.world):
             out[lo[r]:hi[r]] = self.ret_all[r][:hi[r] - lo[r]].cpu().numpy()
@@ -204,6 +320,14 @@ class ShardedEvaluator:
         assert self.rank != self.src
         n_calls = 0
         while True:
+            if self.peer is not None:
+                k, grow = self._peer_serve()
+                n_calls += k
+                if grow is None:
+                    self._release()
+                    return n_calls
+                self._setup(int(grow))
+                continue
             self._scatter()
             hdr = self.recv[:HDR].cpu().numpy()
             if hdr[0] == CMD_SHUTDOWN:
@@ -212,15 +336,25 @@ class ShardedEvaluator:
                 self._setup(int(hdr[1]))
                 continue
             self.seq = int(hdr[2])
-            self._local(int(hdr[0]), int(hdr[1]))
+            self._local(int(hdr[0]))
             n_calls += 1
 
     def shutdown(self):
         """Sampler rank: release the workers."""
         if self.world > 1 and self.rank == self.src:
             self._command(CMD_SHUTDOWN)
-        if self.peer is not None:
-            self.torch.cuda.synchronize(self.device)
+            self._release()
+
+    def __del__(self):
+        try:
+            if self.shm is not None:
+                self.hdr = None
+                self.shm.close()
+                if self.rank == self.src:
+                    self.shm.unlink()
+                self.shm = None
+        except Exception:
+            pass
 
 
 class FrequencySplitEvaluator:

@@ -25,7 +25,9 @@ class BoxPrior(object):
         self.periodics = list(periodic) if periodic is not None else [0] * len(self.names)
         self._lo = np.array([b[0] for b in self.bounds], dtype=float)
         self._hi = np.array([b[1] for b in self.bounds], dtype=float)
-        self._logp = -float(np.sum(np.log(self._hi - self._lo)))
+        width = self._hi - self._lo
+        # a zero-width bound pins the parameter: it carries no volume (and would make the log diverge)
+        self._logp = -float(np.sum(np.log(width[width > 0.0])))
         self.ndim = len(self.names)
 
     def in_bounds(self, x):

@@ -1,37 +1,45 @@
 #!/usr/bin/env python
 """
-bench.py -- headline benchmark of the batched GW likelihood (BASELINE.json metric).
+bench.py -- headline benchmark of the batched GW likelihood (BASELINE.json metric), all five BASELINE configs.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--secondary all|none|C1,C3,..]
 
-A "step" is ONE batched ``GWLikelihood.log_like`` over the configured walker batch (config C2: TaylorF2 3.5PN
-+ 6PN tides BNS, H1/L1/V1, 128 s, 20-4096 Hz = 521 729 bins, 4096 walkers per GPU) -- prologue, fused
-full-grid kernel, epilogue.
+HEADLINE (config C2: TaylorF2 3.5PN + 6PN tides BNS, H1/L1/V1, 128 s, 20-4096 Hz = 521 729 bins, 4096 walkers per GPU).
+A "step" is ONE batched ``GWLikelihood.log_like`` over the walker batch: prologue, FP64 window kernel (the heaviest
+1.6 % of the bins), fused tensor-core kernel (+ its early-exit fix-up launch), epilogue.
 
   value     walker*bins/s over all ranks, inputs resident in HBM, timed per step with CUDA events on the
             launching stream (L2 flushed between steps, outside the timed events), max over ranks
-  e2e       same metric through the host-pointer C-ABI entry (``bj_loglike``): pinned host X -> H2D -> kernels
-            -> D2H logL inside the timed region
-  roofline  the fused kernel against the slower of the FP64-issue and SFU-issue rooflines (the HBM figure is
-            listed too, it is far from binding): achieved = algorithmic instructions per walker*bin (DESIGN.md
-            section 4) x units / kernel time; peaks = DFMA and MUFU issue rates measured live on this GPU
-  cpu_baseline  the oracle port (NumPy restatement of the reference algorithm, oracle/bajes_port.py) on the
-            host cores, multiprocessing over all of them like bajes does, on a bounded sample of the SAME
-            walkers (the reference itself is Python and cannot travel to the GPU box)
+  e2e       N = 1: the host-pointer C-ABI entry ``bj_loglike`` (pinned host X -> H2D -> kernels -> D2H logL);
+            N > 1: ``ShardedEvaluator.evaluate`` on the sampler rank, no collective: host X -> ONE H2D copy into the sampler
+            rank's HBM -> every rank's prologue reads its rows and every rank's epilogue stores its logL there over NVLink
+            (peer memory, flag-ordered) -> D2H
+  strong    (N > 1) the same two numbers with the TOTAL batch fixed at 4096 walkers (a sampler's ensemble does not grow
+            with the GPU count)
+  roofline  the fused kernel against the slower of the FP64-issue and SFU-issue rooflines (HBM is listed too, it is far
+            from binding): achieved = algorithmic instructions per walker*bin x units / kernel
+            time; peaks = DFMA and MUFU issue rates measured live on this GPU
+  cpu_baseline  the oracle port (NumPy restatement of the reference algorithm, oracle/bajes_port.py) on the host cores,
+            multiprocessing over all of them like bajes does, on a bounded sample of the SAME walkers (the reference
+            itself is Python and cannot travel to the GPU box)
+  secondary the other BASELINE configs, each with value / e2e / roofline / parity against the oracle:
+            C1  TaylorF2 3.5PN BBH, H1+L1, 4 s, 64 walkers (launch-latency bound)
+            C3  ROQ, 65 536 points, N_L = 400 / N_Q = 200 JenpyROQ-format basis, 10^4 tc points (HBM bound)
+            C4  relative binning, 256 s, 2^20 points sharded over the N ranks
+            C5  stretch-move ensemble sampler on the C2 data, 4096 walkers in all, through BatchedPool ->
+                ShardedEvaluator (the unchanged-sampler contract: pool.map(posterior.log_post, points))
 
-``--impl reference`` times that CPU implementation alone and prints the same JSON line.
-With N > 1 (torchrun) the walker batch is sharded: every rank evaluates its own 4096 walkers (weak scaling, no
-data-path collective); the timed step is each rank's own work, max over ranks.  The NCCL all-gather of the per-walker
-logL to the sampler rank runs between the timed events and is part of ``e2e`` (ShardedEvaluator.evaluate: host X ->
-NCCL broadcast -> per-rank slices -> NCCL all-gather -> host).
+``--impl reference`` times the CPU implementation alone and prints the same JSON line.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -42,23 +50,24 @@ sys.path.insert(0, ROOT)
 
 METRIC = "likelihood evals/sec (walkers x freq bins / s)"
 UNIT = "walker*bins/s"
+DTYPE = ("f64 phase (DMMA) -> u32 binary angle -> f32 phasor (1 MUFU pair per bin, rotated to the other detectors) + f32 MAC "
+         "-> f64 accumulate every 8 bins; all-f64 in the heaviest 1.6% of the bins")
+LAUNCHES_PER_STEP = 5      # prologue, FP64 window, fused tile kernel, fix-up (early exit), epilogue
+
 
 # Algorithmic instruction counts per walker*bin of the fused kernel:
-#   FP64, Horner kernels : phase Horner (13 for 3.5PN + 6PN tides, 27 for the 5.5PN family) + one time-delay ramp FMA
-#         per detector (+ 2 FMAs per detector per 8 bins for the FP32 -> FP64 flush)
-#   FP64, tensor-core kernel : K = 12 / 28 FMAs of the phase GEMM (executed as DMMA.8x8x4) + per 8 bins and detector
-#         2 flush FMAs and 1 FP64 ramp anchor (uniform grids; else one ramp FMA per bin and detector)
-#   SFU : one MUFU.SIN + one MUFU.COS per detector ("mufu" mode; none in "poly32")
-def instr_per_unit(approx, n_ifo, sincos, tensor_core=False):
+#   FP64 : K = 12 / 28 FMAs of the phase GEMM (executed as DMMA.8x8x4) + per 8 bins: 2 flush FMAs for detector 0 and
+#          10 for every rotated detector (apply and advance its FP64 anchor) + 1 ramp anchor
+#   SFU  : ONE MUFU.SIN + MUFU.COS per bin with the rotation path (uniform grids), else one pair per detector
+def instr_per_unit(approx, n_ifo, sincos, tensor_core=True, rot=True):
     phase = 13 if approx == "TaylorF2_3.5PN" else 27
     if sincos == "fp64":
-        fp64 = phase + 7 + 5 * n_ifo
-        return fp64, 0
+        return phase + 7 + 5 * n_ifo, 0
     if tensor_core:
-        fp64 = (12 if approx == "TaylorF2_3.5PN" else 28) + 3.0 * n_ifo / 8.0
+        fp64 = (12 if approx == "TaylorF2_3.5PN" else 28) + ((3.0 + 10.0 * (n_ifo - 1)) / 8.0 if rot else 3.0 * n_ifo / 8.0)
     else:
         fp64 = phase + n_ifo + 2.0 * n_ifo / 8.0
-    sfu = 2 * n_ifo if sincos == "mufu" else 0
+    sfu = (2 if rot and n_ifo > 1 else 2 * n_ifo) if sincos == "mufu" else 0
     return fp64, sfu
 
 
@@ -73,6 +82,7 @@ def parse():
     ap.add_argument("--sincos", default=os.environ.get("BAJES_B200_SINCOS", "mufu"))
     ap.add_argument("--cpu-points", type=int, default=0, help="points of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--secondary", default="all", help="all | none | comma list of C1,C3,C4,C5")
     return ap.parse_args()
 
 
@@ -127,7 +137,7 @@ def cfg_bins(cfg):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# clocks sampler (nvidia-smi, 200 ms) -- runs during the timed region
+# clocks sampler (nvidia-smi, 50 ms) -- runs during the timed region
 # ---------------------------------------------------------------------------------------------------------
 class Clocks:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -231,27 +241,368 @@ def workload(cfg, args, walkers):
                         % (args.config, cfg["approx"], "/".join(cfg["ifos"]), cfg["seglen"], cfg["f_min"], cfg["f_max"],
                            cfg_bins(cfg), walkers),
             "approx": cfg["approx"], "ifos": cfg["ifos"], "n_bins": cfg_bins(cfg), "walkers_per_gpu": walkers,
-            "sharding": "walkers, dp%d, no data-path collective (logL all-gather untimed here, inside e2e)" % args.gpus if args.gpus > 1 else "walkers, dp1", "l2": "flushed between timed steps (256 MiB memset, untimed)"}
+            "sharding": ("walkers, dp%d, no collective: X read from / logL stored into the sampler rank's HBM by every rank's own "
+                         "kernels (peer memory) -- inside e2e" % args.gpus) if args.gpus > 1
+                        else "walkers, dp1",
+            "l2": "flushed between timed steps (256 MiB memset, untimed)"}
 
 
+def source_sha():
+    """hash of the kernel sources: profiles/traffic.json carries the hash it was measured at"""
+    h = hashlib.sha1()
+    for name in ("kernels.cuh", "walker.cuh", "roq_relbin.cuh", "capi.cu"):
+        with open(os.path.join(ROOT, "bajes_b200", "csrc", name), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture -- only if it was taken at these very
+    kernel sources (else null: a stale figure is worse than none)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "no profiles/traffic.json"
+    if t.get("source_sha") != source_sha():
+        return None, "profiles/traffic.json was captured at kernel sources %s, these are %s" % (t.get("source_sha"), source_sha())
+    return t.get(key), t.get("_note")
+
+
+# ---------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def timed(fn, dev, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    ms = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.median(ms)), float(np.min(ms))
+
+
+def wall(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        t.append(time.perf_counter() - t0)
+    return float(np.median(t)) * 1e3
+
+
+def max_over_ranks(c, v):
+    import torch
+    if c.world == 1:
+        return float(v)
+    t = torch.tensor([float(v)], dtype=torch.float64, device=c.dev)
+    c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def make_evaluator(c, like, names, const, capacity):
+    """ShardedEvaluator over this likelihood (collective constructor)."""
+    import torch
+    from bajes_b200.dist import ShardedEvaluator
+    pmap = like.param_map(names, const)
+
+    def eval_dev(xs, outs):
+        like.engine.loglike_device(xs.data_ptr(), xs.shape[0], len(names), pmap, outs.data_ptr(), 0,
+                                   torch.cuda.current_stream(c.dev).cuda_stream)
+
+    return ShardedEvaluator(lambda Xs: like.log_like_batch(Xs, names, const), ndim=len(names), device=c.dev,
+                            local_eval_device=eval_dev, capacity=capacity)
+
+
+def port_parity(port_like, got, X, names, const, n):
+    from oracle import harness
+    with np.errstate(all="ignore"):
+        ref = harness.eval_batch(port_like, X[:n], names, const)
+    ref = np.where(np.isfinite(ref), ref, -np.inf)
+    fin = np.isfinite(ref)
+    if not np.array_equal(np.isfinite(got[:n]), fin):
+        return float("inf")
+    tol = 1e-6 * np.abs(ref[fin]) + 1e-4
+    return float(np.max(np.abs(got[:n][fin] - ref[fin]) / tol)) if fin.any() else 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# secondary configs
+# ---------------------------------------------------------------------------------------------------------
+def secondary_c1(c, peaks):
+    """64 walkers x 4017 bins x 2 detectors on ONE GPU (rank 0): launch-latency bound."""
+    import ctypes as C
+    import torch
+    from bajes_b200 import GWLikelihood, engine, synthetic as syn
+    from oracle import harness
+    if c.rank != 0:
+        return None
+    cfg = syn.CONFIGS["C1"]
+    like = GWLikelihood(*syn.build_network(cfg, syn.product_classes()), cfg["srate"], cfg["seglen"], cfg["approx"],
+                        device=c.local, sincos=c.args.sincos)
+    names, const = syn.WALKER_NAMES, syn.constants(cfg)
+    W, nb = cfg["n_walkers"], like.engine.n_bins
+    X, _ = syn.draw_walkers(cfg, W, 5, "wide")
+    pm = like.param_map(names, const)
+    xd = torch.from_numpy(X).to(c.dev)
+    out = torch.empty(W, dtype=torch.float64, device=c.dev)
+    st = torch.cuda.current_stream(c.dev).cuda_stream
+    step_ms, _ = timed(lambda: like.engine.loglike_device(xd.data_ptr(), W, len(names), pm, out.data_ptr(), 0, st), c.dev, 50, 5)
+    kms = like.engine.last_kernel_ms()
+    xp, op = torch.from_numpy(X).pin_memory(), torch.empty(W, dtype=torch.float64).pin_memory()
+    lib = engine.load_library()
+    host_ms = wall(lambda: lib.bj_loglike(like.engine._h, C.cast(xp.data_ptr(), C.POINTER(C.c_double)), W, len(names),
+                                          C.byref(pm.c), C.cast(op.data_ptr(), C.POINTER(C.c_double))), 50, 5)
+    parity = port_parity(harness.port_likelihood(cfg), out.cpu().numpy(), X, names, const, W)
+    _, sfu = instr_per_unit(cfg["approx"], len(cfg["ifos"]), c.args.sincos)
+    k_s = kms[1] * 1e-3
+    like.engine.close()
+    return {"workload": "C1: %s, H1/L1, 4 s, 20-1024 Hz (%d bins), %d walkers, one GPU" % (cfg["approx"], nb, W),
+            "value": W * nb / (step_ms * 1e-3), "unit": UNIT, "evals_per_s": W / (step_ms * 1e-3), "ms_per_step": step_ms,
+            "kernel_ms": [round(float(x), 5) for x in kms],
+            "e2e": {"value": W * nb / (host_ms * 1e-3), "unit": UNIT, "ms_per_step": host_ms, "evals_per_s": W / (host_ms * 1e-3),
+                    "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": W * 8, "path": "bj_loglike (host pointers)"},
+            "roofline": {"bound": "launch latency (5 launches, 64 walkers fill 2 of 148 SMs per chunk row)",
+                         "sfu": {"achieved": W * nb * sfu / k_s / 1e9, "peak": peaks["mufu"] / 1e9, "unit": "GMUFU/s",
+                                 "frac": W * nb * sfu / k_s / peaks["mufu"]}},
+            "parity_max_err_over_tol": parity, "parity_points": W, "n_gpus": 1}
+
+
+def secondary_c3(c, peaks):
+    """ROQ, 65 536 points sharded over the ranks; HBM-bound spline gather."""
+    import torch
+    from bajes_b200 import GWLikelihood, roq as roqmod, synthetic as syn
+    from bajes_b200.ensemble import BoxPrior
+    from oracle import harness
+    points, n_lin, n_quad, tc_points = 65536, 400, 200, 10000
+    cfg = dict(syn.CONFIGS["C2_small"])
+    cfg.update(seglen=8.0, seed=3003)
+    ifos, datas, dets, noises, f = syn.build_network(cfg, syn.product_classes())
+    names, const = syn.WALKER_NAMES, syn.constants(cfg)
+    basis = syn.make_roq_basis(cfg, n_lin=n_lin, n_quad=n_quad, seed=7)
+    prior = BoxPrior(names, [[-1, 1]] * len(names), {})
+    prior.bounds[names.index("time_shift")] = [-0.05, 0.05]
+    t0 = time.perf_counter()
+    with tempfile.TemporaryDirectory() as tmp:
+        syn.write_jenpyroq(tmp, basis, cfg)
+        roq = roqmod.build_roq_dict(tmp, tc_points, ifos, datas, noises, f, cfg["f_min"], cfg["f_max"], cfg["seglen"],
+                                    prior, cfg["approx"], device=c.dev)
+    setup_s = time.perf_counter() - t0
+    like = GWLikelihood(ifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"], roq=roq, device=c.local)
+    nl, nq, nifo = len(roq["mask_omega"]), len(roq["mask_psi"]), len(ifos)
+    pm = like.param_map(names, const)
+    st = torch.cuda.current_stream(c.dev).cuda_stream
+    ev = make_evaluator(c, like, names, const, points) if c.world > 1 else None
+    from bajes_b200.dist import shard_bounds
+    lo, hi = shard_bounds(points, c.world)
+    n_loc = hi[c.rank] - lo[c.rank]
+    res, parity, boxes = {}, None, {}
+    # device-resident timings first (collective: max over ranks), then the end-to-end phase (sampler rank vs serve())
+    for box in ("narrow", "wide"):
+        X, _ = syn.draw_walkers(cfg, points, 9, box)
+        boxes[box] = X
+        xd = torch.from_numpy(np.ascontiguousarray(X[lo[c.rank]:hi[c.rank]])).to(c.dev)
+        out = torch.empty(n_loc, dtype=torch.float64, device=c.dev)
+        step_ms, _ = timed(lambda: like.engine.loglike_device(xd.data_ptr(), n_loc, len(names), pm, out.data_ptr(), 0, st),
+                           c.dev, 5, 2)
+        k_ms = like.engine.last_kernel_ms()[1]
+        step_ms, k_ms = max_over_ranks(c, step_ms), max_over_ranks(c, k_ms)
+        alg = n_loc * nifo * 4 * nl * 16
+        res[box] = {"value": points / (step_ms * 1e-3), "ms_per_step": step_ms, "kernel_ms": k_ms, "e2e": None,
+                    "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                 "frac": alg / (k_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                                 "algorithmic_bytes_per_point": nifo * 4 * nl * 16}}
+        if box == "narrow" and c.rank == 0:
+            port_like = harness.port_likelihood(cfg, roq=roq, net=syn.build_network(cfg, harness.port_classes()))
+            parity = port_parity(port_like, out.cpu().numpy(), X[lo[0]:hi[0]], names, const, 48)
+    if c.rank == 0:
+        for box, X in boxes.items():
+            host_ms = wall((lambda: like.log_like_batch(X, names, const)) if c.world == 1 else (lambda: ev.evaluate(X)), 3, 1)
+            res[box]["e2e"] = {"value": points / (host_ms * 1e-3), "unit": "points/s", "ms_per_step": host_ms,
+                               "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": points * 8}
+        if ev is not None:
+            ev.shutdown()
+    elif ev is not None:
+        ev.serve()
+    like.engine.close()
+    if c.rank != 0:
+        return None
+    return {"workload": "C3: ROQ %s, H1/L1/V1, 8 s, N_L = %d / N_Q = %d nodes, %d tc points (spline table %.0f MB), %d points "
+                        "sharded over %d GPU(s)" % (cfg["approx"], nl, nq, tc_points, tc_points * nl * 16 * nifo / 1e6, points, c.world),
+            "unit": "points/s", "setup_s": setup_s, "narrow_box": res["narrow"], "wide_box": res["wide"],
+            "value": res["wide"]["value"], "e2e": res["wide"]["e2e"], "roofline": res["wide"]["roofline"],
+            "parity_max_err_over_tol": parity, "parity_points": 48, "n_gpus": c.world,
+            "note": "headline numbers of this entry are the WIDE box (time shifts over the whole tc grid: every point gathers its "
+                    "own four spline rows from HBM); the narrow box keeps part of the table in L2"}
+
+
+def secondary_c4(c, peaks):
+    """Relative binning, 256 s, 2^20 points sharded over the ranks."""
+    import torch
+    from bajes_b200 import synthetic as syn
+    from bajes_b200.binning import GWBinningLikelihood
+    from bajes_b200.dist import shard_bounds
+    from oracle import bajes_port as port, harness
+    cfg = syn.CONFIGS["C4"]
+    points = 1 << 20
+    ifos, datas, dets, noises, f = syn.build_network(cfg, syn.product_classes())
+    fid = syn.injection_params(cfg)
+    t0 = time.perf_counter()
+    like = GWBinningLikelihood(ifos, datas, dets, noises, dict(fid), f, cfg["srate"], cfg["seglen"], cfg["approx"], device=c.local)
+    setup_s = time.perf_counter() - t0
+    names, const = syn.WALKER_NAMES, syn.constants(cfg)
+    X, _ = syn.draw_walkers(cfg, points, 11, "narrow")
+    lo, hi = shard_bounds(points, c.world)
+    n_loc = hi[c.rank] - lo[c.rank]
+    pm = like.param_map(names, const)
+    st = torch.cuda.current_stream(c.dev).cuda_stream
+    xd = torch.from_numpy(np.ascontiguousarray(X[lo[c.rank]:hi[c.rank]])).to(c.dev)
+    out = torch.empty(n_loc, dtype=torch.float64, device=c.dev)
+    step_ms, _ = timed(lambda: like.engine.loglike_device(xd.data_ptr(), n_loc, len(names), pm, out.data_ptr(), 0, st), c.dev, 5, 2)
+    kms = like.engine.last_kernel_ms()
+    step_ms, k_ms, p_ms = max_over_ranks(c, step_ms), max_over_ranks(c, kms[1]), max_over_ranks(c, kms[0])
+    host_ms = None
+    if c.world == 1:
+        import ctypes as C
+        from bajes_b200 import engine
+        lib = engine.load_library()
+        xp, op = torch.from_numpy(X).pin_memory(), torch.empty(points, dtype=torch.float64).pin_memory()
+        host_ms = wall(lambda: lib.bj_loglike(like.engine._h, C.cast(xp.data_ptr(), C.POINTER(C.c_double)), points, len(names),
+                                              C.byref(pm.c), C.cast(op.data_ptr(), C.POINTER(C.c_double))), 3, 1)
+    else:
+        ev = make_evaluator(c, like, names, const, points)
+        if c.rank == 0:
+            xp = torch.from_numpy(X).pin_memory()        # pinned like the single-GPU arm: no staging copy
+            host_ms = wall(lambda: ev.evaluate(xp), 3, 1)
+            ev.shutdown()
+        else:
+            ev.serve()
+    parity = None
+    if c.rank == 0:
+        net_p = syn.build_network(cfg, harness.port_classes())
+        ref = port.GWBinningLikelihoodPort(net_p[0], net_p[1], net_p[2], net_p[3], dict(fid), net_p[4], cfg["srate"],
+                                           cfg["seglen"], cfg["approx"])
+        parity = port_parity(ref, out.cpu().numpy(), X[lo[0]:hi[0]], names, const, 64)
+    nbin, nifo = int(like.Nbin), len(ifos)
+    fp64_per_point = (nbin + 1) * (24 + 10 * nifo) + 300          # SURVEY.md section 8d
+    like.engine.close()
+    if c.rank != 0:
+        return None
+    return {"workload": "C4: relative binning %s, H1/L1/V1, 256 s, %d bins (chi = 1, eps = 0.5), 2^20 points sharded over %d "
+                        "GPU(s) (%d per GPU)" % (cfg["approx"], nbin, c.world, n_loc),
+            "unit": "points/s", "setup_s": setup_s, "value": points / (step_ms * 1e-3), "ms_per_step": step_ms,
+            "kernel_ms": {"prologue": p_ms, "relbin": k_ms},
+            "e2e": {"value": points / (host_ms * 1e-3), "unit": "points/s", "ms_per_step": host_ms,
+                    "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": points * 8,
+                    "path": "bj_loglike (pinned host pointers)" if c.world == 1 else "ShardedEvaluator.evaluate (scatter + peer stores)",
+                    "note": "109 MB of parameters cross PCIe once per call: the end-to-end figure is a PCIe number"},
+            "roofline": {"bound": "fp64", "achieved": n_loc * fp64_per_point / (k_ms * 1e-3) / 1e9, "peak": peaks["dfma"] / 1e9,
+                         "unit": "GDFMA/s", "frac": n_loc * fp64_per_point / (k_ms * 1e-3) / peaks["dfma"],
+                         "instr_per_point": fp64_per_point, "traffic": None,
+                         "note": "libdevice sincospi per bin edge and detector counts as ~40 more FP64 instructions that the "
+                                 "algorithmic figure does not include"},
+            "parity_max_err_over_tol": parity, "parity_points": 64,
+            "parity_note": "against the NumPy restatement; bins and summary data are pinned to the reference's own "
+                           "setup_bins / compute_sdat (tests/golden/relbin_setup.npz), its log_like is dead code upstream",
+            "n_gpus": c.world}
+
+
+def secondary_c5(c, like, cfg, names, const):
+    """Ensemble sampler (stretch move, the update bajes' emcee wrapper drives) on the C2 data: 4096 walkers IN ALL, every
+    likelihood evaluation through pool.map(posterior.log_post, points) -> BatchedPool -> ShardedEvaluator."""
+    import torch
+    from bajes_b200 import Posterior, synthetic as syn
+    from bajes_b200.dist import ShardedLikelihood
+    from bajes_b200.ensemble import BoxPrior, EnsembleSampler
+    from bajes_b200.pool import BatchedPool
+    walkers, steps = 4096, 20
+    p0, _ = syn.draw_walkers(cfg, walkers, 123, "narrow")
+    lo, hi = p0.min(axis=0), p0.max(axis=0)
+    pad = 0.5 * (hi - lo)
+    bounds = np.stack([lo - pad, hi + pad], axis=1)
+    bounds[names.index("q"), 0] = max(1.0, bounds[names.index("q"), 0])
+    bounds[names.index("cos_iota")] = np.clip(bounds[names.index("cos_iota")], -1, 1)
+    for k in ("lambda1", "lambda2"):
+        bounds[names.index(k), 0] = max(0.0, bounds[names.index(k), 0])
+    prior = BoxPrior(names, bounds, const)
+    ev = make_evaluator(c, like, names, const, walkers) if c.world > 1 else None
+    if c.rank != 0:
+        ev.serve()
+        return None
+
+    def run(evaluator):
+        target = ShardedLikelihood(like, evaluator) if evaluator is not None else like
+        post = Posterior(target, prior)
+        pool = BatchedPool(post, processes=c.world)
+        s = EnsembleSampler(post, walkers, pool, seed=7)
+        s.initialize(p0)
+        torch.cuda.synchronize(c.dev)
+        t0 = time.perf_counter()
+        trace = s.run(steps)
+        torch.cuda.synchronize(c.dev)
+        return s, trace, time.perf_counter() - t0, pool
+
+    s, trace, wall_s, pool = run(ev)
+    same = None
+    if ev is not None:
+        ev.shutdown()
+        s1, _, _, _ = run(None)                    # the same seeded chain on this GPU alone
+        same = bool(np.array_equal(s1.pos, s.pos) and np.array_equal(s1.logp, s.logp))
+    idx = np.arange(0, walkers, 64)
+    fresh = like.log_like_batch(s.pos[idx], names, const) + prior.log_prior(None)
+    nb = like.engine.n_bins
+    n_eval = walkers * steps
+    return {"workload": "C5: stretch-move ensemble, %d walkers in all, %d steps on the C2 data (128 s BNS, %d bins x 3 detectors), "
+                        "likelihood through pool.map(posterior.log_post) -> BatchedPool -> %s"
+                        % (walkers, steps, nb, "ShardedEvaluator over %d GPUs" % c.world if c.world > 1 else "bj_loglike"),
+            "unit": "likelihood evaluations/s (end to end, host in / host out every call)",
+            "value": n_eval / wall_s, "walker_bins_per_s": n_eval * nb / wall_s, "s_per_sampler_step": wall_s / steps,
+            "batched_calls": pool.n_batched_calls, "acceptance": s.acceptance,
+            "logpost_max_first_last": [float(trace[0, 0]), float(trace[-1, 0])],
+            "e2e": {"value": n_eval / wall_s, "unit": "evaluations/s", "ms_per_step": 1e3 * wall_s / steps,
+                    "h2d_bytes_per_step": int(walkers * len(names) * 8), "d2h_bytes_per_step": walkers * 8},
+            "roofline": None,
+            "stored_logp_bit_identical_to_fresh_eval": bool(np.array_equal(fresh, s.logp[idx])),
+            "chain_bit_identical_to_one_gpu": same, "parity_max_err_over_tol": None,
+            "parity_note": "the likelihood is the headline's (parity there); here the check is that the chain is bit-identical "
+                           "for any number of GPUs and that stored log-posteriors equal fresh evaluations",
+            "n_gpus": c.world,
+            "note": "bajes' own samplers are not installable offline on the GPU box; the reference's ptmcmc driven through the "
+                    "same adapter is run in the build container (tests/test_sampler_adapters.py, scripts/run_c5_ptmcmc.py)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from bajes_b200 import GWLikelihood, engine, synthetic as syn
     from bajes_b200.dist import DeviceShardedLikelihood
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    c = Ctx()
+    c.args = args
+    c.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = rank = int(os.environ.get("RANK", "0"))
+    c.local = local = int(os.environ.get("LOCAL_RANK", "0"))
+    c.dist = dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    c.dev = dev = torch.device("cuda", local)
 
     cfg = syn.CONFIGS[args.config]
     W = args.walkers or cfg["n_walkers"]
@@ -297,14 +648,8 @@ def main():
     for a, b in ev:
         flush.zero_()                              # L2 flush, outside the timed events
         a.record()
-        step_device()                              # prologue + fused kernel (+ fix-up) + epilogue on this rank's walkers
+        step_device()                              # prologue + FP64 window + fused kernel (+ fix-up) + epilogue
         b.record()
-        if world > 1:
-            # The path shards by walkers with NO data-path collective: the timed step is each rank's own work.  The
-            # logL all-gather to the sampler rank is a caller-side step; it runs here, untimed (8 x 32 KB), and it is
-            # INSIDE the end-to-end number below.  (Inside the events it measured NCCL's small-message latency jitter
-            # at 8 ranks -- 0.05 to 4 ms per call on this pool, all ranks' local work being done within 20 us.)
-            sh.gather(out_dev)
         b.synchronize()
         kern_ms.append(like.engine.last_kernel_ms()[1])
     barrier()
@@ -321,11 +666,7 @@ def main():
     total_s = float(total_ms.item()) * 1e-3
 
     # ---- end-to-end through the public API, host buffers in / out inside the timed region ----------------------
-    #   N = 1: the host-pointer C-ABI entry bj_loglike (pinned X -> H2D -> prologue/kernel/epilogue -> D2H logL)
-    #   N > 1: ShardedEvaluator.evaluate on the sampler rank (host X -> device, NCCL broadcast, every rank evaluates
-    #          its slice, NCCL all-gather, device -> host), the other ranks in serve()
     pmap = like.param_map(names, const)
-    import ctypes as C
     lib = engine.load_library()
 
     def step_host():
@@ -333,6 +674,7 @@ def main():
                             C.byref(pmap.c), C.cast(out_pin.data_ptr(), C.POINTER(C.c_double)))
         assert rc == 0, lib.bj_last_error()
 
+    strong = None
     if world == 1:
         for _ in range(3):
             step_host()
@@ -344,16 +686,18 @@ def main():
         e2e_s = time.perf_counter() - t0
         assert np.array_equal(out_pin.numpy(), out_dev.cpu().numpy()), "host and device entry points disagree"
         h2d, d2h = int(Xmine.nbytes), int(W * 8)
+        e2e_path = "bj_loglike (host pointers)"
+        peer = None
     else:
-        from bajes_b200.dist import ShardedEvaluator
-
-        def eval_dev(xs, outs):
-            like.engine.loglike_device(xs.data_ptr(), xs.shape[0], len(names), pmap, outs.data_ptr(), 0,
-                                       torch.cuda.current_stream(dev).cuda_stream)
-
-        she = ShardedEvaluator(lambda Xs: like.log_like_batch(Xs, names, const), ndim=len(names), device=dev,
-                               local_eval_device=eval_dev)
-        e2e_s = 0.0
+        she = make_evaluator(c, like, names, const, W * world)
+        peer = she.peer is not None
+        e2e_s = strong_e2e_s = 0.0
+        # strong scaling, device resident: the same 4096 walkers in all, W / world per rank
+        Ws = W // world
+        xs_dev = x_dev[:Ws].contiguous()
+        outs_dev = torch.empty(Ws, dtype=torch.float64, device=dev)
+        strong_ms, _ = timed(lambda: sh.evaluate_local(xs_dev, outs_dev), dev, args.steps, 3)
+        strong_ms = max_over_ranks(c, strong_ms)
         if rank == 0:
             for _ in range(3):
                 got = she.evaluate(Xall)
@@ -362,12 +706,49 @@ def main():
             for _ in range(args.steps):
                 got = she.evaluate(Xall)
             e2e_s = time.perf_counter() - t0
+            Xs = np.ascontiguousarray(Xall[:Ws * world])
+            for _ in range(3):
+                got_s = she.evaluate(Xs)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                got_s = she.evaluate(Xs)
+            strong_e2e_s = time.perf_counter() - t0
             she.shutdown()
-            assert np.array_equal(got[:W], out_dev.cpu().numpy()), "sharded and local results disagree"
+            # EVERY rank's slice against this GPU alone: walker sharding must not change a bit
+            alone = np.concatenate([like.log_like_batch(Xall[r * W:(r + 1) * W], names, const) for r in range(world)])
+            assert np.array_equal(got, alone), "sharded results differ from the single-GPU evaluation of all %d rows" % len(alone)
+            assert np.array_equal(got_s, alone[:Ws * world]), "strong-scaling results differ from the single-GPU evaluation"
+            strong = {"walkers_total": Ws * world, "walkers_per_gpu": Ws,
+                      "value": Ws * world * nb / (strong_ms * 1e-3), "ms_per_step": strong_ms,
+                      "e2e": {"value": Ws * world * nb * args.steps / strong_e2e_s, "ms_per_step": 1e3 * strong_e2e_s / args.steps,
+                              "h2d_bytes_per_step": int(Xs.nbytes), "d2h_bytes_per_step": int(Ws * world * 8)},
+                      "note": "fixed total batch: what a sampler with a 4096-walker ensemble gets from N GPUs"}
         else:
             she.serve()
         h2d, d2h = int(Xall.nbytes), int(W * world * 8)
+        e2e_path = ("ShardedEvaluator.evaluate, no collective: host X -> ONE H2D copy into the sampler rank's HBM -> every rank's "
+                    "prologue reads its rows, and every rank's epilogue stores its logL, over NVLink peer memory (flag-ordered) -> D2H") \
+            if peer else "ShardedEvaluator.evaluate: host X -> H2D -> NCCL scatter -> per-rank kernels -> NCCL gather -> D2H (no peer access)"
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- peaks and the secondary configs (collective: every rank takes part) -------------------------------------
+    peaks = {"dfma": engine.measure_peak("dfma", local), "mufu": engine.measure_peak("mufu", local)}
+    pk = {}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peaks["hbm"] = float(pk.get("hbm_gbs", 6650.0))
+    want = {"C1", "C3", "C4", "C5"} if args.secondary == "all" else set() if args.secondary == "none" else set(args.secondary.split(","))
+    secondary = {}
+    for key, fn in (("C1", lambda: secondary_c1(c, peaks)), ("C3", lambda: secondary_c3(c, peaks)),
+                    ("C4", lambda: secondary_c4(c, peaks)), ("C5", lambda: secondary_c5(c, like, cfg, names, const))):
+        if key in want and args.config == "C2":
+            t0 = time.perf_counter()
+            r = fn()
+            if r is not None:
+                r["wall_s_incl_setup"] = time.perf_counter() - t0
+                secondary[key] = r
 
     if rank != 0:
         if world > 1:
@@ -378,51 +759,41 @@ def main():
     units_per_launch = W * nb
     info = like.engine.last_launch_info()
     tensor_core = info[2] == 256           # fullgrid_tile_kernel: 256 threads = 64 walkers per CTA
-    fp64_pu, sfu_pu = instr_per_unit(cfg["approx"], nifo, args.sincos, tensor_core)
+    rot = tensor_core and nifo > 1 and not os.environ.get("BAJES_B200_NO_ROT")
+    fp64_pu, sfu_pu = instr_per_unit(cfg["approx"], nifo, args.sincos, tensor_core, rot)
     k_s = float(np.mean(kern_ms)) * 1e-3
-    peak_dfma = engine.measure_peak("dfma", local)
-    peak_mufu = engine.measure_peak("mufu", local)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     n_wtiles = (W + 63) // 64 if tensor_core else (W + 127) // 128
     # algorithmic bytes: every walker tile streams the static table once; coefficient block; partial sums
-    alg_bytes = n_wtiles * nb * info[6] * 8 + W * 50 * 8 + info[5] * 2 * nifo * W * 8
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.config + ":" + args.sincos)
-        except Exception:
-            traffic = None
-    lines = {"fp64": (fp64_pu, peak_dfma, "GDFMA/s"), "sfu": (sfu_pu, peak_mufu, "GMUFU/s")}
+    alg_bytes = n_wtiles * nb * info[6] * 8 + W * 70 * 8 + info[5] * 2 * nifo * W * 8
+    traffic, traffic_note = measured_traffic(args.config + ":" + args.sincos)
+    lines = {"fp64": (fp64_pu, peaks["dfma"], "GDFMA/s"), "sfu": (sfu_pu, peaks["mufu"], "GMUFU/s")}
     # the limiting roofline of the two the north star names = the one that needs the longer time
     bound = max(lines, key=lambda k: lines[k][0] / lines[k][1])
     ipu, peak, unit = lines[bound]
     achieved = units_per_launch * ipu / k_s
     other = "sfu" if bound == "fp64" else "fp64"
+    K = 12 if cfg["approx"] == "TaylorF2_3.5PN" else 28
     roofline = {"bound": bound, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": unit,
-                "frac": achieved / peak, "traffic": traffic, "instr_per_unit": ipu,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "instr_per_unit": ipu,
                 "units_per_launch": units_per_launch, "kernel_ms": k_s * 1e3,
-                "kernel": "fullgrid_%s_kernel<%d ifo, %s, %s>" % (
-                    "tile" if tensor_core else "mixed" if args.sincos != "fp64" else "fp64", nifo, cfg["approx"], args.sincos),
+                "kernel": "fullgrid_window_kernel (FP64, heaviest bins) + fullgrid_%s_kernel<%d ifo, %s, %s%s>: the time between "
+                          "the prologue's and the epilogue's events" % (
+                              "tile" if tensor_core else "mixed" if args.sincos != "fp64" else "fp64", nifo, cfg["approx"],
+                              args.sincos, ", rotated detectors" if rot else ""),
                 "peak_source": "measured live by bj_measure_peak (register-resident DFMA / MUFU chains); "
                                "MEASURED_PEAKS.json has no FP64 or SFU figure",
+                "note": "what limits this kernel is neither pipe but instruction issue / register-operand bandwidth "
+                        "(DESIGN.md section 4.1): with one MUFU pair per bin the SFU line no longer measures it; the FP64 line "
+                        "(12 of its 13.9 FMAs per unit run as DMMA.8x8x4) is the larger of the two the north star names",
                 other: {"instr_per_unit": lines[other][0], "achieved": units_per_launch * lines[other][0] / k_s / 1e9,
                         "peak": lines[other][1] / 1e9, "unit": lines[other][2],
                         "frac": units_per_launch * lines[other][0] / k_s / lines[other][1]},
-                # the phase GEMM alone, in the units of a tensor-core roofline: K FMAs per walker*bin on DMMA.8x8x4 against
-                # the FP64 rate measured on this GPU (DMMA and DFMA share it: scripts/ubench_dmma.cu)
-                "tensor": ({"achieved": units_per_launch * 2 * (12 if cfg["approx"] == "TaylorF2_3.5PN" else 28) / k_s / 1e12,
-                            "peak": 2 * peak_dfma / 1e12, "unit": "TFLOP/s (FP64, DMMA)",
-                            "frac": units_per_launch * (12 if cfg["approx"] == "TaylorF2_3.5PN" else 28) / k_s / peak_dfma}
+                "tensor": ({"achieved": units_per_launch * 2 * K / k_s / 1e12, "peak": 2 * peaks["dfma"] / 1e12,
+                            "unit": "TFLOP/s (FP64, DMMA)", "frac": units_per_launch * K / k_s / peaks["dfma"]}
                            if tensor_core else None),
-                "hbm": {"achieved": alg_bytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": alg_bytes / k_s / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
-                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+                "hbm": {"achieved": alg_bytes / k_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": alg_bytes / k_s / 1e9 / peaks["hbm"], "algorithmic_bytes": alg_bytes,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in pk else "fallback"}}
 
     value = W * world * nb * args.steps / total_s
     e2e_value = W * world * nb * args.steps / e2e_s
@@ -446,15 +817,16 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE if args.sincos != "fp64" else "f64", "data": "synthetic",
             "config": workload(cfg, args, W), "evals_per_s": value / nb,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "path": "bj_loglike (host pointers)" if world == 1 else
-                            "ShardedEvaluator.evaluate: host X -> NCCL broadcast -> per-rank slices -> NCCL all-gather -> host"},
-            "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "path": e2e_path},
+            "strong_scaling": strong,
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "parity_max_err_over_tol": None if cpu is None else cpu["parity_max_err_over_tol"],
             "sincos": args.sincos, "wall_s_timed_region": t_wall,
-            "per_rank_ms": {"step_and_fused_kernel": per_rank_all}}
+            "per_rank_ms": {"step_and_fused_kernel": per_rank_all},
+            "kernel_source_sha": source_sha(), "secondary": secondary}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -335,6 +335,48 @@ def test_calibration_envelopes_and_psd_weights(key, sincos):
     assert one[0] == got[5]
 
 
+def test_detector_inner_products_with_psd_weights_are_consistent():
+    """Detector.compute_inner_products with PSD weights (detector.py:524-531): dd is recomputed with psd * weights and
+    the fourth value is sum(log w); together with the weighted dh / hh they rebuild logL as log_like.py:181 does."""
+    cfg = syn.CONFIGS["C2_small"]
+    gold = load_golden("extras_small.npz")
+    key = "both_marg0"
+    like = _like(cfg, gold, nspcal=len(gold["spcal_freqs_" + key]), spcal_freqs=gold["spcal_freqs_" + key],
+                 nweights=len(gold["len_weights_" + key]), len_weights=gold["len_weights_" + key])
+    names = [str(n) for n in gold["names_" + key]]
+    p = {k: float(v) for k, v in zip(names, gold["X_" + key][3])}
+    p.update(syn.constants(cfg))
+    dh = hh = dd = w = 0.0
+    for ifo in like.ifos:
+        a, b, c, d = like.dets[ifo].compute_inner_products(None, dict(p), "freq", psd_weight_factor=True)
+        assert d != 0.0 and c != like.dets[ifo]._dd
+        dh, hh, dd, w = dh + a, hh + b, dd + c, w + d
+    rebuilt = -0.5 * (hh + dd) + np.real(dh) - like.logZ_noise - 0.5 * w
+    ref = gold["logl_" + key][3]
+    assert abs(rebuilt - ref) <= harness.tolerance(np.array([ref]))[0]
+
+
+def test_time_marginalised_context_parts_and_frequency_split():
+    """A time-marginalised likelihood still reports the per-detector <d|h>, <h|h> of a point (they do not depend on
+    the marginalisation), and refuses the frequency split (the FFT needs a walker's whole spectrum on one GPU)."""
+    cfg = syn.CONFIGS["C1"]
+    gold = load_golden("c1_bbh.npz")
+    plain = _like(cfg, gold)
+    tm = _like(cfg, gold, marg_time_shift=True)
+    p = {k: float(v) for k, v in zip(_names(gold), gold["X"][1])}
+    p.update(syn.constants(cfg))
+    a, b = plain.inner_products(dict(p)), tm.inner_products(dict(p))
+    for ifo in plain.ifos:          # same numbers up to FP32 rounding (the plain context evaluates its heaviest bins in FP64)
+        assert abs(a[ifo][0] - b[ifo][0]) <= 1e-6 * abs(a[ifo][0]) and abs(a[ifo][1] - b[ifo][1]) <= 1e-9 * a[ifo][1]
+    assert np.isfinite(tm.log_like(dict(p))) and tm.log_like(dict(p)) != plain.log_like(dict(p))
+    import torch
+    x = torch.zeros((1, 13), dtype=torch.float64, device="cuda")
+    sums = torch.zeros((4, 1), dtype=torch.float64, device="cuda")
+    with pytest.raises(NotImplementedError):
+        tm.engine.partial_device(x.data_ptr(), 1, 13, tm.param_map(_names(gold), syn.constants(cfg)), 0, 1,
+                                 sums.data_ptr())
+
+
 # ------------------------------------------------------------------------------------------------------
 # time-shift marginalisation (log_like.py:135-156), against reference golden vectors
 # ------------------------------------------------------------------------------------------------------
