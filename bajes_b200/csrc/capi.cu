@@ -226,7 +226,7 @@ struct Layout {
 
 // binweight[k] ~ share of bin k in <h|h> of an inspiral (sum_i f^(-7/3) / S_i).  The shortest run of consecutive slots
 // that holds the fraction prec_share of the sum of SQUARED weights (the bins whose terms are signal-dominated at high SNR,
-// where FP32 rounding does not average down), at most prec_frac of the table, is cut into small chunks that a launch of
+// where FP32 rounding does not average down), at most prec_frac of the table, is cut into 64-record chunks that a launch of
 // the FP64 window kernel evaluates.  For the design PSDs of H1/L1/V1 a share of 0.9 is the band 20-87 Hz: 1.6 % of the
 // bins of a 128 s segment sampled to 4096 Hz.
 static int build_layout(Layout& L, long n, const double* freqs, const bj_extras* ex, const std::vector<double>* binweight,
@@ -275,7 +275,9 @@ static int build_layout(Layout& L, long n, const double* freqs, const bj_extras*
 #ifndef BJ_TARGET_CHUNKS
 #define BJ_TARGET_CHUNKS 128
 #endif
-    long per = (total + BJ_TARGET_CHUNKS - 1) / BJ_TARGET_CHUNKS;
+    long target = BJ_TARGET_CHUNKS;
+    if (const char* ev = getenv("BAJES_B200_CHUNKS")) target = std::max(1L, atol(ev));
+    long per = (total + target - 1) / target;
     per = ((per + kTileBins - 1) / kTileBins) * kTileBins;
     if (per < 256) per = 256;
     L.per = (int)per;
@@ -318,7 +320,7 @@ static int build_layout(Layout& L, long n, const double* freqs, const bj_extras*
         const long cut[4] = {s0, std::min(std::max(L.prec_lo, s0), s1), std::min(std::max(L.prec_hi, s0), s1), s1};
         for (int piece = 0; piece < 3; ++piece) {
             const bool precise = piece == 1;
-            const long step = precise ? 256 : per;
+            const long step = precise ? kTileBins : per;      // one TMA tile per FP64 CTA: short serial chains, many CTAs
             for (long a = cut[piece]; a < cut[piece + 1]; a += step) {
                 ChunkDesc cd;
                 cd.start = (int)a;
@@ -849,7 +851,7 @@ template <int NIFO, int MODEL, int SC, bool SPCAL>
 static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
     constexpr int RB = RecM<NIFO>::kBytes;
     if (c0 < c->n_precise) {
-        // the heaviest bins in FP64 (chunks of 256 records; the table pointer is offset so that chunk.start indexes it)
+        // the heaviest bins in FP64 (chunks of 64 records; the table pointer is offset so that chunk.start indexes it)
         constexpr int RS = Rec<NIFO>::kDoubles;
         const int p1 = c1 < c->n_precise ? c1 : c->n_precise;
         const size_t smem64 = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
@@ -1065,8 +1067,10 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
     to_dev_map(map, pm);
     const int tpb = 128;
     const unsigned nblk = (unsigned)((n_walkers + tpb - 1) / tpb);
+    const unsigned nblk_pro = (unsigned)((n_walkers + kProWalkers - 1) / kProWalkers);
+    const dim3 blk_pro(kProWalkers, 1 + BJ_MAX_IFO);
     CUDA_TRY(cudaEventRecord(c->ev[0], st));
-    prologue_kernel<<<nblk, tpb, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
+    prologue_kernel<<<nblk_pro, blk_pro, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
     if (c->d_coef_ex)
         prologue_extras_kernel<<<nblk, tpb, 0, st>>>(c->cfg, c->dims, *emap, x_dev, ndim, n_walkers, c->d_coef,
                                                      c->d_coef_ex, c->cap_walkers);
@@ -1143,7 +1147,8 @@ extern "C" int bj_partial_device(bj_ctx* c, const double* x_dev, int64_t n_walke
     ParamMapDev pm;
     to_dev_map(map, pm);
     const unsigned nblk = (unsigned)((n_walkers + 127) / 128);
-    prologue_kernel<<<nblk, 128, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
+    prologue_kernel<<<(unsigned)((n_walkers + kProWalkers - 1) / kProWalkers), dim3(kProWalkers, 1 + BJ_MAX_IFO), 0, st>>>(
+        c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
     if (c->d_coef_ex)
         prologue_extras_kernel<<<nblk, 128, 0, st>>>(c->cfg, c->dims, *emap, x_dev, ndim, n_walkers, c->d_coef,
                                                      c->d_coef_ex, c->cap_walkers);
@@ -1237,7 +1242,7 @@ extern "C" int bj_project_waveform(bj_ctx* c, const double* x_host, int32_t ndim
     ParamMapDev pm;
     to_dev_map(map, pm);
     cudaMemcpyAsync(d_x, x_host, ndim * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-    prologue_kernel<<<1, 32, 0, c->stream>>>(c->cfg, pm, d_x, ndim, 1, c->d_coef, c->cap_walkers);
+    prologue_kernel<<<1, dim3(kProWalkers, 1 + BJ_MAX_IFO), 0, c->stream>>>(c->cfg, pm, d_x, ndim, 1, c->d_coef, c->cap_walkers);
     const unsigned nblk = (unsigned)((c->n_bins + 255) / 256);
     waveform_kernel<<<nblk, 256, 0, c->stream>>>(c->cfg, c->d_freqs, c->n_bins, c->d_coef, c->cap_walkers, d_h);
     cudaMemcpyAsync(out_h_host, d_h, (size_t)c->cfg.n_ifo * c->n_bins * sizeof(double2), cudaMemcpyDeviceToHost,
@@ -1286,7 +1291,7 @@ extern "C" int bj_polarizations(int device, int approx, double seglen, int centr
     if (e == cudaSuccess) e = cudaMemcpy(d_x, x_host, ndim * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_f, freqs, (size_t)n_freqs * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        prologue_kernel<<<1, 32>>>(cfg, pm, d_x, ndim, 1, d_coef, 1);
+        prologue_kernel<<<1, dim3(kProWalkers, 1 + BJ_MAX_IFO)>>>(cfg, pm, d_x, ndim, 1, d_coef, 1);
         polarizations_kernel<<<(unsigned)((n_freqs + 255) / 256), 256>>>(seglen, centre_shift, d_f, n_freqs, d_coef, 1,
                                                                          d_hp, d_hc);
         e = cudaGetLastError();
@@ -1415,6 +1420,34 @@ extern "C" int bj_peer_signal(int device, void* base_dev, int32_t slot, int64_t 
     if (!base_dev || slot < 0 || slot >= BJ_PEER_FLAGS) return fail(BJ_ERR_INVALID, "bad arguments");
     CUDA_TRY(cudaSetDevice(device));
     peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)base_dev, slot, (long long)value);
+    CUDA_TRY(cudaGetLastError());
+    return BJ_OK;
+}
+
+extern "C" int bj_peer_scatter(int device, void* base_dev, int64_t dst_offset_bytes, const void* src_host,
+                               void* stage_pinned, int32_t n_parts, const int64_t* part_begin, const int64_t* part_end,
+                               const int32_t* part_flag_slot, int64_t value, void* stream) {
+    if (!base_dev || !src_host || n_parts < 0 || !part_begin || !part_end || !part_flag_slot)
+        return fail(BJ_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    char* dst = (char*)base_dev + dst_offset_bytes;
+    const char* src = (const char*)src_host;
+    char* stage = (char*)stage_pinned;
+    const int64_t piece = 2 << 20;
+    for (int p = 0; p < n_parts; ++p) {
+        if (part_flag_slot[p] < 0 || part_flag_slot[p] >= BJ_PEER_FLAGS) return fail(BJ_ERR_INVALID, "bad flag slot");
+        for (int64_t o = part_begin[p]; o < part_end[p]; o += piece) {
+            const int64_t n = std::min(piece, part_end[p] - o);
+            if (stage) {
+                memcpy(stage + o, src + o, (size_t)n);
+                CUDA_TRY(cudaMemcpyAsync(dst + o, stage + o, (size_t)n, cudaMemcpyHostToDevice, st));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(dst + o, src + o, (size_t)n, cudaMemcpyHostToDevice, st));
+            }
+        }
+        peer_signal_kernel<<<1, 1, 0, st>>>((long long*)base_dev, part_flag_slot[p], (long long)value);
+    }
     CUDA_TRY(cudaGetLastError());
     return BJ_OK;
 }

@@ -222,14 +222,60 @@ __global__ void calibrate_kernel(double* out) {
 }
 
 // ---- prologue ---------------------------------------------------------------------------------
-__global__ void prologue_kernel(DeviceConfig cfg, ParamMapDev pm, const double* __restrict__ x, int ndim,
-                                long n_walkers, double* __restrict__ coef, long stride) {
-    const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_walkers) return;
-    double out[C_NUM];
-    walker_coefficients(cfg, pm, x + w * ndim, out);
+// One walker = 1 + BJ_MAX_IFO threads: role 0 derives the source's phase / amplitude coefficients, role 1 + i the antenna
+// pattern, delay and rotation constants of detector i (all independent given the walker's row), then role 0 combines the
+// validity flags.  A call with few walkers is latency-bound in this kernel: the split shortens its dependent chain ~2x.
+constexpr int kProWalkers = 32;
+__global__ void __launch_bounds__(kProWalkers * (1 + BJ_MAX_IFO))
+prologue_kernel(DeviceConfig cfg, ParamMapDev pm, const double* __restrict__ x, int ndim, long n_walkers,
+                double* __restrict__ coef, long stride) {
+    __shared__ double s_tau[BJ_MAX_IFO][kProWalkers];
+    __shared__ int s_ok[BJ_MAX_IFO][kProWalkers];
+    const int lane = threadIdx.x, role = threadIdx.y;
+    const long w = (long)blockIdx.x * kProWalkers + lane;
+    const bool live = w < n_walkers;
+    const double* xr = x + (live ? w : 0) * ndim;
+    double out[C_ROT0];
+    bool ok = true;
+    if (role == 0) {
 #pragma unroll 1
-    for (int j = 0; j < C_NUM; ++j) coef[j * stride + w] = out[j];
+        for (int j = 0; j < C_ROT0; ++j) out[j] = 0.0;
+        ok = walker_intrinsic(cfg, pm, xr, out);
+    } else {
+        const int i = role - 1;
+        double o5[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, rot[kRotSlots];
+#pragma unroll 1
+        for (int a = 0; a < kRotSlots; ++a) rot[a] = 0.0;
+        bool okd = true;
+        if (i < cfg.n_ifo) okd = walker_detector(cfg, pm, xr, i, o5, i >= 1 ? rot : nullptr);
+        s_tau[i][lane] = fabs(o5[0]);
+        s_ok[i][lane] = okd ? 1 : 0;
+        if (live) {
+            coef[(C_TAU0 + i) * stride + w] = o5[0];
+            coef[(C_CR0 + i) * stride + w] = o5[1];
+            coef[(C_CI0 + i) * stride + w] = o5[2];
+            coef[(C_FP0 + i) * stride + w] = o5[3];
+            coef[(C_FC0 + i) * stride + w] = o5[4];
+            if (i >= 1) {
+#pragma unroll 1
+                for (int a = 0; a < kRotSlots; ++a) coef[(size_t)(C_ROT0 + kRotSlots * (i - 1) + a) * stride + w] = rot[a];
+            }
+        }
+    }
+    __syncthreads();
+    if (role == 0 && live) {
+        double tmax = 0.0;
+        for (int i = 0; i < cfg.n_ifo; ++i) {
+            ok = ok && s_ok[i][lane] != 0;
+            tmax = fmax(tmax, s_tau[i][lane]);
+        }
+        out[C_VALID] = walker_validity(cfg, out, ok, tmax);
+#pragma unroll 1
+        for (int j = 0; j < C_TAU0; ++j) coef[j * stride + w] = out[j];
+        coef[C_AMP * stride + w] = out[C_AMP];
+        coef[C_VALID * stride + w] = out[C_VALID];
+        coef[C_COSI * stride + w] = out[C_COSI];
+    }
 }
 
 // calibration-envelope node values and PSD weights of every walker (contexts created with extras)
@@ -468,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
 // ---- the FP64 window kernel ----------------------------------------------------------------------------------------
 // The production path evaluates the bins that carry most of the signal power -- where, at high SNR, the terms of <d|h>
 // are coherent and FP32 rounding does not average down -- in FP64 (capi.cu: build_layout, the "precise window": a few
-// per cent of the table, cut into chunks of 256 records).  Same structure as fullgrid_kernel (one thread = one walker,
+// per cent of the table, cut into chunks of 64 records = one TMA tile).  Same structure as fullgrid_kernel (one thread = one walker,
 // TMA ring of FP64 records), but built for speed on a uniform grid:
 //   * ONE sin/cos per bin (detector 0), from the exactly reduced angle with FP64 polynomials on [-pi/4, pi/4];
 //   * the other detectors by FP64 rotation e^{-2 pi i f (tau_i - tau_0)}, advanced bin to bin by a complex multiplication
@@ -1775,6 +1821,38 @@ __device__ __forceinline__ void cis_neg_turns(double turns, double& c, double& s
     double s;
     sincospi(2.0 * r, &s, &c);
     s_neg = -s;
+}
+// the same with the in-house FP64 polynomials (|error| < 1e-14: ROQ / relative-binning kernels, where the libdevice
+// sincospi was a third of the instructions)
+__device__ __forceinline__ void cis_neg_turns_fast(double turns, double& c, double& s_neg) {
+    double s;
+    sincos_turns_f64(turns, s, c);
+    s_neg = -s;
+}
+// eval_point for the 3.5PN + 6PN-tides model: the coefficients a[1], a[8], a[9], a[11], a[13..15], b[2..6], c8 are
+// structurally zero (walker.cuh), so the phase needs 13 instead of 30 FMAs
+template <int MODEL>
+__device__ __forceinline__ void eval_point_m(const WalkerCoefReg& r, double u, double L, double w5, double& turns,
+                                             double& Q) {
+    if constexpr (MODEL == MODEL_35) {
+        const double u2 = u * u;
+        double p = fma(r.a[12], u2, r.a[10]);
+        p = fma(p, u2 * u, r.a[7]);
+#pragma unroll
+        for (int k = 6; k >= 2; --k) p = fma(p, u, r.a[k]);
+        p = fma(p, u2, r.a[0]);
+        const double bl = fma(r.b[1], u, r.b[0]);
+        turns = fma(w5, p, fma(L, bl, r.k0));
+        double qq = fma(r.q6l, L, r.q[4]);
+        qq = fma(r.q[5], u, qq);
+        qq = fma(qq, u, r.q[3]);
+        qq = fma(qq, u, r.q[2]);
+        qq = fma(qq, u, r.q[1]);
+        qq = fma(qq, u, r.q[0]);
+        Q = fma(u2, qq, 1.0);
+    } else {
+        eval_point(r, u, L, w5, turns, Q);
+    }
 }
 
 // ---- waveform of ONE walker (walker index 0 of coef) on every detector ---------------------------

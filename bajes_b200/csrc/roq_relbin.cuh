@@ -105,16 +105,24 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 constexpr int kRoqWarps = 4;
 
+// Two phases per walker (one warp):
+//   1. the waveform at the linear nodes, FP64 (generic Horner + sincospi), into shared memory -- compute only;
+//   2. per detector, the four cubic-B-spline coefficient rows are STREAMED against it: the loop body is four independent
+//      16-byte loads per node and lane, unrolled, with nothing but FMAs behind them, so that a warp keeps ~8 KB in
+//      flight (the first version evaluated the waveform inside this loop: every load waited behind ~100 dependent FP64
+//      instructions and the kernel sat at 17 % of the DRAM bandwidth, profiles/r02_roq_wide_before_*.txt).
+// Shared memory: kRoqWarps x n_lin complex doubles (26 KB at n_lin = 400).
+template <int MODEL>
 __global__ void __launch_bounds__(kRoqWarps * 32) roq_kernel(DeviceConfig cfg, RoqDevice tab,
                                                               const double* __restrict__ coef, long stride,
                                                               long n_walkers, double* __restrict__ logl,
                                                               double* __restrict__ sums) {
-    const long w = (long)blockIdx.x * kRoqWarps + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char roq_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* hs = reinterpret_cast<double2*>(roq_smem) + (size_t)warp * tab.n_lin;
+    const long w = (long)blockIdx.x * kRoqWarps + warp;
     if (w >= n_walkers) return;
     const int nifo = cfg.n_ifo;
-    WalkerCoefReg r;
-    load_coef(r, coef, stride, w);
     const double amp = coef[C_AMP * stride + w];
     bool valid = coef[C_VALID * stride + w] != 0.0;
 
@@ -133,39 +141,51 @@ __global__ void __launch_bounds__(kRoqWarps * 32) roq_kernel(DeviceConfig cfg, R
         }
     }
 
-    // <d|h>: sum_j omega_ij(tc) h(F_L,j)     (h without centre shift / ramp: waveform.py:390, detector.py:418)
-    double zr[BJ_MAX_IFO] = {0, 0, 0}, zi[BJ_MAX_IFO] = {0, 0, 0};
-    for (long j = lane; j < tab.n_lin; j += 32) {
-        const int idx = tab.mask_omega[j];
-        const double4 nd = reinterpret_cast<const double4*>(tab.node)[idx];
-        double turns, Q;
-        eval_point(r, nd.x, nd.y, nd.z, turns, Q);
-        double c, sn;
-        cis_neg_turns(turns, c, sn);
-        const double a = Q * nd.w;
-        const double hr = a * c, hi = a * sn;
-        for (int i = 0; i < nifo; ++i) {
-            const double2* cp = tab.coef + ((size_t)i * tab.n_coef + row0[i]) * tab.n_lin + j;
-            double wr = 0.0, wi = 0.0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const double2 cc = cp[(size_t)m * tab.n_lin];
-                wr = fma(N[i][m], cc.x, wr);
-                wi = fma(N[i][m], cc.y, wi);
-            }
-            zr[i] += wr * hr - wi * hi;
-            zi[i] += wr * hi + wi * hr;
+    // ---- phase 1: h(F_L,j) (no centre shift / ramp: waveform.py:390, detector.py:418) and <h|h> ----
+    double hh[BJ_MAX_IFO] = {0, 0, 0};
+    {
+        WalkerCoefReg r;
+        load_coef(r, coef, stride, w);
+        for (long j = lane; j < tab.n_lin; j += 32) {
+            const double4 nd = reinterpret_cast<const double4*>(tab.node)[tab.mask_omega[j]];
+            double turns, Q;
+            eval_point_m<MODEL>(r, nd.x, nd.y, nd.z, turns, Q);
+            double c, sn;
+            cis_neg_turns_fast(turns, c, sn);
+            const double a = Q * nd.w;
+            hs[j] = make_double2(a * c, a * sn);
+        }
+        // <h|h>: sum_j psi_ij |h(F_Q,j)|^2
+        for (long j = lane; j < tab.n_quad; j += 32) {
+            const double4 nd = reinterpret_cast<const double4*>(tab.node)[tab.mask_psi[j]];
+            double turns, Q;
+            eval_point_m<MODEL>(r, nd.x, nd.y, nd.z, turns, Q);
+            const double a = Q * nd.w;
+            for (int i = 0; i < nifo; ++i) hh[i] = fma(tab.psi[(size_t)i * tab.n_quad + j], a * a, hh[i]);
         }
     }
-    // <h|h>: sum_j psi_ij |h(F_Q,j)|^2
-    double hh[BJ_MAX_IFO] = {0, 0, 0};
-    for (long j = lane; j < tab.n_quad; j += 32) {
-        const int idx = tab.mask_psi[j];
-        const double4 nd = reinterpret_cast<const double4*>(tab.node)[idx];
-        double turns, Q;
-        eval_point(r, nd.x, nd.y, nd.z, turns, Q);
-        const double a = Q * nd.w;
-        for (int i = 0; i < nifo; ++i) hh[i] = fma(tab.psi[(size_t)i * tab.n_quad + j], a * a, hh[i]);
+    __syncwarp();
+
+    // ---- phase 2: <d|h>_i = sum_j omega_ij(tc) h_j, omega = sum_m N_m c_{row0 + m, j} ----
+    double zr[BJ_MAX_IFO] = {0, 0, 0}, zi[BJ_MAX_IFO] = {0, 0, 0};
+    for (int i = 0; i < nifo; ++i) {
+        const double2* p0 = tab.coef + ((size_t)i * tab.n_coef + row0[i]) * tab.n_lin;
+        const double2* p1 = p0 + tab.n_lin;
+        const double2* p2 = p1 + tab.n_lin;
+        const double2* p3 = p2 + tab.n_lin;
+        const double n0 = N[i][0], n1 = N[i][1], n2 = N[i][2], n3 = N[i][3];
+        double ar = 0.0, ai = 0.0;
+#pragma unroll 4
+        for (long j = lane; j < tab.n_lin; j += 32) {
+            const double2 c0 = __ldg(p0 + j), c1 = __ldg(p1 + j), c2 = __ldg(p2 + j), c3 = __ldg(p3 + j);
+            const double2 h = hs[j];
+            const double wr = fma(n3, c3.x, fma(n2, c2.x, fma(n1, c1.x, n0 * c0.x)));
+            const double wi = fma(n3, c3.y, fma(n2, c2.y, fma(n1, c1.y, n0 * c0.y)));
+            ar += wr * h.x - wi * h.y;
+            ai += wr * h.y + wi * h.x;
+        }
+        zr[i] = ar;
+        zi[i] = ai;
     }
 
     double dh_re = 0.0, dh_im = 0.0, hh_tot = 0.0;
@@ -190,13 +210,26 @@ __global__ void __launch_bounds__(kRoqWarps * 32) roq_kernel(DeviceConfig cfg, R
     }
 }
 
-static inline int launch_roq(const DeviceConfig& cfg, const RoqDevice& tab, const double* coef, long stride,
-                             long n_walkers, double* logl, double* sums, cudaStream_t st, int* info) {
+template <int MODEL>
+static inline int launch_roq_m(const DeviceConfig& cfg, const RoqDevice& tab, const double* coef, long stride,
+                               long n_walkers, double* logl, double* sums, cudaStream_t st, int* info) {
     const unsigned nblk = (unsigned)((n_walkers + kRoqWarps - 1) / kRoqWarps);
-    roq_kernel<<<nblk, kRoqWarps * 32, 0, st>>>(cfg, tab, coef, stride, n_walkers, logl, sums);
-    info[0] = (int)nblk; info[1] = 1; info[2] = kRoqWarps * 32; info[3] = 0;
+    const size_t smem = (size_t)kRoqWarps * tab.n_lin * sizeof(double2);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(roq_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    roq_kernel<MODEL><<<nblk, kRoqWarps * 32, smem, st>>>(cfg, tab, coef, stride, n_walkers, logl, sums);
+    info[0] = (int)nblk; info[1] = 1; info[2] = kRoqWarps * 32; info[3] = (int)smem;
     info[4] = (int)tab.n_lin; info[5] = (int)tab.n_quad; info[6] = (int)tab.n_coef; info[7] = 100;
     return (int)cudaGetLastError();
+}
+
+static inline int launch_roq(const DeviceConfig& cfg, const RoqDevice& tab, const double* coef, long stride,
+                             long n_walkers, double* logl, double* sums, cudaStream_t st, int* info) {
+    if (cfg.approx == BJ_APPROX_TAYLORF2_35PN)
+        return launch_roq_m<MODEL_35>(cfg, tab, coef, stride, n_walkers, logl, sums, st, info);
+    return launch_roq_m<MODEL_GENERIC>(cfg, tab, coef, stride, n_walkers, logl, sums, st, info);
 }
 
 // ================================================================================================
@@ -258,42 +291,66 @@ struct RelbinDevice {
     }
 };
 
+// One thread per walker, loop over the bin edges.  NIFO is a template parameter so that the per-detector state stays in
+// registers (the first version indexed it with a run-time detector count: it lived in local memory), and the edge / bin
+// tables -- read by every thread at the same index -- sit in shared memory when they fit (STAGE).
+template <int NIFO, int MODEL, bool STAGE>
 __global__ void __launch_bounds__(128) relbin_kernel(DeviceConfig cfg, RelbinDevice tab,
                                                       const double* __restrict__ coef, long stride, long n_walkers,
                                                       double* __restrict__ logl, double* __restrict__ sums) {
+    extern __shared__ __align__(16) unsigned char relbin_smem[];
+    const long ne = tab.n_edges, nb = ne - 1;
+    const double* edge = tab.edge;
+    const double2* inv_h0 = tab.inv_h0;
+    const double* bin = tab.bin;
+    if constexpr (STAGE) {
+        double* s_edge = reinterpret_cast<double*>(relbin_smem);
+        double2* s_ih = reinterpret_cast<double2*>(s_edge + 6 * ne);
+        double* s_bin = reinterpret_cast<double*>(s_ih + (size_t)NIFO * ne);
+        for (long k = threadIdx.x; k < 6 * ne; k += blockDim.x) s_edge[k] = tab.edge[k];
+        for (long k = threadIdx.x; k < (long)NIFO * ne; k += blockDim.x) s_ih[k] = tab.inv_h0[k];
+        for (long k = threadIdx.x; k < (long)NIFO * nb * 8; k += blockDim.x) s_bin[k] = tab.bin[k];
+        __syncthreads();
+        edge = s_edge;
+        inv_h0 = s_ih;
+        bin = s_bin;
+    }
     const long w = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_walkers) return;
-    const int nifo = cfg.n_ifo;
-    const long ne = tab.n_edges, nb = ne - 1;
     WalkerCoefReg r;
     load_coef(r, coef, stride, w);
     const double amp = coef[C_AMP * stride + w];
     const bool valid = coef[C_VALID * stride + w] != 0.0;
-    double tau[BJ_MAX_IFO], cr[BJ_MAX_IFO], ci[BJ_MAX_IFO];
-    for (int i = 0; i < nifo; ++i) {
+    double tau[NIFO], cr[NIFO], ci[NIFO];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) {
         tau[i] = coef[(C_TAU0 + i) * stride + w];
         cr[i] = coef[(C_CR0 + i) * stride + w];
         ci[i] = coef[(C_CI0 + i) * stride + w];
     }
-    double pr[BJ_MAX_IFO], pi_[BJ_MAX_IFO];   // r(f) = h / h0 at the previous edge
-    double dre[BJ_MAX_IFO] = {0, 0, 0}, dim[BJ_MAX_IFO] = {0, 0, 0}, hh[BJ_MAX_IFO] = {0, 0, 0};
+    double pr[NIFO], pi_[NIFO];   // r(f) = h / h0 at the previous edge
+    double dre[NIFO], dim[NIFO], hh[NIFO];
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) { pr[i] = pi_[i] = dre[i] = dim[i] = hh[i] = 0.0; }
+#pragma unroll 1
     for (long k = 0; k < ne; ++k) {
-        const double* ed = tab.edge + 6 * k;
+        const double* ed = edge + 6 * k;
         const double u = ed[0], L = ed[1], w5 = ed[2], g = ed[3], f = ed[4];
         double turns, Q;
-        eval_point(r, u, L, w5, turns, Q);
+        eval_point_m<MODEL>(r, u, L, w5, turns, Q);
         const double a = amp * Q * g;
-        for (int i = 0; i < nifo; ++i) {
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) {
             // h_det = C_i a exp(-2 pi i [turns - f T / 2 + f tau_i])
             double c, sn;
-            cis_neg_turns(turns + f * tau[i] - 0.5 * f * tab.seglen, c, sn);
+            cis_neg_turns_fast(turns + f * tau[i] - 0.5 * f * tab.seglen, c, sn);
             const double hr = a * (cr[i] * c - ci[i] * sn);
             const double hi = a * (cr[i] * sn + ci[i] * c);
-            const double2 ih = tab.inv_h0[(size_t)i * ne + k];
+            const double2 ih = inv_h0[(size_t)i * ne + k];
             const double rr = hr * ih.x - hi * ih.y;
             const double ri = hr * ih.y + hi * ih.x;
             if (k > 0) {
-                const double* bn = tab.bin + ((size_t)i * nb + (k - 1)) * 8;
+                const double* bn = bin + ((size_t)i * nb + (k - 1)) * 8;
                 // binning.py:301-304
                 const double r0r = 0.5 * (pr[i] + rr), r0i = 0.5 * (pi_[i] + ri);
                 const double r1r = (rr - pr[i]) * bn[6], r1i = (ri - pi_[i]) * bn[6];
@@ -308,11 +365,12 @@ __global__ void __launch_bounds__(128) relbin_kernel(DeviceConfig cfg, RelbinDev
         }
     }
     double dh_re = 0.0, dh_im = 0.0, hh_tot = 0.0;
-    for (int i = 0; i < nifo; ++i) {
+#pragma unroll
+    for (int i = 0; i < NIFO; ++i) {
         if (sums) {
-            sums[(w * nifo + i) * 3 + 0] = dre[i];
-            sums[(w * nifo + i) * 3 + 1] = dim[i];
-            sums[(w * nifo + i) * 3 + 2] = hh[i];
+            sums[(w * NIFO + i) * 3 + 0] = dre[i];
+            sums[(w * NIFO + i) * 3 + 1] = dim[i];
+            sums[(w * NIFO + i) * 3 + 2] = hh[i];
         }
         dh_re += dre[i]; dh_im += dim[i]; hh_tot += hh[i];
     }
@@ -322,13 +380,43 @@ __global__ void __launch_bounds__(128) relbin_kernel(DeviceConfig cfg, RelbinDev
     logl[w] = v;
 }
 
-static inline int launch_relbin(const DeviceConfig& cfg, const RelbinDevice& tab, const double* coef, long stride,
-                                long n_walkers, double* logl, double* sums, cudaStream_t st, int* info) {
+template <int NIFO, int MODEL>
+static inline int launch_relbin_n(const DeviceConfig& cfg, const RelbinDevice& tab, const double* coef, long stride,
+                                  long n_walkers, double* logl, double* sums, cudaStream_t st, int* info) {
     const unsigned nblk = (unsigned)((n_walkers + 127) / 128);
-    relbin_kernel<<<nblk, 128, 0, st>>>(cfg, tab, coef, stride, n_walkers, logl, sums);
-    info[0] = (int)nblk; info[1] = 1; info[2] = 128; info[3] = 0;
+    const long ne = tab.n_edges, nb = ne - 1;
+    const size_t smem = (size_t)(6 * ne + 2 * NIFO * ne + 8 * NIFO * nb) * sizeof(double);
+    if (smem <= 100 * 1024) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(relbin_kernel<NIFO, MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        relbin_kernel<NIFO, MODEL, true><<<nblk, 128, smem, st>>>(cfg, tab, coef, stride, n_walkers, logl, sums);
+        info[3] = (int)smem;
+    } else {
+        relbin_kernel<NIFO, MODEL, false><<<nblk, 128, 0, st>>>(cfg, tab, coef, stride, n_walkers, logl, sums);
+        info[3] = 0;
+    }
+    info[0] = (int)nblk; info[1] = 1; info[2] = 128;
     info[4] = (int)tab.n_edges; info[5] = 0; info[6] = 0; info[7] = 200;
     return (int)cudaGetLastError();
+}
+
+template <int NIFO>
+static inline int launch_relbin_i(const DeviceConfig& cfg, const RelbinDevice& tab, const double* coef, long stride,
+                                  long n_walkers, double* logl, double* sums, cudaStream_t st, int* info) {
+    if (cfg.approx == BJ_APPROX_TAYLORF2_35PN)
+        return launch_relbin_n<NIFO, MODEL_35>(cfg, tab, coef, stride, n_walkers, logl, sums, st, info);
+    return launch_relbin_n<NIFO, MODEL_GENERIC>(cfg, tab, coef, stride, n_walkers, logl, sums, st, info);
+}
+
+static inline int launch_relbin(const DeviceConfig& cfg, const RelbinDevice& tab, const double* coef, long stride,
+                                long n_walkers, double* logl, double* sums, cudaStream_t st, int* info) {
+    switch (cfg.n_ifo) {
+        case 1: return launch_relbin_i<1>(cfg, tab, coef, stride, n_walkers, logl, sums, st, info);
+        case 2: return launch_relbin_i<2>(cfg, tab, coef, stride, n_walkers, logl, sums, st, info);
+        default: return launch_relbin_i<3>(cfg, tab, coef, stride, n_walkers, logl, sums, st, info);
+    }
 }
 
 }  // namespace bj

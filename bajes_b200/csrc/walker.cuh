@@ -189,11 +189,14 @@ __device__ __forceinline__ double quadrupole_yy(double lam) {
     return exp(0.194 + 0.0936 * ll + 0.0474 * ll2 - 4.21e-3 * ll2 * ll + 1.23e-4 * ll2 * ll2);
 }
 
-// Fills out[C_NUM].  `x` is the walker's row.
-__device__ inline void walker_coefficients(const DeviceConfig& cfg, const ParamMapDev& pm,
-                                           const double* __restrict__ x, double* out) {
-#pragma unroll 1
-    for (int i = 0; i < C_NUM; ++i) out[i] = 0.0;
+// The prologue in three parts, so that one walker can be spread over a few threads (kernels.cuh: prologue_kernel):
+//   walker_intrinsic   phase / amplitude coefficients of the source               -> out[0 .. C_TAU0), C_AMP, C_COSI
+//   walker_detector    antenna pattern, delay, rotation constants of ONE detector -> out[C_TAU0 + i], C_CR0/CI0/FP0/FC0 + i,
+//                                                                                    C_ROT0 + 10 (i - 1) ..
+//   walker_validity    log_like.py:121-129 and the wide-phase flag                -> out[C_VALID]
+// `x` is the walker's row.  Returns whether every intrinsic quantity is finite and the waveform is not identically zero.
+__device__ inline bool walker_intrinsic(const DeviceConfig& cfg, const ParamMapDev& pm,
+                                        const double* __restrict__ x, double* out) {
 
     // ---- parameter derivations (waveform.py:334-377) --------------------------------------
     const double q = get(pm, x, BJ_P_Q);
@@ -224,10 +227,7 @@ __device__ inline void walker_coefficients(const DeviceConfig& cfg, const ParamM
     if (has(pm, BJ_P_COS_IOTA)) iota = acos(get(pm, x, BJ_P_COS_IOTA));
     else                        iota = get(pm, x, BJ_P_IOTA);
     const double cosi = cos(iota);
-    const double ra = get(pm, x, BJ_P_RA), dec = get(pm, x, BJ_P_DEC), psi = get(pm, x, BJ_P_PSI);
-    const double tshift = get(pm, x, BJ_P_TIME_SHIFT);
     const double phiref = get(pm, x, BJ_P_PHI_REF);
-    const double tgps = get(pm, x, BJ_P_T_GPS);
 
     // ---- mass / spin combinations (taylorf2.py:176-210,380) -------------------------------
     const double eta = q / ((1.0 + q) * (1.0 + q));
@@ -438,51 +438,73 @@ __device__ inline void walker_coefficients(const DeviceConfig& cfg, const ParamM
         out[C_AMP] = kPre * (pow(fabs(mc), 5.0 / 6.0) / dist / pow(kPi, 2.0 / 3.0) * sqrt(5.0 / 24.0));
     }
 
-    // ---- detector projection (detector.py:394-418, taylorf2.py:427-432) ----------------------
     const double incl_plus = (1.0 + cosi * cosi) * 0.5;
     out[C_COSI] = cosi;
-    const double t_arr = tgps + tshift;
     bool ok = true;
-    for (int i = 0; i < cfg.n_ifo; ++i) {
-        double fp, fc;
-        antenna_pattern(cfg.det[i], ra, dec, psi, t_arr, fp, fc);
-        const double tau = geocentric_delay(cfg.det[i], ra, dec, t_arr) + tshift;
-        out[C_TAU0 + i] = tau;
-        out[C_CR0 + i] = fp * incl_plus;     // C_i = F+ (1+cos^2 i)/2 - i Fx cos i
-        out[C_CI0 + i] = -fc * cosi;
-        out[C_FP0 + i] = fp;
-        out[C_FC0 + i] = fc;
-        ok = ok && isfinite(tau) && isfinite(fp) && isfinite(fc);
-    }
+    for (int j = 0; j < C_TAU0; ++j) ok = ok && isfinite(out[j]);
+    ok = ok && isfinite(out[C_AMP]);
+    const double hp_scale = out[C_AMP] * incl_plus;
+    ok = ok && isfinite(hp_scale) && (hp_scale != 0.0) && isfinite(out[C_AMP] * cosi);
+    // quirk (taylorf2.py:252): the 5.5PN phase takes (pi M f gt)^(1/3) WITHOUT abs -> NaN for M < 0
+    if (order55 && !(mtot > 0.0)) ok = false;
+    return ok;
+}
+
+// geocentric arrival-time offset of detector i: delay + time_shift
+__device__ __forceinline__ double walker_tau(const DeviceConfig& cfg, const ParamMapDev& pm, const double* __restrict__ x,
+                                             int i) {
+    const double tshift = get(pm, x, BJ_P_TIME_SHIFT);
+    return geocentric_delay(cfg.det[i], get(pm, x, BJ_P_RA), get(pm, x, BJ_P_DEC), get(pm, x, BJ_P_T_GPS) + tshift) + tshift;
+}
+
+// detector projection (detector.py:394-418, taylorf2.py:427-432) of detector i; o5 = {tau, Re C, Im C, F+, Fx},
+// rot10 (i >= 1, uniform grids) = the rotation constants against detector 0.  Returns finiteness.
+__device__ inline bool walker_detector(const DeviceConfig& cfg, const ParamMapDev& pm, const double* __restrict__ x, int i,
+                                       double* o5, double* rot10) {
+    double iota;
+    if (has(pm, BJ_P_COS_IOTA)) iota = acos(get(pm, x, BJ_P_COS_IOTA));
+    else                        iota = get(pm, x, BJ_P_IOTA);
+    const double cosi = cos(iota);
+    const double incl_plus = (1.0 + cosi * cosi) * 0.5;
+    const double ra = get(pm, x, BJ_P_RA), dec = get(pm, x, BJ_P_DEC), psi = get(pm, x, BJ_P_PSI);
+    const double t_arr = get(pm, x, BJ_P_T_GPS) + get(pm, x, BJ_P_TIME_SHIFT);
+    double fp, fc;
+    antenna_pattern(cfg.det[i], ra, dec, psi, t_arr, fp, fc);
+    const double tau = walker_tau(cfg, pm, x, i);
+    o5[0] = tau;
+    o5[1] = fp * incl_plus;      // C_i = F+ (1+cos^2 i)/2 - i Fx cos i
+    o5[2] = -fc * cosi;
+    o5[3] = fp;
+    o5[4] = fc;
     // rotation constants: the phase of detector i differs from detector 0's by 2 pi f (tau_i - tau_0) only
-    if (cfg.grid_df > 0.0) {
-        for (int i = 1; i < cfg.n_ifo; ++i) {
-            const double turns_per_bin = cfg.grid_df * (out[C_TAU0 + i] - out[C_TAU0]);
-            double* o = out + C_ROT0 + kRotSlots * (i - 1);
+    if (i >= 1 && rot10 != nullptr) {
+        if (cfg.grid_df > 0.0) {
+            const double turns_per_bin = cfg.grid_df * (tau - walker_tau(cfg, pm, x, 0));
             const double offs[4] = {3.5, 4.5, 11.5, 12.5};
 #pragma unroll 1
             for (int a = 0; a < 4; ++a) {
                 double sh, ch, sn, cs;
                 sincospi(offs[a] * turns_per_bin, &sh, &ch);          // half angle: cos x - 1 = -2 sin^2(x / 2)
                 sincospi(2.0 * offs[a] * turns_per_bin, &sn, &cs);
-                o[a] = -2.0 * sh * sh;
-                o[4 + a] = sn;
+                rot10[a] = -2.0 * sh * sh;
+                rot10[4 + a] = sn;
             }
             double sn, cs;
             sincospi(64.0 * turns_per_bin, &sn, &cs);
-            o[8] = cs;
-            o[9] = -sn;
+            rot10[8] = cs;
+            rot10[9] = -sn;
+        } else {
+#pragma unroll 1
+            for (int a = 0; a < kRotSlots; ++a) rot10[a] = 0.0;
         }
     }
+    return isfinite(tau) && isfinite(fp) && isfinite(fc);
+}
 
-    // ---- validity (log_like.py:121-129): NaN/Inf anywhere in hp/hc, or hp identically zero ---
-    for (int j = 0; j < C_AMP; ++j) ok = ok && isfinite(out[j]);
-    const double hp_scale = out[C_AMP] * incl_plus;
-    ok = ok && isfinite(hp_scale) && (hp_scale != 0.0) && isfinite(out[C_AMP] * cosi);
-    // quirk (taylorf2.py:252): the 5.5PN phase takes (pi M f gt)^(1/3) WITHOUT abs -> NaN for M < 0
-    if (order55 && !(mtot > 0.0)) ok = false;
-    // The fast kernel reads the binary angle from the low word of (turns + 1.5 * 2^20), exact while |turns| < 2^19.
-    // Every term of the phase is monotone in f, so its magnitude is bounded by the larger of the two band ends.
+// C_VALID: 0 = -inf (log_like.py:121-129: NaN/Inf anywhere in hp/hc, or hp identically zero), 1 = evaluate, 2 = evaluate
+// with the wide-phase path.  The fast kernel reads the binary angle from the low word of (turns + 1.5 * 2^20), exact while
+// |turns| < 2^19; every term of the phase is monotone in f, so its magnitude is bounded by the larger of the two band ends.
+__device__ inline double walker_validity(const DeviceConfig& cfg, const double* out, bool ok, double tmax) {
     double wide = 0.0;
     if (ok && cfg.f_hi > 0.0) {
         double bound = 0.0;
@@ -500,12 +522,30 @@ __device__ inline void walker_coefficients(const DeviceConfig& cfg, const ParamM
             }
             bound = fmax(bound, w5 * sa + L * sb + L * L * fabs(out[C_C8]) * u * u * u);
         }
-        double tmax = 0.0;
-        for (int i = 0; i < cfg.n_ifo; ++i) tmax = fmax(tmax, fabs(out[C_TAU0 + i]));
         bound += fabs(out[C_K0]) + cfg.f_hi * tmax;
         if (!(bound < 500000.0)) wide = 1.0;
     }
-    out[C_VALID] = ok ? 1.0 + wide : 0.0;
+    return ok ? 1.0 + wide : 0.0;
+}
+
+// one thread does it all (single-point entry points); fills out[C_NUM]
+__device__ inline void walker_coefficients(const DeviceConfig& cfg, const ParamMapDev& pm,
+                                           const double* __restrict__ x, double* out) {
+#pragma unroll 1
+    for (int i = 0; i < C_NUM; ++i) out[i] = 0.0;
+    bool ok = walker_intrinsic(cfg, pm, x, out);
+    double tmax = 0.0;
+    for (int i = 0; i < cfg.n_ifo; ++i) {
+        double o5[5];
+        ok = walker_detector(cfg, pm, x, i, o5, i >= 1 ? out + C_ROT0 + kRotSlots * (i - 1) : nullptr) && ok;
+        out[C_TAU0 + i] = o5[0];
+        out[C_CR0 + i] = o5[1];
+        out[C_CI0 + i] = o5[2];
+        out[C_FP0 + i] = o5[3];
+        out[C_FC0 + i] = o5[4];
+        tmax = fmax(tmax, fabs(o5[0]));
+    }
+    out[C_VALID] = walker_validity(cfg, out, ok, tmax);
 }
 
 }  // namespace bj

@@ -195,20 +195,13 @@ class ShardedEvaluator:
         self.hdr[:, 0] = self.seq                        # published last
         # X into the sampler rank's HBM, slice by slice (the other ranks' first, each followed by its flag), staged through
         # pinned memory in pieces so that the host copy of one piece overlaps the DMA of the previous one
-        pinned_src = X if (isinstance(X, torch.Tensor) and X.is_pinned()) else None
-        flat = None if pinned_src is not None else X.reshape(-1)
-        stage = self.x_pin.numpy()
-        piece = 1 << 18                                   # doubles per piece (2 MiB)
-        for r in [q for q in range(self.world) if q != self.src] + [self.src]:
-            a, b = lo[r] * self.ndim, hi[r] * self.ndim
-            if pinned_src is not None:
-                self.x_all[a:b].copy_(pinned_src.view(-1)[a:b], non_blocking=True)
-            else:
-                for p0 in range(a, b, piece):
-                    p1 = min(b, p0 + piece)
-                    stage[p0:p1] = flat[p0:p1]
-                    self.x_all[p0:p1].copy_(self.x_pin[p0:p1], non_blocking=True)
-            self.peer.signal(X_FLAG0 + r, self.seq, stream.cuda_stream)
+        pinned = isinstance(X, torch.Tensor)              # evaluate() only lets pinned float64 tensors through as such
+        src_ptr = X.data_ptr() if pinned else X.ctypes.data
+        order = [q for q in range(self.world) if q != self.src] + [self.src]
+        from .engine import PEER_HEADER_BYTES
+        self.peer.scatter(PEER_HEADER_BYTES + 8 * self.capacity, src_ptr, 0 if pinned else self.x_pin.data_ptr(),
+                          [8 * lo[r] * self.ndim for r in order], [8 * hi[r] * self.ndim for r in order],
+                          [X_FLAG0 + r for r in order], self.seq, stream.cuda_stream)
         self._peer_local(hi[self.src] - lo[self.src], lo[self.src])
         others = [r for r in range(self.world) if r != self.src]
         first, last = min(others), max(others)

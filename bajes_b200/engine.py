@@ -129,6 +129,8 @@ EXPORTS = {
     "bj_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "bj_peer_close": (C.c_int, [C.c_int, C.c_void_p, C.c_int]),
     "bj_peer_signal": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "bj_peer_scatter": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int64, C.c_void_p]),
     "bj_peer_wait": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_void_p]),
     "bj_measure_peak": (C.c_int, [C.c_int, C.c_int, _DP]),
     "bj_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -226,6 +228,19 @@ class PeerBuffer:
         lib = load_library()
         _check(lib, lib.bj_peer_signal(self.device, C.c_void_p(self.base), slot, value, C.c_void_p(stream or None)),
                "bj_peer_signal")
+
+    def scatter(self, dst_offset_bytes: int, src_ptr: int, stage_ptr: int, begins, ends, slots, value: int,
+                stream: int = 0) -> None:
+        """byte ranges [begins[p], ends[p]) of the host block at src_ptr -> this buffer (+ dst_offset_bytes), each
+        followed by its flag; stage_ptr = 0 when the source is pinned (bj_peer_scatter)"""
+        lib = load_library()
+        b = np.ascontiguousarray(begins, dtype=np.int64)
+        e = np.ascontiguousarray(ends, dtype=np.int64)
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        _check(lib, lib.bj_peer_scatter(self.device, C.c_void_p(self.base), dst_offset_bytes, C.c_void_p(src_ptr),
+                                        C.c_void_p(stage_ptr or None), len(b), b.ctypes.data_as(C.POINTER(C.c_int64)),
+                                        e.ctypes.data_as(C.POINTER(C.c_int64)), sl.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        value, C.c_void_p(stream or None)), "bj_peer_scatter")
 
     def wait(self, first: int, n: int, value: int, timeout_ms: float = 5000.0, stream: int = 0) -> None:
         lib = load_library()

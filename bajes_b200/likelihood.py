@@ -73,8 +73,11 @@ class GWLikelihood(Likelihood):
                                       % (_engine.BJ_MAX_SPCAL, _engine.BJ_MAX_WEIGHTS))
         self.spcal_freqs = None if not nspcal else np.asarray(spcal_freqs, dtype=float)
         self.len_weights = None if not nweights else np.asarray(len_weights, dtype=np.int64)
-        if len(self.ifos) > _engine.BJ_MAX_IFO:
-            raise NotImplementedError("more than %d detectors in one fused pass" % _engine.BJ_MAX_IFO)
+        # networks of more than BJ_MAX_IFO detectors (the reference loops over any number, log_like.py:57-96: ET1-3 + CE
+        # ...) are evaluated in passes of at most BJ_MAX_IFO detectors each; <d|h> and <h|h> are additive over detectors
+        self._groups = [self.ifos[k:k + _engine.BJ_MAX_IFO] for k in range(0, len(self.ifos), _engine.BJ_MAX_IFO)]
+        if len(self._groups) > 1 and self.marg_time_shift:
+            raise NotImplementedError("time-shift marginalisation with more than %d detectors" % _engine.BJ_MAX_IFO)
 
         # consistency checks of log_like.py:57-96
         n_freqs = f_min_check = f_max_check = None
@@ -113,47 +116,62 @@ class GWLikelihood(Likelihood):
         self._build_engine()
 
     # ---- engine life cycle ------------------------------------------------------------------------
-    def _config(self):
+    def _config(self, ifos=None):
+        ifos = self.ifos if ifos is None else ifos
         dd_sum = 0.0
-        for ifo in self.ifos:
+        for ifo in ifos:
             dd_sum += np.real(self.dets[ifo]._dd)
-        return _engine.make_config(self.device, self.approx, len(self.ifos), self.seglen,
-                                   [self.dets[i].constants() for i in self.ifos],
-                                   marg_phi_ref=self.marg_phi_ref, sincos=self.sincos,
-                                   dd_sum=dd_sum, logZ_noise=self.logZ_noise)
+        single = len(self._groups) == 1
+        return _engine.make_config(self.device, self.approx, len(ifos), self.seglen,
+                                   [self.dets[i].constants() for i in ifos],
+                                   marg_phi_ref=self.marg_phi_ref and single, sincos=self.sincos,
+                                   dd_sum=dd_sum, logZ_noise=self.logZ_noise if single else -0.5 * dd_sum)
+
+    def _build_one(self, ifos):
+        cfg = self._config(ifos)
+        if self.roq is None:
+            d0 = self.dets[ifos[0]]
+            return _engine.Engine.fullgrid(cfg, d0.freqs,
+                                           [self.dets[i].data for i in ifos],
+                                           [self.dets[i].psd for i in ifos],
+                                           spcal_freqs=self.spcal_freqs, len_weights=self.len_weights,
+                                           marg_time_shift=self.marg_time_shift, n_full=self.Nfr,
+                                           band_offset=self._band_offset)
+        from .roq import spline_tables
+        knots, coefs, tc_min, tc_max = [], [], None, None
+        for ifo in ifos:
+            t, c, lo, hi = spline_tables(self.roq[ifo]["omega_weights_interp"])
+            knots.append(t)
+            coefs.append(c)
+            tc_min = lo if tc_min is None else max(tc_min, lo)
+            tc_max = hi if tc_max is None else min(tc_max, hi)
+        return _engine.Engine.roq(cfg, self.roq["freqs_join"], self.roq["mask_omega"],
+                                  self.roq["mask_psi"], knots, coefs,
+                                  [self.roq[i]["psi_weights"] for i in ifos], tc_min, tc_max)
 
     def _build_engine(self):
-        cfg = self._config()
-        if self.roq is None:
-            d0 = self.dets[self.ifos[0]]
-            self._engine = _engine.Engine.fullgrid(cfg, d0.freqs,
-                                                   [self.dets[i].data for i in self.ifos],
-                                                   [self.dets[i].psd for i in self.ifos],
-                                                   spcal_freqs=self.spcal_freqs, len_weights=self.len_weights,
-                                                   marg_time_shift=self.marg_time_shift, n_full=self.Nfr,
-                                                   band_offset=self._band_offset)
-        else:
-            from .roq import spline_tables
-            knots, coefs, tc_min, tc_max = [], [], None, None
-            for ifo in self.ifos:
-                t, c, lo, hi = spline_tables(self.roq[ifo]["omega_weights_interp"])
-                knots.append(t)
-                coefs.append(c)
-                tc_min = lo if tc_min is None else max(tc_min, lo)
-                tc_max = hi if tc_max is None else min(tc_max, hi)
-            self._engine = _engine.Engine.roq(cfg, self.roq["freqs_join"], self.roq["mask_omega"],
-                                              self.roq["mask_psi"], knots, coefs,
-                                              [self.roq[i]["psi_weights"] for i in self.ifos], tc_min, tc_max)
+        self._engines = [self._build_one(g) for g in self._groups]
+        self._engine = self._engines[0]
+
+    @property
+    def engines(self):
+        if self._engine is None:        # after unpickling: re-upload lazily (SURVEY.md section 5)
+            self._build_engine()
+        return self._engines
 
     @property
     def engine(self):
-        if self._engine is None:        # after unpickling: re-upload lazily (SURVEY.md section 5)
-            self._build_engine()
-        return self._engine
+        """The CUDA context of a network of at most BJ_MAX_IFO detectors (larger networks own several: ``engines``)."""
+        engines = self.engines
+        if len(engines) > 1:
+            raise NotImplementedError("this network is evaluated in %d passes: use log_like_batch / log_like / "
+                                      "inner_products, or the per-pass contexts in .engines" % len(engines))
+        return engines[0]
 
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_engine"] = None         # device handles never travel through pickle
+        state["_engines"] = None
         return state
 
     def __setstate__(self, state):
@@ -175,16 +193,67 @@ class GWLikelihood(Likelihood):
         X = np.ascontiguousarray(X, dtype=np.float64)
         if X.ndim != 2 or X.shape[1] != len(names):
             raise ValueError("X must be [n_points, %d]" % len(names))
-        return self.engine.loglike(X, self.param_map(names, const))
+        if len(self._groups) == 1:
+            return self.engine.loglike(X, self.param_map(names, const))
+        return self._multi_pass(X, [_engine.ParamMap(names, const, ifos=g, nspcal=self.nspcal, nweights=self.nweights)
+                                    for g in self._groups])[0]
+
+    def _multi_pass(self, X, pmaps):
+        """Networks of more than BJ_MAX_IFO detectors: one pass per group of detectors on the same device-resident
+        batch; per-pass logL (without phase marginalisation) and per-detector <d|h>, <h|h> are combined as
+        log_like.py:158-181 does.  Returns (logL [W], parts [W, n_ifo, 3])."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        W = X.shape[0]
+        parts_all = np.empty((W, len(self.ifos), 3))
+        if W == 0:
+            return np.empty(0), parts_all
+        xd = torch.from_numpy(X).to(dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        outs, parts = [], []
+        for g, eng, pm in zip(self._groups, self.engines, pmaps):
+            o = torch.empty(W, dtype=torch.float64, device=dev)
+            p = torch.empty((W, len(g), 3), dtype=torch.float64, device=dev)
+            eng.loglike_device(xd.data_ptr(), W, X.shape[1], pm, o.data_ptr(), p.data_ptr(), st)
+            outs.append(o)
+            parts.append(p)
+        logl = torch.stack(outs).sum(dim=0).cpu().numpy()
+        k = 0
+        for g, p in zip(self._groups, parts):
+            parts_all[:, k:k + len(g)] = p.cpu().numpy()
+            k += len(g)
+        if self.marg_phi_ref:
+            from scipy.special import i0e
+            dh = parts_all[:, :, 0].sum(axis=1) + 1j * parts_all[:, :, 1].sum(axis=1)
+            with np.errstate(invalid="ignore"):
+                a = np.abs(dh)
+                logl = logl - np.real(dh) + (np.log(i0e(a)) + a)            # log_like.py:176-177
+            logl = np.where(np.isnan(logl), -np.inf, logl)
+        return logl, parts_all
 
     def log_like(self, params):
         """Reference per-point contract (log_like.py:107-183): dict -> float."""
+        if len(self._groups) > 1:
+            x, pmaps = self._point_maps(params)
+            return float(self._multi_pass(x.reshape(1, -1), pmaps)[0][0])
         pmap, x = self._point_map(params)
         return float(self.engine.loglike(x.reshape(1, -1), pmap)[0])
+
+    def _point_maps(self, params):
+        """one parameter row + a map per pass (the extras of a pass are looked up under its own detector names)"""
+        sub = _physical_subset(params)
+        names = [n for n in _engine.PARAM_SLOTS if n in sub]
+        names += [n for n in sub if n.startswith(_engine.ParamMap.EXTRA_PREFIXES) and n != "weights"]
+        x = np.array([float(sub[n]) for n in names], dtype=np.float64)
+        return x, [_engine.ParamMap(names, {}, ifos=g, nspcal=self.nspcal, nweights=self.nweights) for g in self._groups]
 
     def _parts(self, params):
         """per-detector Re<d|h>, Im<d|h>, <h|h> of one point via the device entry."""
         import torch
+        if len(self._groups) > 1:
+            x, pmaps = self._point_maps(params)
+            logl, parts = self._multi_pass(x.reshape(1, -1), pmaps)
+            return parts[0], float(logl[0])
         pmap, x = self._point_map(params)
         dev = torch.device("cuda", self.device)
         xd = torch.from_numpy(x.reshape(1, -1)).to(dev)
@@ -206,8 +275,11 @@ class GWLikelihood(Likelihood):
             raise NotImplementedError("projected strain on the full axis is not defined for an ROQ likelihood")
         sub = _physical_subset(params)
         pmap, x = _engine.ParamMap.from_dict(sub)
-        h = self.engine.project_waveform(x, pmap)
-        return {ifo: h[i] for i, ifo in enumerate(self.ifos)}
+        out = {}
+        for g, eng in zip(self._groups, self.engines):
+            h = eng.project_waveform(x, pmap)
+            out.update({ifo: h[i] for i, ifo in enumerate(g)})
+        return out
 
 
 def _physical_subset(params):

@@ -244,6 +244,13 @@ int bj_peer_create(int device, int64_t capacity_doubles, void** base_dev, unsign
 int bj_peer_open(int device, const unsigned char* handle64, void** base_dev);
 int bj_peer_close(int device, void* base_dev, int opened_from_handle);
 int bj_peer_signal(int device, void* base_dev, int32_t slot, int64_t value, void* stream);
+/* Sampler rank: copy n_parts byte ranges [part_begin, part_end) of a host block to base_dev + dst_offset (same offsets),
+ * each followed by a release of `value` in flags[part_flag_slot[p]] -- one call, in the given order, so that the rank
+ * whose rows landed can start while the next rows travel.  src_host pageable: pass a pinned staging block of the same
+ * size (pieces of 2 MiB are staged while the previous piece is in flight); src_host pinned: stage_pinned = NULL. */
+int bj_peer_scatter(int device, void* base_dev, int64_t dst_offset_bytes, const void* src_host, void* stage_pinned,
+                    int32_t n_parts, const int64_t* part_begin, const int64_t* part_end,
+                    const int32_t* part_flag_slot, int64_t value, void* stream);
 int bj_peer_wait(int device, void* base_dev, int32_t first_slot, int32_t n_slots, int64_t value, double timeout_ms,
                  void* stream);
 

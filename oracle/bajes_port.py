@@ -488,6 +488,12 @@ SITES = {
     "L1": (0.53342313506, -1.58430937078, -6.574, 3.4508039105, 5.0216002373, 0.0, 0.0),
     "V1": (0.76151183984, 0.18333805213, 51.884, 1.2316334746, 2.8024298014, 0.0, 0.0),
     "K1": (0.6355068497, 2.396441015, 414.181, 0.5166831721, 2.0874762035, 0.0, 0.0),
+    "G1": (0.91184982752, 0.17116780435, 114.425, 2.02358884, 0.377195322, 0.0, 0.0),
+    "I1": (0.2484185302005, 1.334013324941, 0.0, 2.1991043855, 3.7699007123, 0.0, 0.0),
+    "ET1": (0.76151183984, 0.18333805213, 51.884, 0.33916285222, 5.57515060820, 0.0, 0.0),
+    "ET2": (0.76299307990, 0.18405858870, 59.735, 4.52795305701, 3.48075550581, 0.0, 0.0),
+    "ET3": (0.76270463257, 0.18192996730, 59.727, 2.43355795462, 1.38636040342, 0.0, 0.0),
+    "CE": (0.81079526383, -2.08405676917, 142.554, 2.1991043855, 3.7699007123, -6.195e-4, 1.25e-5),
 }
 
 

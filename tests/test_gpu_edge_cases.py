@@ -193,3 +193,41 @@ def test_frequency_split_partial_sums_recombine():
     from bajes_b200.dist import FrequencySplitEvaluator
     ev = FrequencySplitEvaluator(like, names, const)
     assert np.array_equal(ev.evaluate(X), whole) or np.all(np.abs(ev.evaluate(X) - whole) <= 1e-9 * (np.abs(whole) + 1))
+
+
+# ------------------------------------------------------------------------------------------------------
+# networks of more than three detectors (the reference loops over any number: log_like.py:57-96; ET1-3, K1, CE in
+# detector.py:26-29): evaluated in passes of three
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("marg", [False, True])
+@pytest.mark.parametrize("ifos", [["H1", "L1", "V1", "K1"], ["H1", "L1", "V1", "K1", "ET1", "ET2", "ET3"]])
+def test_networks_of_more_than_three_detectors(ifos, marg):
+    from types import SimpleNamespace
+    from conftest import design_asd_any, product_network_from_port
+    cfg = dict(syn.CONFIGS["C2_small"])
+    cfg.update(ifos=list(ifos), seglen=8.0, seed=5105)
+    pc = harness.port_classes()
+    cl = SimpleNamespace(**{**vars(pc), "design_asd": design_asd_any})
+    net = syn.build_network(cfg, cl)
+    port_like = harness.port_likelihood(cfg, marg_phi_ref=marg, net=net)
+    pifos, datas, dets, noises, f = product_network_from_port(cfg, net)
+    like = GWLikelihood(pifos, datas, dets, noises, f, cfg["srate"], cfg["seglen"], cfg["approx"], marg_phi_ref=marg)
+    assert len(like.engines) == -(-len(ifos) // 3)
+    Xa, names = syn.draw_walkers(cfg, 48, 61, "narrow")
+    Xb, _ = syn.draw_walkers(cfg, 16, 62, "wide")
+    X = np.concatenate([Xa, Xb])
+    X[-1, names.index("distance")] = np.inf
+    const = syn.constants(cfg)
+    with np.errstate(all="ignore"):
+        ref = harness.eval_batch(port_like, X, names, const)
+    got = like.log_like_batch(X, names, const)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin) and np.all(np.isneginf(got[~fin]))
+    assert np.all(np.abs(got[fin] - ref[fin]) <= harness.tolerance(ref[fin]))
+    p = {k: float(v) for k, v in zip(names, X[3])}
+    p.update(const)
+    assert like.log_like(dict(p)) == got[3]
+    ip = like.inner_products(dict(p))
+    assert sorted(ip) == sorted(ifos)
+    h = like.project_fdwave(dict(p))
+    assert sorted(h) == sorted(ifos) and len(h[ifos[-1]]) == len(h[ifos[0]]) == like.engines[0].n_bins

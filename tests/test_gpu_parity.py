@@ -536,3 +536,40 @@ def test_data_configurations_vs_fp64_kernel(kind, upd):
     slow = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], sincos="fp64").log_like_batch(X, names, const)
     fast = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"]).log_like_batch(X, names, const)
     _check(fast, slow, "%s %s, 20 011 walkers vs FP64 kernel" % (kind, upd))
+
+
+# ------------------------------------------------------------------------------------------------------
+# C5 / N1: the call trace of the UNMODIFIED reference ptmcmc sampler (recorded in the build container with the oracle
+# behind the adapters, scripts/make_ptmcmc_trace.py) replayed on the GPU likelihood through the same adapters
+# ------------------------------------------------------------------------------------------------------
+def test_reference_ptmcmc_call_trace_on_the_gpu():
+    """Every batch bajes' parallel-tempered sampler sent through pool.map(posterior.log_likeprior, points)
+    (ptmcmc.py:272-281; 2 temperatures x 16 walkers x 12 iterations on the 16 s BNS injection) is sent through
+    BatchedPool -> Posterior.log_likeprior_batch -> GWLikelihood.log_like_batch on the GPU: same number of calls, same
+    batch shapes, and every log-likelihood the sampler saw reproduced within the tolerance."""
+    from bajes_b200.likelihood import Posterior
+    from bajes_b200.pool import BatchedPool
+    cfg = syn.CONFIGS["C2_small"]
+    tr = load_golden("ptmcmc_trace.npz")
+    like = _like(cfg, tr)
+    names = [str(n) for n in tr["names"]]
+    const = {str(k): float(v) for k, v in zip(tr["const_keys"], tr["const_vals"])}
+
+    class _OpenPrior(object):               # the sampler already applied the bounds: every recorded point is in the box
+        pass
+
+    prior = _OpenPrior()
+    prior.names, prior.const = names, const
+    prior.in_bounds = lambda x: True
+    prior.log_prior = lambda x: 0.0
+    post = Posterior(like, prior)
+    pool = BatchedPool(post)
+    k, worst = 0, 0.0
+    for n in tr["sizes"]:
+        pts = tr["X"][k:k + n]
+        res = pool.map(post.log_likeprior, pts)
+        got = np.array([r[0] for r in res])
+        worst = max(worst, _check(got, tr["logl"][k:k + n], "ptmcmc call of %d points" % n))
+        k += n
+    assert pool.n_batched_calls == len(tr["sizes"]) == 1 + 2 * int(tr["shape"][2]) and pool.n_points == len(tr["X"])
+    print("reference ptmcmc trace: %d calls, %d points, worst %.3g x tol" % (len(tr["sizes"]), k, worst))
