@@ -125,7 +125,18 @@ struct bj_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
+    bool shadow = false;          // a compressed level of another context: owns static tables only
     int launch_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // compressed frequency axis (build_compressed_axis): a second set of mixed-precision tables on Chebyshev nodes.  `cmp`
+    // owns its static tables only; workspace, Gram moments, stream and events are this context's and are lent per call.
+    bj_ctx* cmp[kMaxLevels] = {nullptr, nullptr};   // levels of growing design budget (kernels.cuh: classify_kernel)
+    int n_levels = 0;
+    SteepTable steep;
+    int* d_lists = nullptr;           // [n_levels + 1][cap_walkers] work lists: one per level, the last = the full grid
+    int* d_counts = nullptr;          // [kMaxLevels + 1]
+    int cmp_info[kMaxLevels][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // nodes, nodes that are plain bins, blocks, nodes per block
+    double cmp_spec[kMaxLevels][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};   // mchirp_min, tau_max, reach, margin
+    long last_walkers = 0;
 };
 
 static int check_config(const bj_config* cfg) {
@@ -206,6 +217,25 @@ static void data_weight(const BinStatics& b, double four_over_t, double dre, dou
     const double cre = dre, cim = -dim;
     wr = sc * (cre * b.cs - cim * b.sn);
     wi = sc * (cre * b.sn + cim * b.cs);
+}
+
+// A frequency axis the table builders work on: bin (or node) frequencies and, per detector, the complex weight
+// (4/T) conj(d)/S f^(-7/6) exp(i pi f T) that multiplies Q e^{-i theta} in <d|h>.  The full grid carries the weights of its
+// bins (full_axis_weights); the compressed axis carries Chebyshev-node weights (build_compressed_axis).
+struct Axis {
+    long n = 0;
+    const double* f = nullptr;
+    const double* w[BJ_MAX_IFO] = {nullptr, nullptr, nullptr};    // interleaved (re, im)
+};
+static void full_axis_weights(std::vector<double>* wts, int nifo, long n, const double* freqs,
+                              const double* const* data_ri, const double* const* psd, double seglen) {
+    const double four_over_t = 4.0 / seglen;
+    for (int i = 0; i < nifo; ++i) wts[i].assign((size_t)2 * n, 0.0);
+    for (long k = 0; k < n; ++k) {
+        const BinStatics b = bin_statics(freqs[k], seglen);
+        for (int i = 0; i < nifo; ++i)
+            data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wts[i][2 * k], wts[i][2 * k + 1]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -378,41 +408,35 @@ static void build_gram(std::vector<double>& gram, std::vector<double>& dd_band, 
 
 // all-FP64 records (validation mode)
 template <int NIFO>
-static void build_records(std::vector<double>& rec, const Layout& L, const double* freqs,
-                          const double* const* data_ri, const double* const* psd, double seglen) {
+static void build_records(std::vector<double>& rec, const Layout& L, const Axis& ax, double seglen) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     const size_t n = L.slot_bin.size();
     rec.assign(n * RS, 0.0);
-    const double four_over_t = 4.0 / seglen;
     for (size_t sidx = 0; sidx < n; ++sidx) {
         const long k = L.slot_bin[sidx];
-        const BinStatics b = bin_statics(freqs[k], seglen);
+        const BinStatics b = bin_statics(ax.f[k], seglen);
         double* r = &rec[sidx * RS];
         r[0] = b.u; r[1] = b.L; r[2] = b.w5; r[3] = b.f;
         if (!L.slot_real[sidx]) continue;
-        for (int i = 0; i < NIFO; ++i)
-            data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], r[4 + 2 * i], r[5 + 2 * i]);
+        for (int i = 0; i < NIFO; ++i) { r[4 + 2 * i] = ax.w[i][2 * k]; r[5 + 2 * i] = ax.w[i][2 * k + 1]; }
     }
 }
 
 // all-FP64 records of the precise window [lo, hi), data weights times the complex factor (sr + i si) that the epilogue's
 // common <d|h> correction (table scale, calibrated phasor bias) will undo again
 template <int NIFO>
-static void build_records_window(std::vector<double>& rec, const Layout& L, long lo, long hi, const double* freqs,
-                                 const double* const* data_ri, const double* const* psd, double seglen, double sr,
-                                 double si) {
+static void build_records_window(std::vector<double>& rec, const Layout& L, long lo, long hi, const Axis& ax,
+                                 double seglen, double sr, double si) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     rec.assign((size_t)(hi - lo) * RS, 0.0);
-    const double four_over_t = 4.0 / seglen;
     for (long sidx = lo; sidx < hi; ++sidx) {
         const long k = L.slot_bin[sidx];
-        const BinStatics b = bin_statics(freqs[k], seglen);
+        const BinStatics b = bin_statics(ax.f[k], seglen);
         double* r = &rec[(size_t)(sidx - lo) * RS];
         r[0] = b.u; r[1] = b.L; r[2] = b.w5; r[3] = b.f;
         if (!L.slot_real[sidx]) continue;
         for (int i = 0; i < NIFO; ++i) {
-            double wr, wi;
-            data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            const double wr = ax.w[i][2 * k], wi = ax.w[i][2 * k + 1];
             r[4 + 2 * i] = wr * sr - wi * si;
             r[5 + 2 * i] = wr * si + wi * sr;
         }
@@ -421,20 +445,18 @@ static void build_records_window(std::vector<double>& rec, const Layout& L, long
 
 // mixed-precision records: FP64 phase statics, FP32 amplitude statics and data weights scaled by 2^-e
 template <int NIFO>
-static int build_records_mixed(std::vector<unsigned char>& rec, const Layout& L, const double* freqs,
-                               const double* const* data_ri, const double* const* psd, double seglen, int* exp_out) {
+static int build_records_mixed(std::vector<unsigned char>& rec, const Layout& L, const Axis& ax, double seglen,
+                               int* exp_out) {
     constexpr int RB = RecM<NIFO>::kBytes;
     const size_t n = L.slot_bin.size();
     rec.assign(n * RB, 0);
-    const double four_over_t = 4.0 / seglen;
+    const double* freqs = ax.f;
     double mx = 0.0;
     for (size_t sidx = 0; sidx < n; ++sidx) {
         if (!L.slot_real[sidx]) continue;
         const long k = L.slot_bin[sidx];
-        const BinStatics b = bin_statics(freqs[k], seglen);
         for (int i = 0; i < NIFO; ++i) {
-            double wr, wi;
-            data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            const double wr = ax.w[i][2 * k], wi = ax.w[i][2 * k + 1];
             if (!std::isfinite(wr) || !std::isfinite(wi)) return -1;
             mx = std::fmax(mx, std::fmax(std::fabs(wr), std::fabs(wi)));
         }
@@ -463,7 +485,7 @@ static int build_records_mixed(std::vector<unsigned char>& rec, const Layout& L,
         memcpy(r + 32, hf, 16);
         for (int i = 0; i < NIFO; ++i) {
             double wr = 0.0, wi = 0.0;
-            if (L.slot_real[sidx]) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            if (L.slot_real[sidx]) { wr = ax.w[i][2 * k]; wi = ax.w[i][2 * k + 1]; }
             const float fr = (float)(wr * sc), fi = (float)(wi * sc);
             float d4[4] = {fr, fi, fi, -fr};
             memcpy(r + 48 + 16 * i, d4, 16);
@@ -478,14 +500,13 @@ static int build_records_mixed(std::vector<unsigned char>& rec, const Layout& L,
 // and data[bin] = f, the FP32 pair slot and the scaled data weights of build_records_mixed (same 2^-e)
 template <int MODEL>
 static void build_records_tile(std::vector<double>& tab_basis, std::vector<unsigned char>& rec, const Layout& L,
-                               const double* freqs, const double* const* data_ri, const double* const* psd,
-                               double seglen, int nifo, int e2, bool rot) {
+                               const Axis& ax, double seglen, int nifo, int e2, bool rot) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes;
     const size_t n = L.slot_bin.size();
     rec.assign(n * RB, 0);
     tab_basis.assign(n * R::K, 0.0);
-    const double four_over_t = 4.0 / seglen;
+    const double* freqs = ax.f;
     const double sc = std::ldexp(1.0, -e2);
     for (size_t sidx = 0; sidx < n; ++sidx) {
         const long k = L.slot_bin[sidx];
@@ -521,7 +542,7 @@ static void build_records_tile(std::vector<double>& tab_basis, std::vector<unsig
         float dri[BJ_MAX_IFO][2];
         for (int i = 0; i < nifo; ++i) {
             double wr = 0.0, wi = 0.0;
-            if (L.slot_real[sidx]) data_weight(b, four_over_t, data_ri[i][2 * k], data_ri[i][2 * k + 1], psd[i][k], wr, wi);
+            if (L.slot_real[sidx]) { wr = ax.w[i][2 * k]; wi = ax.w[i][2 * k + 1]; }
             dri[i][0] = (float)(wr * sc);
             dri[i][1] = (float)(wi * sc);
         }
@@ -553,6 +574,188 @@ static cudaError_t upload(T** dst, const std::vector<T>& src) {
     cudaError_t e = cudaMalloc((void**)dst, src.size() * sizeof(T));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static void adopt_layout(bj_ctx* c, const Layout& L) {
+    c->n_precise = L.n_precise;
+    c->prec_lo = L.prec_lo;
+    c->prec_hi = L.prec_hi;
+    c->n_cells = (int)L.cell_band.size();
+    c->n_chunks = (int)L.chunks.size();
+    c->bins_per_chunk = L.per;
+    c->n_bins_kernel = (long)L.slot_bin.size();
+}
+
+// The mixed-precision table set of one frequency axis (the full grid, or the compressed node axis): layout, Horner
+// records (fix-up / time marginalisation / amplitude correction), FP64 window, tensor-core tables; uploads them into c.
+static int build_mixed_set(bj_ctx* c, const bj_config* cfg, const Axis& ax, const bj_extras* ex,
+                           const std::vector<double>& bw, const double* eps, bool uniform_ok, bool tm, Layout& L) {
+    double share = 0.9, frac = 0.08;
+    if (const char* ev = getenv("BAJES_B200_PRECISE_SHARE")) share = atof(ev);
+    if (const char* ev = getenv("BAJES_B200_PRECISE_FRAC")) frac = atof(ev);
+    if (tm || getenv("BAJES_B200_NO_TC")) frac = 0.0;
+    if (build_layout(L, ax.n, ax.f, ex, &bw, share, frac)) return fail(BJ_ERR_INVALID, "len_weights do not cover the band");
+    adopt_layout(c, L);
+    std::vector<unsigned char> recm;
+    int e2 = 0, bad = 0;
+    switch (cfg->n_ifo) {
+        case 1: bad = build_records_mixed<1>(recm, L, ax, cfg->seglen, &e2); c->rec_doubles = RecM<1>::kDoubles; break;
+        case 2: bad = build_records_mixed<2>(recm, L, ax, cfg->seglen, &e2); c->rec_doubles = RecM<2>::kDoubles; break;
+        default: bad = build_records_mixed<3>(recm, L, ax, cfg->seglen, &e2); c->rec_doubles = RecM<3>::kDoubles; break;
+    }
+    if (bad) return fail(BJ_ERR_INVALID, "non-finite static table entry (check data / PSD)");
+    // computed phasor = true phasor * (1 + eps_a - i eps_p): divide it out, and undo the 2^-e table scale
+    const double ar = 1.0 + eps[0], ai = -eps[1];
+    const double den = ar * ar + ai * ai;
+    const double sc = std::ldexp(1.0, e2);
+    c->cfg.dh_fix_re = sc * ar / den;
+    c->cfg.dh_fix_im = -sc * ai / den;
+    if (c->n_precise > 0) {
+        // the epilogue multiplies every chunk sum by 2^e / (ar + i ai): pre-multiply the FP64 window by its inverse
+        std::vector<double> rec64;
+        const double inv = std::ldexp(1.0, -e2);
+        switch (cfg->n_ifo) {
+            case 1: build_records_window<1>(rec64, L, L.prec_lo, L.prec_hi, ax, cfg->seglen, ar * inv, ai * inv); break;
+            case 2: build_records_window<2>(rec64, L, L.prec_lo, L.prec_hi, ax, cfg->seglen, ar * inv, ai * inv); break;
+            default: build_records_window<3>(rec64, L, L.prec_lo, L.prec_hi, ax, cfg->seglen, ar * inv, ai * inv); break;
+        }
+        cudaError_t e64 = upload(&c->d_rec64, rec64);
+        if (e64 != cudaSuccess) return fail(BJ_ERR_CUDA, "uploading the FP64 window failed: %s", cudaGetErrorString(e64));
+    }
+    // the tensor-core kernel (phase as an FP64 GEMM) is the production path
+    if (!getenv("BAJES_B200_NO_TC")) {
+        // uniform in-band grid (every FFT grid bajes produces): integer time-delay ramps, and one phasor per bin
+        // rotated to the other detectors
+        if (uniform_ok && ax.n >= 2 && !getenv("BAJES_B200_NO_IRAMP")) {
+            const double df = (ax.f[ax.n - 1] - ax.f[0]) / (double)(ax.n - 1);
+            bool uniform = df > 0.0;
+            for (long k = 0; k < ax.n && uniform; ++k)
+                uniform = std::fabs(ax.f[k] - (ax.f[0] + (double)k * df)) <= 1e-7 * df;
+            if (uniform) c->grid_df = df;
+        }
+        c->rot = c->grid_df > 0.0 && cfg->n_ifo >= 2 && !getenv("BAJES_B200_NO_ROT");
+        if (c->rot) c->cfg.grid_df = c->grid_df;
+        std::vector<unsigned char> rect;
+        std::vector<double> basis;
+        if (cfg->approx == BJ_APPROX_TAYLORF2_35PN) build_records_tile<MODEL_35>(basis, rect, L, ax, cfg->seglen, cfg->n_ifo, e2, c->rot);
+        else                                        build_records_tile<MODEL_GENERIC>(basis, rect, L, ax, cfg->seglen, cfg->n_ifo, e2, c->rot);
+        cudaError_t et = cudaMalloc(&c->d_tile_data, rect.size());
+        if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_data, rect.data(), rect.size(), cudaMemcpyHostToDevice);
+        if (et == cudaSuccess) et = cudaMalloc(&c->d_tile_basis, basis.size() * sizeof(double));
+        if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_basis, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (et != cudaSuccess) return fail(BJ_ERR_CUDA, "uploading the tensor-core tables failed: %s", cudaGetErrorString(et));
+    }
+    cudaError_t e = cudaMalloc(&c->d_rec, recm.size());
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, recm.data(), recm.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = upload(&c->d_chunks, L.chunks);
+    if (e == cudaSuccess) e = upload(&c->d_cell_band, L.cell_band);
+    if (e == cudaSuccess) e = upload(&c->d_cell_seg, L.cell_seg);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "uploading static tables failed: %s", cudaGetErrorString(e));
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compressed frequency axis.
+//
+// <d|h>_i = sum_k w_ik g_i(f_k) with static weights w_ik = (4/T) conj(d_ik)/S_ik f_k^(-7/6) e^{i pi f_k T} and the walker's
+// SMOOTH factor g_i(f) = Q(f) e^{-2 pi i [Phi(f)/2pi + f tau_i]}.  On a run of bins [a, b] over which the phase of g turns
+// by at most `reach` radians to either side of the centre, g is reproduced to ~1e-11 by its Chebyshev interpolant on n
+// nodes f_j, so
+//     sum_{k in run} w_ik g_i(f_k) = sum_j [ sum_k w_ik l_j(f_k) ] g_i(f_j) = sum_j W_ij g_i(f_j)
+// with the Lagrange cardinal functions l_j: the run's bins collapse into n "bins" with weights W_ij that the very same
+// kernels evaluate (non-uniform axis).  The run length follows from a DESIGN bound on the phase slope,
+//     |d(Phi/2pi + f tau)/df| <= margin t_N(f; mchirp_min) + tau_max        (t_N: Newtonian time to coalescence),
+// that steep_kernel checks per walker; walkers outside the design are evaluated on the full grid (run_device).  Where a run
+// would hold fewer than 1.5 n bins (low frequencies of a long signal) the bins are kept as they are.  Weights are formed in
+// long double with the barycentric formula; nothing about the walker enters, and <h|h> never used the grid (Gram moments).
+// ------------------------------------------------------------------------------------------------
+struct CompressSpec {
+    int on, nodes;
+    double reach, mchirp_min, tau_max, margin;
+};
+static CompressSpec compress_spec(const bj_extras* ex) {
+    CompressSpec sp = {1, 32, 10.0, 0.5, 0.11, 1.3};
+    if (ex && ex->compress != 0) {
+        sp.on = ex->compress > 0;
+        if (ex->compress_mchirp_min > 0.0) sp.mchirp_min = ex->compress_mchirp_min;
+        if (ex->compress_tau_max > 0.0) sp.tau_max = ex->compress_tau_max;
+    }
+    if (const char* ev = getenv("BAJES_B200_COMPRESS")) sp.on = atoi(ev) != 0;
+    if (const char* ev = getenv("BAJES_B200_COMPRESS_NODES")) sp.nodes = std::max(4, std::min(64, atoi(ev)));
+    if (const char* ev = getenv("BAJES_B200_COMPRESS_REACH")) sp.reach = atof(ev);
+    if (const char* ev = getenv("BAJES_B200_COMPRESS_MCHIRP_MIN")) sp.mchirp_min = atof(ev);
+    if (const char* ev = getenv("BAJES_B200_COMPRESS_TAU_MAX")) sp.tau_max = atof(ev);
+    return sp;
+}
+// seconds: the design bound on |d(Phi/2pi)/df| + |tau_i| at frequency f  (gt: taylorf2.py:6)
+static double design_budget(const CompressSpec& sp, double f) {
+    const double t = 5.0 / 256.0 * std::pow(sp.mchirp_min * 4.92549094830932e-6, -5.0 / 3.0) * std::pow(M_PI * f, -8.0 / 3.0);
+    return sp.margin * t + sp.tau_max;
+}
+static void build_compressed_axis(const Axis& full, int nifo, const std::vector<double>& bw, const CompressSpec& sp,
+                                  std::vector<double>& nf, std::vector<double>* nw, std::vector<double>& nbw, int* info) {
+    const int n = sp.nodes;
+    const long N = full.n;
+    nf.clear();
+    nbw.clear();
+    for (int i = 0; i < nifo; ++i) nw[i].clear();
+    std::vector<long double> xn(n), lam(n), ell(n);
+    for (int j = 0; j < n; ++j) {
+        const long double th = M_PIl * (2 * j + 1) / (2.0L * n);
+        xn[j] = -cosl(th);                               // ascending
+        lam[j] = ((j & 1) ? -1.0L : 1.0L) * sinl(th);    // barycentric weights of the first-kind Chebyshev points
+    }
+    std::vector<long double> acc((size_t)2 * nifo * n), accb(n);
+    long k = 0, kept = 0, blocks = 0;
+    while (k < N) {
+        const double width = 2.0 * sp.reach / (2.0 * M_PI * design_budget(sp, full.f[k]));    // Hz
+        long k1 = k + 1;
+        while (k1 < N && full.f[k1] - full.f[k] <= width) ++k1;
+        const long nb = k1 - k;
+        if (nb <= n + n / 2) {                           // too few bins to gain: keep n of them as they are
+            const long ke = std::min(N, k + (long)n);
+            for (; k < ke; ++k, ++kept) {
+                nf.push_back(full.f[k]);
+                nbw.push_back(bw[k]);
+                for (int i = 0; i < nifo; ++i) { nw[i].push_back(full.w[i][2 * k]); nw[i].push_back(full.w[i][2 * k + 1]); }
+            }
+            continue;
+        }
+        const long double a = full.f[k], b = full.f[k1 - 1];
+        const long double mid = 0.5L * (a + b), half = 0.5L * (b - a);
+        std::fill(acc.begin(), acc.end(), 0.0L);
+        std::fill(accb.begin(), accb.end(), 0.0L);
+        for (long q = k; q < k1; ++q) {
+            const long double x = ((long double)full.f[q] - mid) / half;
+            int hit = -1;
+            long double den = 0.0L;
+            for (int j = 0; j < n; ++j) {
+                const long double d = x - xn[j];
+                if (d == 0.0L) { hit = j; break; }
+                ell[j] = lam[j] / d;
+                den += ell[j];
+            }
+            if (hit >= 0) { for (int j = 0; j < n; ++j) ell[j] = j == hit ? 1.0L : 0.0L; }
+            else          { for (int j = 0; j < n; ++j) ell[j] /= den; }
+            for (int i = 0; i < nifo; ++i) {
+                const long double wr = full.w[i][2 * q], wi = full.w[i][2 * q + 1];
+                long double* ai = &acc[(size_t)2 * i * n];
+                for (int j = 0; j < n; ++j) { ai[2 * j] += wr * ell[j]; ai[2 * j + 1] += wi * ell[j]; }
+            }
+            for (int j = 0; j < n; ++j) accb[j] += (long double)bw[q] * fabsl(ell[j]);
+        }
+        for (int j = 0; j < n; ++j) {
+            nf.push_back((double)(mid + half * xn[j]));
+            nbw.push_back((double)accb[j]);
+            for (int i = 0; i < nifo; ++i) { nw[i].push_back((double)acc[(size_t)2 * (i * n + j)]); nw[i].push_back((double)acc[(size_t)2 * (i * n + j) + 1]); }
+        }
+        ++blocks;
+        k = k1;
+    }
+    info[0] = (int)nf.size();
+    info[1] = (int)kept;
+    info[2] = (int)blocks;
+    info[3] = n;
 }
 
 extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, const double* freqs,
@@ -605,28 +808,52 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
         c->tm_offset = (long)ex->band_offset;
     }
 
-    Layout L;
-    {
-        // share of each bin in <h|h> of an inspiral; the precise window only exists in the mixed-precision modes
-        std::vector<double> bw((size_t)n_bins, 0.0);
-        for (int64_t k = 0; k < n_bins; ++k) {
-            double w = 0.0;
-            for (int i = 0; i < cfg->n_ifo; ++i) w += 1.0 / psd[i][k];
-            bw[k] = w * std::pow(freqs[k], -7.0 / 3.0);
-        }
-        double share = 0.9, frac = 0.08;
-        if (const char* ev = getenv("BAJES_B200_PRECISE_SHARE")) share = atof(ev);
-        if (const char* ev = getenv("BAJES_B200_PRECISE_FRAC")) frac = atof(ev);
-        if (cfg->sincos == BJ_SINCOS_FP64 || (ex && ex->marg_time_shift) || getenv("BAJES_B200_NO_TC")) frac = 0.0;
-        if (build_layout(L, n_bins, freqs, ex, &bw, share, frac)) { bj_destroy(c); return fail(BJ_ERR_INVALID, "len_weights do not cover the band"); }
+    // per-bin weights of the full grid, shared by every table builder
+    std::vector<double> wts[BJ_MAX_IFO];
+    full_axis_weights(wts, cfg->n_ifo, (long)n_bins, freqs, data_ri, psd, cfg->seglen);
+    Axis ax;
+    ax.n = (long)n_bins;
+    ax.f = freqs;
+    for (int i = 0; i < cfg->n_ifo; ++i) ax.w[i] = wts[i].data();
+    // share of each bin in <h|h> of an inspiral; the precise window only exists in the mixed-precision modes
+    std::vector<double> bw((size_t)n_bins, 0.0);
+    for (int64_t k = 0; k < n_bins; ++k) {
+        double w = 0.0;
+        for (int i = 0; i < cfg->n_ifo; ++i) w += 1.0 / psd[i][k];
+        bw[k] = w * std::pow(freqs[k], -7.0 / 3.0);
     }
-    c->n_precise = L.n_precise;
-    c->prec_lo = L.prec_lo;
-    c->prec_hi = L.prec_hi;
-    c->n_cells = (int)L.cell_band.size();
-    c->n_chunks = (int)L.chunks.size();
-    c->bins_per_chunk = L.per;
-    c->n_bins_kernel = (long)L.slot_bin.size();
+    const bool tm = ex && ex->marg_time_shift;
+
+    Layout L;
+    if (cfg->sincos == BJ_SINCOS_FP64) {
+        if (build_layout(L, n_bins, freqs, ex, &bw, 0.0, 0.0)) { bj_destroy(c); return fail(BJ_ERR_INVALID, "len_weights do not cover the band"); }
+        adopt_layout(c, L);
+        std::vector<double> rec;
+        switch (cfg->n_ifo) {
+            case 1: build_records<1>(rec, L, ax, cfg->seglen); c->rec_doubles = Rec<1>::kDoubles; break;
+            case 2: build_records<2>(rec, L, ax, cfg->seglen); c->rec_doubles = Rec<2>::kDoubles; break;
+            default: build_records<3>(rec, L, ax, cfg->seglen); c->rec_doubles = Rec<3>::kDoubles; break;
+        }
+        for (size_t i = 0; i < rec.size(); ++i)
+            if (!std::isfinite(rec[i])) {
+                bj_destroy(c);
+                return fail(BJ_ERR_INVALID, "non-finite static table entry at record %zu (check data / PSD)", i / c->rec_doubles);
+            }
+        cudaError_t e = cudaMalloc(&c->d_rec, rec.size() * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = upload(&c->d_chunks, L.chunks);
+        if (e == cudaSuccess) e = upload(&c->d_cell_band, L.cell_band);
+        if (e == cudaSuccess) e = upload(&c->d_cell_seg, L.cell_seg);
+        if (e != cudaSuccess) { bj_destroy(c); return fail(BJ_ERR_CUDA, "uploading static tables failed: %s", cudaGetErrorString(e)); }
+    } else {
+        double eps[2] = {0.0, 0.0};
+        rc = cfg->sincos == BJ_SINCOS_MUFU ? calibrate<BJ_SINCOS_MUFU>(eps) : calibrate<BJ_SINCOS_POLY32>(eps);
+        if (rc) { bj_destroy(c); return rc; }
+        c->calib[0] = eps[0];
+        c->calib[1] = eps[1];
+        rc = build_mixed_set(c, cfg, ax, ex, bw, eps, /*uniform_ok=*/true, tm, L);
+        if (rc) { bj_destroy(c); return rc; }
+    }
 
     std::vector<double> gram, dd_band;
     build_gram(gram, dd_band, L, cfg->n_ifo, nsp, nw, freqs, data_ri, psd, cfg->seglen);
@@ -635,96 +862,8 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
             bj_destroy(c);
             return fail(BJ_ERR_INVALID, "non-finite <h|h> moment (check the PSD)");
         }
-    const void* rec_ptr = nullptr;
-    size_t rec_bytes = 0;
-    std::vector<double> rec;
-    std::vector<unsigned char> recm;
-    if (cfg->sincos == BJ_SINCOS_FP64) {
-        switch (cfg->n_ifo) {
-            case 1: build_records<1>(rec, L, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<1>::kDoubles; break;
-            case 2: build_records<2>(rec, L, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<2>::kDoubles; break;
-            default: build_records<3>(rec, L, freqs, data_ri, psd, cfg->seglen); c->rec_doubles = Rec<3>::kDoubles; break;
-        }
-        for (size_t i = 0; i < rec.size(); ++i)
-            if (!std::isfinite(rec[i])) {
-                bj_destroy(c);
-                return fail(BJ_ERR_INVALID, "non-finite static table entry at record %zu (check data / PSD)", i / c->rec_doubles);
-            }
-        rec_ptr = rec.data();
-        rec_bytes = rec.size() * sizeof(double);
-    } else {
-        int e2 = 0, bad = 0;
-        switch (cfg->n_ifo) {
-            case 1: bad = build_records_mixed<1>(recm, L, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<1>::kDoubles; break;
-            case 2: bad = build_records_mixed<2>(recm, L, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<2>::kDoubles; break;
-            default: bad = build_records_mixed<3>(recm, L, freqs, data_ri, psd, cfg->seglen, &e2); c->rec_doubles = RecM<3>::kDoubles; break;
-        }
-        if (bad) {
-            bj_destroy(c);
-            return fail(BJ_ERR_INVALID, "non-finite static table entry (check data / PSD)");
-        }
-        double eps[2] = {0.0, 0.0};
-        rc = cfg->sincos == BJ_SINCOS_MUFU ? calibrate<BJ_SINCOS_MUFU>(eps) : calibrate<BJ_SINCOS_POLY32>(eps);
-        if (rc) { bj_destroy(c); return rc; }
-        // computed phasor = true phasor * (1 + eps_a - i eps_p): divide it out, and undo the 2^-e table scale
-        const double ar = 1.0 + eps[0], ai = -eps[1];
-        const double den = ar * ar + ai * ai;
-        const double sc = std::ldexp(1.0, e2);
-        c->cfg.dh_fix_re = sc * ar / den;
-        c->cfg.dh_fix_im = -sc * ai / den;
-        c->calib[0] = eps[0];
-        c->calib[1] = eps[1];
-        rec_ptr = recm.data();
-        rec_bytes = recm.size();
-        if (c->n_precise > 0) {
-            // the epilogue multiplies every chunk sum by 2^e / (ar + i ai): pre-multiply the FP64 window by its inverse
-            std::vector<double> rec64;
-            const double inv = std::ldexp(1.0, -e2);
-            switch (cfg->n_ifo) {
-                case 1: build_records_window<1>(rec64, L, L.prec_lo, L.prec_hi, freqs, data_ri, psd, cfg->seglen, ar * inv, ai * inv); break;
-                case 2: build_records_window<2>(rec64, L, L.prec_lo, L.prec_hi, freqs, data_ri, psd, cfg->seglen, ar * inv, ai * inv); break;
-                default: build_records_window<3>(rec64, L, L.prec_lo, L.prec_hi, freqs, data_ri, psd, cfg->seglen, ar * inv, ai * inv); break;
-            }
-            cudaError_t e64 = upload(&c->d_rec64, rec64);
-            if (e64 != cudaSuccess) {
-                bj_destroy(c);
-                return fail(BJ_ERR_CUDA, "uploading the FP64 window failed: %s", cudaGetErrorString(e64));
-            }
-        }
-        // the tensor-core kernel (phase as an FP64 GEMM) is the production path
-        if (!getenv("BAJES_B200_NO_TC")) {
-            // uniform in-band grid (every FFT grid bajes produces): integer time-delay ramps, and one phasor per bin
-            // rotated to the other detectors
-            if (n_bins >= 2 && !getenv("BAJES_B200_NO_IRAMP")) {
-                const double df = (freqs[n_bins - 1] - freqs[0]) / (double)(n_bins - 1);
-                bool uniform = df > 0.0;
-                for (int64_t k = 0; k < n_bins && uniform; ++k)
-                    uniform = std::fabs(freqs[k] - (freqs[0] + (double)k * df)) <= 1e-7 * df;
-                if (uniform) c->grid_df = df;
-            }
-            c->rot = c->grid_df > 0.0 && cfg->n_ifo >= 2 && !getenv("BAJES_B200_NO_ROT");
-            if (c->rot) c->cfg.grid_df = c->grid_df;
-            std::vector<unsigned char> rect;
-            std::vector<double> basis;
-            if (cfg->approx == BJ_APPROX_TAYLORF2_35PN) build_records_tile<MODEL_35>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2, c->rot);
-            else                                        build_records_tile<MODEL_GENERIC>(basis, rect, L, freqs, data_ri, psd, cfg->seglen, cfg->n_ifo, e2, c->rot);
-            cudaError_t et = cudaMalloc(&c->d_tile_data, rect.size());
-            if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_data, rect.data(), rect.size(), cudaMemcpyHostToDevice);
-            if (et == cudaSuccess) et = cudaMalloc(&c->d_tile_basis, basis.size() * sizeof(double));
-            if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_basis, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice);
-            if (et != cudaSuccess) {
-                bj_destroy(c);
-                return fail(BJ_ERR_CUDA, "uploading the tensor-core tables failed: %s", cudaGetErrorString(et));
-            }
-        }
-    }
-    cudaError_t e = cudaMalloc(&c->d_rec, rec_bytes);
-    if (e == cudaSuccess) e = cudaMemcpy(c->d_rec, rec_ptr, rec_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = upload(&c->d_gram, gram);
+    cudaError_t e = upload(&c->d_gram, gram);
     if (e == cudaSuccess) e = upload(&c->d_dd_band, dd_band);
-    if (e == cudaSuccess) e = upload(&c->d_chunks, L.chunks);
-    if (e == cudaSuccess) e = upload(&c->d_cell_band, L.cell_band);
-    if (e == cudaSuccess) e = upload(&c->d_cell_seg, L.cell_seg);
     if (e == cudaSuccess && nsp > 0) {
         std::vector<double> nf(ex->spcal_freqs, ex->spcal_freqs + nsp);
         e = upload(&c->d_spcal_freqs, nf);
@@ -734,6 +873,65 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
     if (e != cudaSuccess) {
         bj_destroy(c);
         return fail(BJ_ERR_CUDA, "uploading static tables failed: %s", cudaGetErrorString(e));
+    }
+
+    // ---- compressed frequency axes (mixed-precision modes, tensor-core tables, no extras, no time marginalisation) ----
+    CompressSpec sp = compress_spec(ex);
+    if (sp.on && cfg->sincos != BJ_SINCOS_FP64 && c->d_tile_basis && nsp == 0 && nw == 0 && !tm) {
+        // level 0: the design; level 1: time shifts up to ~1 s (the default prior of the reference's pipeline,
+        // pipe/scripts/bajes_pipe:526) -- samplers start there and end in level 0
+        double taus[kMaxLevels] = {sp.tau_max, std::fmax(1.1, 2.0 * sp.tau_max)};
+        int want = sp.tau_max >= 1.1 ? 1 : kMaxLevels;
+        if (const char* ev = getenv("BAJES_B200_COMPRESS_LEVELS")) want = std::max(1, std::min(kMaxLevels, atoi(ev)));
+        for (int lv = 0; lv < want; ++lv) {
+            CompressSpec sl = sp;
+            sl.tau_max = taus[lv];
+            std::vector<double> nf, nbw, nwt[BJ_MAX_IFO];
+            int info[4] = {0, 0, 0, 0};
+            build_compressed_axis(ax, cfg->n_ifo, bw, sl, nf, nwt, nbw, info);
+            // worth it only when the node axis is markedly shorter than the grid
+            if ((double)nf.size() > 0.7 * (double)n_bins) break;
+            Axis cx;
+            cx.n = (long)nf.size();
+            cx.f = nf.data();
+            for (int i = 0; i < cfg->n_ifo; ++i) cx.w[i] = nwt[i].data();
+            bj_ctx* m = new bj_ctx();
+            m->kind = KIND_FULLGRID;
+            m->shadow = true;
+            m->device = c->device;
+            m->sm_count = c->sm_count;
+            m->sincos = c->sincos;
+            m->cfg = c->cfg;
+            memset(&m->dims, 0, sizeof(m->dims));
+            m->n_bins = cx.n;
+            c->cmp[c->n_levels] = m;
+            Layout Lc;
+            rc = build_mixed_set(m, cfg, cx, nullptr, nbw, c->calib, /*uniform_ok=*/false, false, Lc);
+            if (rc) { c->n_levels++; bj_destroy(c); return rc; }
+            const int q0 = c->n_levels++;
+            for (int q = 0; q < 4; ++q) c->cmp_info[q0][q] = info[q];
+            c->cmp_spec[q0][0] = sl.mchirp_min; c->cmp_spec[q0][1] = sl.tau_max; c->cmp_spec[q0][2] = sl.reach; c->cmp_spec[q0][3] = sl.margin;
+            for (int q = 0; q < kSteepChecks; ++q) {
+                const double f = freqs[0] * std::pow(freqs[n_bins - 1] / freqs[0], (double)q / (double)(kSteepChecks - 1));
+                c->steep.budget[q0][q] = design_budget(sl, f);
+            }
+        }
+        if (c->n_levels > 0) {
+            // check frequencies of classify_kernel: log-spaced over the band, both ends included
+            c->steep.n = kSteepChecks;
+            c->steep.n_levels = c->n_levels;
+            for (int q = 0; q < kSteepChecks; ++q) {
+                const double f = freqs[0] * std::pow(freqs[n_bins - 1] / freqs[0], (double)q / (double)(kSteepChecks - 1));
+                c->steep.u[q] = std::cbrt(f);
+                c->steep.L[q] = std::log(f);
+                c->steep.w5[q] = std::pow(f, -5.0 / 3.0);
+                c->steep.inv_f[q] = 1.0 / f;
+            }
+            if (cudaMalloc(&c->d_counts, (kMaxLevels + 1) * sizeof(int)) != cudaSuccess) {
+                bj_destroy(c);
+                return fail(BJ_ERR_CUDA, "allocating the work-list counters failed");
+            }
+        }
     }
     *out = c;
     return BJ_OK;
@@ -747,6 +945,21 @@ extern "C" int bj_create(bj_ctx** out, const bj_config* cfg, int64_t n_bins, con
 extern "C" int bj_destroy(bj_ctx* c) {
     if (!c) return BJ_OK;
     cudaSetDevice(c->device);
+    for (int lv = 0; lv < kMaxLevels; ++lv) {
+        bj_ctx* m = c->cmp[lv];
+        if (!m) continue;
+        cudaFree(m->d_rec);
+        cudaFree(m->d_tile_basis);
+        cudaFree(m->d_tile_data);
+        cudaFree(m->d_rec64);
+        cudaFree(m->d_chunks);
+        cudaFree(m->d_cell_band);
+        cudaFree(m->d_cell_seg);
+        delete m;
+        c->cmp[lv] = nullptr;
+    }
+    cudaFree(c->d_lists);
+    cudaFree(c->d_counts);
     cudaFree(c->d_rec);
     cudaFree(c->d_tile_basis);
     cudaFree(c->d_tile_data);
@@ -792,7 +1005,15 @@ static int ensure_workspace(bj_ctx* c, long n_walkers) {
     if (c->dims.nspcal > 0 || c->dims.nweights > 0)
         CUDA_TRY(cudaMalloc(&c->d_coef_ex, (size_t)ex_num_slots(c->dims, c->cfg.n_ifo) * cap * sizeof(double)));
     size_t part = 0;
-    if (c->kind == KIND_FULLGRID) part = (size_t)c->n_chunks * 2 * c->cfg.n_ifo * cap;
+    if (c->kind == KIND_FULLGRID) {
+        int nch = c->n_chunks;
+        for (int lv = 0; lv < c->n_levels; ++lv) nch = std::max(nch, c->cmp[lv]->n_chunks);
+        part = (size_t)nch * 2 * c->cfg.n_ifo * cap;
+    }
+    if (c->n_levels > 0) {
+        cudaFree(c->d_lists); c->d_lists = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_lists, (size_t)(c->n_levels + 1) * cap * sizeof(int)));
+    }
     if (part) CUDA_TRY(cudaMalloc(&c->d_partial, part * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->d_logl, (size_t)cap * sizeof(double)));
     c->cap_walkers = cap;
@@ -833,22 +1054,24 @@ static void note_launch(bj_ctx* c, dim3 grid, size_t smem, int rec8, int model, 
     c->launch_info[7] = model;
 }
 
+// sel (kernels.cuh: Sel): the work list the launch evaluates (contexts with compressed axes: one list per table); the grid
+// is sized for the whole batch and CTAs beyond the end of the list return at once.  {null, null} = every walker.
 template <int NIFO, int MODEL, bool SPCAL>
-static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
+static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1, Sel sel) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     const size_t smem = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
     auto kern = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, SPCAL>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(c1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
     kern<<<grid, kThreads, smem, st>>>((const double*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
-                                       c->d_partial, c->d_coef_ex, c->dims, c->d_spcal_freqs, c0);
+                                       c->d_partial, c->d_coef_ex, c->dims, c->d_spcal_freqs, c0, sel);
     CUDA_TRY(cudaGetLastError());
     note_launch(c, grid, smem, RS, MODEL);
     return BJ_OK;
 }
 
 template <int NIFO, int MODEL, int SC, bool SPCAL>
-static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
+static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1, Sel sel) {
     constexpr int RB = RecM<NIFO>::kBytes;
     if (c0 < c->n_precise) {
         // the heaviest bins in FP64 (chunks of 64 records; the table pointer is offset so that chunk.start indexes it)
@@ -861,13 +1084,13 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
             CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
             pk<<<pgrid, kThreads, smem64, st>>>(c->d_rec64 - (size_t)c->prec_lo * RS, c->d_chunks, c->d_coef,
                                                 c->cap_walkers, n_walkers, c->d_partial, c->d_coef_ex, c->dims,
-                                                c->d_spcal_freqs, c0, c->grid_df);
+                                                c->d_spcal_freqs, c0, c->grid_df, sel);
         } else {
             auto pk = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, SPCAL>;
             CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
             pk<<<pgrid, kThreads, smem64, st>>>(c->d_rec64 - (size_t)c->prec_lo * RS, c->d_chunks, c->d_coef,
                                                 c->cap_walkers, n_walkers, c->d_partial, c->d_coef_ex, c->dims,
-                                                c->d_spcal_freqs, c0);
+                                                c->d_spcal_freqs, c0, sel);
         }
         CUDA_TRY(cudaGetLastError());
         c0 = p1;
@@ -891,7 +1114,7 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
         tkern<<<tgrid, kTileThreads, smem_t, st>>>((const unsigned char*)c->d_tile_basis, (const unsigned char*)c->d_tile_data,
                                                    (const unsigned char*)c->d_rec, RB, c->d_chunks, c->d_coef,
                                                    c->cap_walkers, n_walkers, c->d_partial, c0, c->grid_df,
-                                                   c->d_coef_ex, c->dims);
+                                                   c->d_coef_ex, c->dims, sel);
         note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -899,7 +1122,9 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
                                            n_walkers, c->d_partial, c->d_coef_ex, c->dims, c0);
         note_launch(c, grid, smem, RB / 8, MODEL);
     }
-    // wide-phase fix-up: every CTA returns immediately unless the prologue flagged one of its walkers
+    // wide-phase fix-up: every CTA returns immediately unless the prologue flagged one of its walkers.  (Compressed
+    // tables never see such walkers: classify_kernel sends them to the full grid.)
+    if (c->shadow) return BJ_OK;
     fixup<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers,
                                         n_walkers, c->d_partial, c->d_coef_ex, c->dims, c0);
     CUDA_TRY(cudaGetLastError());
@@ -907,31 +1132,31 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
 }
 
 template <int NIFO, int MODEL, bool SPCAL>
-static int launch_fullgrid_s(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
+static int launch_fullgrid_s(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1, Sel sel) {
     switch (c->sincos) {
-        case BJ_SINCOS_MUFU: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_MUFU, SPCAL>(c, n_walkers, st, c0, c1);
-        case BJ_SINCOS_POLY32: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_POLY32, SPCAL>(c, n_walkers, st, c0, c1);
-        default: return launch_fullgrid_fp64<NIFO, MODEL, SPCAL>(c, n_walkers, st, c0, c1);
+        case BJ_SINCOS_MUFU: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_MUFU, SPCAL>(c, n_walkers, st, c0, c1, sel);
+        case BJ_SINCOS_POLY32: return launch_fullgrid_mixed<NIFO, MODEL, BJ_SINCOS_POLY32, SPCAL>(c, n_walkers, st, c0, c1, sel);
+        default: return launch_fullgrid_fp64<NIFO, MODEL, SPCAL>(c, n_walkers, st, c0, c1, sel);
     }
 }
 
 template <int NIFO, int MODEL>
-static int launch_fullgrid_m(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
-    if (c->dims.nspcal > 0) return launch_fullgrid_s<NIFO, MODEL, true>(c, n_walkers, st, c0, c1);
-    return launch_fullgrid_s<NIFO, MODEL, false>(c, n_walkers, st, c0, c1);
+static int launch_fullgrid_m(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1, Sel sel) {
+    if (c->dims.nspcal > 0) return launch_fullgrid_s<NIFO, MODEL, true>(c, n_walkers, st, c0, c1, sel);
+    return launch_fullgrid_s<NIFO, MODEL, false>(c, n_walkers, st, c0, c1, sel);
 }
 
 template <int NIFO>
-static int launch_fullgrid_n(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
-    if (c->cfg.approx == BJ_APPROX_TAYLORF2_35PN) return launch_fullgrid_m<NIFO, MODEL_35>(c, n_walkers, st, c0, c1);
-    return launch_fullgrid_m<NIFO, MODEL_GENERIC>(c, n_walkers, st, c0, c1);
+static int launch_fullgrid_n(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1, Sel sel) {
+    if (c->cfg.approx == BJ_APPROX_TAYLORF2_35PN) return launch_fullgrid_m<NIFO, MODEL_35>(c, n_walkers, st, c0, c1, sel);
+    return launch_fullgrid_m<NIFO, MODEL_GENERIC>(c, n_walkers, st, c0, c1, sel);
 }
 
-static int launch_fullgrid(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1) {
+static int launch_fullgrid(bj_ctx* c, long n_walkers, cudaStream_t st, int c0, int c1, Sel sel = Sel{nullptr, nullptr}) {
     switch (c->cfg.n_ifo) {
-        case 1: return launch_fullgrid_n<1>(c, n_walkers, st, c0, c1);
-        case 2: return launch_fullgrid_n<2>(c, n_walkers, st, c0, c1);
-        default: return launch_fullgrid_n<3>(c, n_walkers, st, c0, c1);
+        case 1: return launch_fullgrid_n<1>(c, n_walkers, st, c0, c1, sel);
+        case 2: return launch_fullgrid_n<2>(c, n_walkers, st, c0, c1, sel);
+        default: return launch_fullgrid_n<3>(c, n_walkers, st, c0, c1, sel);
     }
 }
 
@@ -948,10 +1173,10 @@ static EpilogueTables epilogue_tables(const bj_ctx* c) {
 }
 
 static int launch_epilogue(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl, double* parts, int mode, int c0,
-                           int c1, double* sums_io) {
+                           int c1, double* sums_io, Sel sel = Sel{nullptr, nullptr}) {
     epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers), kEpiWalkers * kEpiSlices, 0, st>>>(
         c->cfg, epilogue_tables(c), c->dims, c->d_partial, c->d_coef, c->d_coef_ex, c->cap_walkers, n_walkers, logl,
-        parts, mode, c0, c1, sums_io);
+        parts, mode, c0, c1, sums_io, sel);
     CUDA_TRY(cudaGetLastError());
     return BJ_OK;
 }
@@ -1088,6 +1313,34 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
         rc = run_timemarg(c, n_walkers, st, out_logl_dev);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    } else if (c->kind == KIND_FULLGRID && c->n_levels > 0) {
+        // compressed frequency axes: classify_kernel sorts the walkers into one work list per table (levels of growing
+        // design budget, then the full grid); the bin kernels and the epilogue then run once per list on that list's
+        // table.  Grids are sized for the whole batch; CTAs beyond the end of their list return at once.  The lists are
+        // disjoint, so the passes share the partial-sum buffer.
+        c->last_walkers = n_walkers;
+        CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, (kMaxLevels + 1) * sizeof(int), st));
+        classify_kernel<<<(unsigned)((n_walkers + 3) / 4), 128, 0, st>>>(c->steep, c->cfg.n_ifo, c->d_coef, c->cap_walkers,
+                                                                        n_walkers, c->d_lists, c->d_counts);
+        CUDA_TRY(cudaGetLastError());
+        for (int lv = 0; lv <= c->n_levels; ++lv) {
+            bj_ctx* m = lv < c->n_levels ? c->cmp[lv] : c;
+            if (m != c) {
+                m->d_coef = c->d_coef;
+                m->d_partial = c->d_partial;
+                m->d_coef_ex = nullptr;
+                m->cap_walkers = c->cap_walkers;
+                m->d_gram = c->d_gram;
+                m->d_dd_band = c->d_dd_band;
+            }
+            const Sel sel = {c->d_lists + (size_t)lv * c->cap_walkers, c->d_counts + lv};
+            rc = launch_fullgrid(m, n_walkers, st, 0, m->n_chunks, sel);
+            if (rc) return rc;
+            if (lv == 0) for (int q = 0; q < 8; ++q) c->launch_info[q] = m->launch_info[q];
+            if (lv == c->n_levels) CUDA_TRY(cudaEventRecord(c->ev[2], st));
+            rc = launch_epilogue(m, n_walkers, st, out_logl_dev, out_parts_dev, 0, 0, m->n_chunks, nullptr, sel);
+            if (rc) return rc;
+        }
     } else if (c->kind == KIND_FULLGRID) {
         rc = launch_fullgrid(c, n_walkers, st, 0, c->n_chunks);
         if (rc) return rc;
@@ -1219,6 +1472,27 @@ extern "C" int bj_last_kernel_ms(bj_ctx* c, float* ms3) {
 extern "C" int bj_last_launch_info(bj_ctx* c, int32_t* info8) {
     if (!c || !info8) return fail(BJ_ERR_INVALID, "null argument");
     for (int i = 0; i < 8; ++i) info8[i] = c->launch_info[i];
+    return BJ_OK;
+}
+
+extern "C" int bj_compress_info(bj_ctx* c, int32_t level, int32_t* info4, double* spec4) {
+    if (!c || !info4 || !spec4) return fail(BJ_ERR_INVALID, "null argument");
+    const bool have = level >= 0 && level < c->n_levels;
+    for (int q = 0; q < 4; ++q) { info4[q] = have ? c->cmp_info[level][q] : 0; spec4[q] = have ? c->cmp_spec[level][q] : 0.0; }
+    return BJ_OK;
+}
+
+extern "C" int bj_last_level_counts(bj_ctx* c, int64_t* counts3) {
+    if (!c || !counts3) return fail(BJ_ERR_INVALID, "null argument");
+    for (int q = 0; q <= kMaxLevels; ++q) counts3[q] = 0;
+    if (c->n_levels == 0 || c->last_walkers <= 0) return BJ_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    int h[kMaxLevels + 1];
+    CUDA_TRY(cudaMemcpy(h, c->d_counts, sizeof(h), cudaMemcpyDeviceToHost));
+    // levels that do not exist stay 0; the full grid is always reported last
+    for (int q = 0; q < c->n_levels; ++q) counts3[q] = h[q];
+    counts3[kMaxLevels] = h[c->n_levels];
     return BJ_OK;
 }
 

@@ -287,6 +287,64 @@ __global__ void prologue_extras_kernel(DeviceConfig cfg, ExtrasDims dims, ExtraM
     if (!walker_extras(cfg, dims, em, x + w * ndim, coef_ex, stride, w)) coef[C_VALID * stride + w] = 0.0;
 }
 
+// ---- compressed frequency axes: which table evaluates which walker ----------------------------------------------------
+// A compressed axis (capi.cu: build_compressed_axis) replaces runs of bins by Chebyshev nodes whose spacing is chosen for
+// a DESIGN bound on the phase slope  |d(Phi/2pi)/df| + |tau_i| <= budget(f) = margin t_N(f; mchirp_min) + tau_max.  A
+// context holds up to kMaxLevels such axes with growing budgets, and the full grid.  classify_kernel -- one warp per
+// walker, one lane per check frequency (log-spaced over the band, both ends included) -- evaluates the slope of the
+// walker's own phase series  P = w5 sum_j A_j u^j + L sum_m B_m u^m + L^2 C8 u^3 :
+//     dP/df = [ w5 sum_j A_j (j-5)/3 u^j + sum_m B_m u^m (1 + L m/3) + C8 u^3 (2 L + L^2) ] / f ,
+// and appends the walker to the work list of the first level whose budget it respects everywhere, else (or when its phase
+// is too wide for the binary-angle trick, C_VALID == 2, or anything is NaN) to the list of the full grid.  Every bin
+// kernel then runs once per list, on that list's table (Sel below); walkers that return -inf anyway go to level 0.
+// The order of a list varies from run to run (atomics), the results do not: no kernel mixes walkers.
+constexpr int kSteepChecks = 32;
+constexpr int kMaxLevels = 2;
+struct SteepTable {
+    int n, n_levels;
+    double u[kSteepChecks], L[kSteepChecks], w5[kSteepChecks], inv_f[kSteepChecks];
+    double budget[kMaxLevels][kSteepChecks];
+};
+// work list of one table: idx[0 .. *count) are walker indices (idx == nullptr: all walkers, in order)
+struct Sel {
+    const int* idx;
+    const int* count;
+};
+__global__ void __launch_bounds__(128) classify_kernel(SteepTable tab, int n_ifo, double* __restrict__ coef, long stride,
+                                                       long n_walkers, int* __restrict__ lists, int* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_walkers) return;
+    const int c = lane < tab.n ? lane : 0;
+    const double u = tab.u[c], L = tab.L[c];
+    double up = 1.0, sa = 0.0, sb = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+        sa = fma(coef[(size_t)(C_A0 + j) * stride + w] * ((double)(j - 5) * (1.0 / 3.0)), up, sa);
+        if (j < 7) sb = fma(coef[(size_t)(C_B0 + j) * stride + w] * fma(L, (double)j * (1.0 / 3.0), 1.0), up, sb);
+        up *= u;
+    }
+    const double c8 = coef[(size_t)C_C8 * stride + w];
+    const double slope = tab.inv_f[c] * (tab.w5[c] * sa + sb + c8 * u * u * u * (2.0 * L + L * L));
+    double tmax = 0.0;
+    for (int i = 0; i < n_ifo; ++i) tmax = fmax(tmax, fabs(coef[(size_t)(C_TAU0 + i) * stride + w]));
+    const double need = fabs(slope) + tmax;
+    const double valid = coef[(size_t)C_VALID * stride + w];
+    int level = tab.n_levels;                      // n_levels = the full grid
+    if (valid == 0.0) level = 0;
+    else if (valid == 1.0) {
+        for (int lv = tab.n_levels - 1; lv >= 0; --lv) {
+            const bool bad = lane < tab.n && !(need <= tab.budget[lv][c]);
+            if (!__any_sync(0xffffffffu, bad)) level = lv;
+        }
+    }
+    if (lane == 0) {
+        coef[(size_t)C_STEEP * stride + w] = (double)level;
+        const int pos = atomicAdd(&counts[level], 1);
+        lists[(size_t)level * stride + pos] = (int)w;
+    }
+}
+
 // per-chunk description: records [start, start + len) of the table, all in one (weight band, calibration segment) cell
 struct ChunkDesc {
     int start, len, band, seg;
@@ -421,14 +479,20 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
                                                                  const double* __restrict__ coef, long stride,
                                                                  long n_walkers, double* __restrict__ partial,
                                                                  const double* __restrict__ coef_ex, ExtrasDims dims,
-                                                                 const double* __restrict__ spcal_freqs, int chunk0) {
+                                                                 const double* __restrict__ spcal_freqs, int chunk0,
+                                                                 Sel sel) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileBins * RS * 8);
 
-    const long wi = (long)blockIdx.y * kThreads + threadIdx.x;
-    const long wl = wi < n_walkers ? wi : n_walkers - 1;
+    // work list (Sel): entry -> walker; a CTA beyond the end of the list has nothing to do
+    const long n_sel = sel.idx ? (long)*sel.count : n_walkers;
+    if ((long)blockIdx.y * kThreads >= n_sel) return;
+    const long entry = (long)blockIdx.y * kThreads + threadIdx.x;
+    const bool live = entry < n_sel;
+    const long wl = sel.idx ? (long)sel.idx[live ? entry : n_sel - 1] : (live ? entry : n_sel - 1);
+    const long wi = wl;
 
     WalkerRegs<NIFO, MODEL> w;
 #pragma unroll
@@ -501,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
         }
     }
 
-    if (wi < n_walkers) {
+    if (live) {
         double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
@@ -552,15 +616,19 @@ __global__ void __launch_bounds__(kThreads, 2) fullgrid_window_kernel(const doub
                                                                       long n_walkers, double* __restrict__ partial,
                                                                       const double* __restrict__ coef_ex, ExtrasDims dims,
                                                                       const double* __restrict__ spcal_freqs, int chunk0,
-                                                                      double df) {
+                                                                      double df, Sel sel) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     constexpr int NR = NIFO > 1 ? NIFO - 1 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileBins * RS * 8);
 
-    const long wi = (long)blockIdx.y * kThreads + threadIdx.x;
-    const long wl = wi < n_walkers ? wi : n_walkers - 1;
+    const long n_sel = sel.idx ? (long)*sel.count : n_walkers;
+    if ((long)blockIdx.y * kThreads >= n_sel) return;
+    const long entry = (long)blockIdx.y * kThreads + threadIdx.x;
+    const bool live = entry < n_sel;
+    const long wl = sel.idx ? (long)sel.idx[live ? entry : n_sel - 1] : (live ? entry : n_sel - 1);
+    const long wi = wl;
 
     WalkerRegs<NIFO, MODEL> w;
 #pragma unroll
@@ -708,7 +776,7 @@ __global__ void __launch_bounds__(kThreads, 2) fullgrid_window_kernel(const doub
         }
     }
 
-    if (wi < n_walkers) {
+    if (live) {
         double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
@@ -907,8 +975,11 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 
     const long wi = (long)blockIdx.y * kThreads + threadIdx.x;
     const long wl = wi < n_walkers ? wi : n_walkers - 1;
+    // ROBUST: the walkers this pass replaces -- those the prologue flagged wide-phase
+    bool selected = true;
     if constexpr (ROBUST) {
-        if (!__syncthreads_or(coef[C_VALID * stride + wl] == 2.0)) return;
+        selected = coef[C_VALID * stride + wl] == 2.0;
+        if (!__syncthreads_or(selected)) return;
     }
 
     WalkerRegsM<NIFO, MODEL> w;
@@ -1036,7 +1107,7 @@ __global__ void __launch_bounds__(kThreads, BJ_MIN_CTAS) fullgrid_mixed_kernel(c
 
     // the fix-up pass replaces the sums of the flagged walkers only: every walker is written by exactly one path, so
     // its bits do not depend on which other walkers share its tile
-    if (wi < n_walkers && (!ROBUST || coef[C_VALID * stride + wi] == 2.0)) {
+    if (wi < n_walkers && (!ROBUST || selected)) {
         double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
@@ -1389,7 +1460,8 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
                                                                   const double* __restrict__ coef, long stride,
                                                                   long n_walkers, double* __restrict__ partial,
                                                                   int chunk0, double df,
-                                                                  const double* __restrict__ coef_ex, ExtrasDims dims) {
+                                                                  const double* __restrict__ coef_ex, ExtrasDims dims,
+                                                                  Sel sel) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes, BB = R::kBasisBytes;
     constexpr int kStageBytes = R::kTileBins * (BB + RB);
@@ -1399,8 +1471,13 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const long wi = (long)blockIdx.y * kTileWalkers + warp * 8 + g;
-    const long wl = wi < n_walkers ? wi : n_walkers - 1;
+    // work list (Sel): entry -> walker; a CTA beyond the end of the list has nothing to do
+    const long n_sel = sel.idx ? (long)*sel.count : n_walkers;
+    if ((long)blockIdx.y * kTileWalkers >= n_sel) return;
+    const long entry = (long)blockIdx.y * kTileWalkers + warp * 8 + g;
+    const bool live = entry < n_sel;
+    const long wl = sel.idx ? (long)sel.idx[live ? entry : n_sel - 1] : (live ? entry : n_sel - 1);
+    const long wi = wl;
 
     // A fragments: row g (this lane's walker), columns 4 s + t; the magic constant rides on the constant term
     double afrag[R::kSteps];
@@ -1618,7 +1695,7 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
         zr[i] += __shfl_xor_sync(0xffffffffu, zr[i], 2);
         zi[i] += __shfl_xor_sync(0xffffffffu, zi[i], 2);
     }
-    if (t == 0 && wi < n_walkers) {
+    if (t == 0 && live) {
         double* out = partial + (size_t)chunk_id * (2 * NIFO) * stride + wi;
 #pragma unroll
         for (int i = 0; i < NIFO; ++i) {
@@ -1667,11 +1744,15 @@ __global__ void __launch_bounds__(kEpiWalkers * kEpiSlices)
 epilogue_kernel(DeviceConfig cfg, EpilogueTables tab, ExtrasDims dims, const double* __restrict__ partial,
                 const double* __restrict__ coef, const double* __restrict__ coef_ex, long stride, long n_walkers,
                 double* __restrict__ logl, double* __restrict__ sums, int mode, int chunk_begin, int chunk_end,
-                double* __restrict__ sums_io) {
+                double* __restrict__ sums_io, Sel sel) {
     __shared__ double red[kEpiSlices][2 * BJ_MAX_IFO][kEpiWalkers];
     const int lane_w = threadIdx.x % kEpiWalkers, slice = threadIdx.x / kEpiWalkers;
-    const long w = (long)blockIdx.x * kEpiWalkers + lane_w;
-    const long wc = w < n_walkers ? w : n_walkers - 1;
+    const long n_sel = sel.idx ? (long)*sel.count : n_walkers;
+    if ((long)blockIdx.x * kEpiWalkers >= n_sel) return;
+    const long entry = (long)blockIdx.x * kEpiWalkers + lane_w;
+    const bool live = entry < n_sel;
+    const long w = sel.idx ? (long)sel.idx[live ? entry : n_sel - 1] : (live ? entry : n_sel - 1);
+    const long wc = w;
     const int nifo = cfg.n_ifo;
     // stage 1: slice s adds chunks s, s + kEpiSlices, ... in ascending order (fixed tree: bits do not depend on W);
     // with PSD weights every chunk lies in one band and is scaled by 1 / w_band (detector.py:529)
@@ -1690,7 +1771,7 @@ epilogue_kernel(DeviceConfig cfg, EpilogueTables tab, ExtrasDims dims, const dou
         red[slice][j][lane_w] = acc;
     }
     __syncthreads();
-    if (slice != 0 || w >= n_walkers) return;
+    if (slice != 0 || !live) return;
     if (mode == 1) {
         for (int j = 0; j < 2 * nifo; ++j) {
             double acc = 0.0;

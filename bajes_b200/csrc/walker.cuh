@@ -45,7 +45,10 @@ enum : int {
     // against detector 0, d = tau_{r+1} - tau_0, eps = 2 pi df d:  C_ROT0 + 10 r + {0..3} = cos(a eps) - 1,
     // {4..7} = sin(a eps) for a = 3.5, 4.5, 11.5, 12.5 bins; {8, 9} = cos, -sin of 32 eps (advance per 32-bin step)
     C_ROT0 = 50,
-    C_NUM = C_ROT0 + 10 * (BJ_MAX_IFO - 1)
+    // 1 = the walker's phase slope exceeds the design bound of the compressed frequency axis (kernels.cuh: steep_kernel):
+    // it is evaluated on the full grid instead
+    C_STEEP = C_ROT0 + 10 * (BJ_MAX_IFO - 1),
+    C_NUM
 };
 constexpr int kRotSlots = 10;
 

@@ -13,7 +13,7 @@ from typing import Dict, Optional, Sequence
 
 import numpy as np
 
-BJ_ABI_VERSION = 1
+BJ_ABI_VERSION = 2
 BJ_MAX_IFO = 3
 BJ_MAX_SPCAL = 16
 BJ_MAX_WEIGHTS = 16
@@ -73,7 +73,9 @@ class bj_extras(C.Structure):
     _fields_ = [("nspcal", C.c_int32), ("nweights", C.c_int32),
                 ("spcal_freqs", C.POINTER(C.c_double)), ("len_weights", C.POINTER(C.c_int64)),
                 ("marg_time_shift", C.c_int32), ("reserved", C.c_int32),
-                ("n_full", C.c_int64), ("band_offset", C.c_int64)]
+                ("n_full", C.c_int64), ("band_offset", C.c_int64),
+                ("compress", C.c_int32), ("reserved2", C.c_int32),
+                ("compress_mchirp_min", C.c_double), ("compress_tau_max", C.c_double)]
 
 
 class bj_extra_map(C.Structure):
@@ -135,6 +137,8 @@ EXPORTS = {
     "bj_measure_peak": (C.c_int, [C.c_int, C.c_int, _DP]),
     "bj_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bj_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "bj_compress_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), _DP]),
+    "bj_last_level_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -379,7 +383,10 @@ class Engine:
     # -- constructors --------------------------------------------------------------------------
     @classmethod
     def fullgrid(cls, cfg: bj_config, freqs, datas, psds, spcal_freqs=None, len_weights=None,
-                 marg_time_shift=False, n_full=0, band_offset=0) -> "Engine":
+                 marg_time_shift=False, n_full=0, band_offset=0, compress=None) -> "Engine":
+        """``compress``: None = library default (compressed frequency axis on), False = full grid only, True = on, or
+        a dict ``{"mchirp_min": solar masses, "tau_max": seconds}`` giving the design bounds (include/bajes_b200.h:
+        bj_extras.compress*).  Walkers outside the design are evaluated on the full grid in the same call."""
         lib = load_library()
         freqs = _as_f64(freqs)
         d_ri = [np.ascontiguousarray(np.asarray(d, dtype=np.complex128)).view(np.float64) for d in datas]
@@ -399,9 +406,15 @@ class Engine:
             ex.nweights, ex.len_weights = lw.size, lw.ctypes.data_as(C.POINTER(C.c_int64))
         if marg_time_shift:
             ex.marg_time_shift, ex.n_full, ex.band_offset = 1, int(n_full), int(band_offset)
+        if compress is not None:
+            if isinstance(compress, dict):
+                ex.compress = 1
+                ex.compress_mchirp_min = float(compress.get("mchirp_min", 0.0))
+                ex.compress_tau_max = float(compress.get("tau_max", 0.0))
+            else:
+                ex.compress = 1 if compress else -1
         _check(lib, lib.bj_create_ex(C.byref(h), C.byref(cfg), freqs.size, _ptr(freqs), _ptr_array(d_ri), _ptr_array(p),
-                                     C.byref(ex) if (sf is not None or lw is not None or marg_time_shift) else None),
-               "bj_create_ex")
+                                     C.byref(ex)), "bj_create_ex")
         return cls(h, cfg.n_ifo, "fullgrid", freqs.size)
 
     @classmethod
@@ -501,6 +514,23 @@ class Engine:
         info = (C.c_int32 * 8)()
         _check(self._lib, self._lib.bj_last_launch_info(self._h, info), "bj_last_launch_info")
         return list(info)
+
+    def compress_info(self, level: int = 0) -> Dict[str, object]:
+        """Compressed frequency axis `level` of this context: {"nodes", "kept_bins", "blocks", "nodes_per_block",
+        "mchirp_min", "tau_max", "reach_rad", "margin", "n_bins"}; nodes == 0 when the level does not exist (the context
+        then evaluates the full grid only if level == 0)."""
+        info = (C.c_int32 * 4)()
+        spec = (C.c_double * 4)()
+        _check(self._lib, self._lib.bj_compress_info(self._h, int(level), info, spec), "bj_compress_info")
+        return {"nodes": int(info[0]), "kept_bins": int(info[1]), "blocks": int(info[2]), "nodes_per_block": int(info[3]),
+                "mchirp_min": float(spec[0]), "tau_max": float(spec[1]), "reach_rad": float(spec[2]),
+                "margin": float(spec[3]), "n_bins": int(self.n_bins)}
+
+    def last_level_counts(self):
+        """Walkers of the last call per table: (level 0, level 1, full grid).  Synchronises."""
+        n = (C.c_int64 * 3)()
+        _check(self._lib, self._lib.bj_last_level_counts(self._h, n), "bj_last_level_counts")
+        return tuple(int(v) for v in n)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -45,8 +45,14 @@ class GWLikelihood(Likelihood):
     def __init__(self, ifos, datas, dets, noises, freqs, srate, seglen, approx,
                  nspcal=0, spcal_freqs=None, nweights=0, len_weights=None,
                  marg_phi_ref=False, marg_time_shift=False, roq=None,
-                 device=0, sincos="mufu", **kwargs):
+                 device=0, sincos="mufu", compress=None, **kwargs):
+        """``compress`` (no counterpart in the reference): None = library default (the compressed frequency axis is
+        used where it pays), False = evaluate every bin, or {"mchirp_min": .., "tau_max": ..} = the design bounds of
+        the compression (chirp mass in solar masses, |geocentric delay + time_shift| in s; defaults 0.5 / 0.11).  Points
+        outside the design are evaluated on the full grid in the same call: the option changes speed, never results
+        beyond the parity tolerance."""
         super(GWLikelihood, self).__init__()
+        self.compress = compress
         self.ifos = list(ifos)
         self.dets = dets
         self.roq = roq
@@ -136,7 +142,7 @@ class GWLikelihood(Likelihood):
                                            [self.dets[i].psd for i in ifos],
                                            spcal_freqs=self.spcal_freqs, len_weights=self.len_weights,
                                            marg_time_shift=self.marg_time_shift, n_full=self.Nfr,
-                                           band_offset=self._band_offset)
+                                           band_offset=self._band_offset, compress=getattr(self, "compress", None))
         from .roq import spline_tables
         knots, coefs, tc_min, tc_max = [], [], None, None
         for ifo in ifos:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BJ_ABI_VERSION 1
+#define BJ_ABI_VERSION 2
 #define BJ_MAX_IFO 3            /* detectors fused in one pass of the kernel            */
 #define BJ_MAX_SPCAL 16         /* spectral-calibration nodes per detector               */
 #define BJ_MAX_WEIGHTS 16       /* PSD-weight bands per detector                         */
@@ -139,6 +139,18 @@ typedef struct {
     int32_t reserved;
     int64_t n_full;               /* len(series.freqs): T * srate / 2 + 1                          */
     int64_t band_offset;          /* index of the first in-band bin on that axis                   */
+    /* Compressed frequency axis (no counterpart in the reference: an exact-to-1e-11 regrouping of the bin sum of
+     * detector.py:541).  Runs of bins over which the phase of any walker INSIDE THE DESIGN turns by a bounded amount are
+     * replaced by Chebyshev nodes with pre-summed data weights; the same kernels then evaluate ~10-30x fewer "bins" on
+     * long segments.  Design = bound on the phase slope: chirp mass >= compress_mchirp_min (solar masses) and
+     * |geocentric delay + time_shift| <= compress_tau_max (s).  Walkers outside the design are detected per call and
+     * evaluated on the full grid, so results never leave the parity tolerance; only speed depends on the design.
+     * compress: 0 = default (on, unless BAJES_B200_COMPRESS=0), 1 = on, -1 = off.  Zero / negative bounds = defaults
+     * (0.5 solar masses, 0.11 s).  Ignored with spcal / weights / time marginalisation / sincos fp64 (full grid only). */
+    int32_t compress;
+    int32_t reserved2;
+    double  compress_mchirp_min;
+    double  compress_tau_max;
 } bj_extras;
 
 /* where the per-point values of 'spcal_amp{j}_{ifo}', 'spcal_phi{j}_{ifo}', 'weight{b}_{ifo}' live:
@@ -265,6 +277,15 @@ int bj_measure_peak(int device, int which, double* out);
 int bj_last_kernel_ms(bj_ctx* ctx, float* ms3);
 /* static description of the last launch: grid, block, dynamic smem, bins per chunk, #chunks */
 int bj_last_launch_info(bj_ctx* ctx, int32_t* info8);
+/* Compressed frequency axes of a full-grid context (bj_extras.compress*).  A context holds up to BJ_COMPRESS_LEVELS node
+ * axes of growing design budget (level 0: the design; level 1: |tau| up to max(1.1 s, 2 tau_max), the default time-shift
+ * prior of the reference's pipeline) and the full grid; every call sorts its walkers into the first table that covers them.
+ * info4 = {nodes, nodes that are plain bins, compressed runs, nodes per run} (all 0 when `level` does not exist),
+ * spec4 = {mchirp_min, tau_max, reach in rad, slope margin}. */
+#define BJ_COMPRESS_LEVELS 2
+int bj_compress_info(bj_ctx* ctx, int32_t level, int32_t* info4, double* spec4);
+/* walkers of the last call per table: counts3 = {level 0, level 1, full grid}.  Synchronises the device. */
+int bj_last_level_counts(bj_ctx* ctx, int64_t* counts3);
 
 #ifdef __cplusplus
 }
