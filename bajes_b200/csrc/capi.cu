@@ -84,6 +84,7 @@ struct bj_ctx {
     void* d_rec = nullptr;
     void* d_tile_basis = nullptr; // tables of the tensor-core kernel; null: Horner kernels only
     double grid_df = 0.0;         // bin spacing if the in-band grid is uniform (integer time-delay ramps), else 0
+    double window_df = 0.0;       // bin spacing of the slots the FP64 window covers if they are uniform (fullgrid_window_kernel), else 0
     bool rot = false;             // tile tables in the rotation layout (kernels.cuh: tile_step_rot)
     int n_precise = 0;            // chunks [0, n_precise): the FP64 window (heaviest bins), evaluated by fullgrid_kernel
     double* d_rec64 = nullptr;    // FP64 records of the window's slots [prec_lo, prec_hi)
@@ -260,7 +261,7 @@ struct Layout {
 // the FP64 window kernel evaluates.  For the design PSDs of H1/L1/V1 a share of 0.9 is the band 20-87 Hz: 1.6 % of the
 // bins of a 128 s segment sampled to 4096 Hz.
 static int build_layout(Layout& L, long n, const double* freqs, const bj_extras* ex, const std::vector<double>* binweight,
-                        double prec_share, double prec_frac) {
+                        double prec_share, double prec_frac, long window_limit = -1) {
     const int nsp = ex ? ex->nspcal : 0, nw = ex ? ex->nweights : 0;
     std::vector<int> band(n, 0), seg(n, 0);
     std::vector<double> tt(n, 0.0);
@@ -339,6 +340,13 @@ static int build_layout(Layout& L, long n, const double* freqs, const bj_extras*
         if (best_lo + win > total) best_lo = (total - win) & ~1L;
         L.prec_lo = best_lo;
         L.prec_hi = best_lo + win;
+        if (window_limit >= 0 && L.prec_hi > window_limit) {
+            // compressed axis: the window stays inside the leading run of plain (uniformly spaced) bins
+            L.prec_hi = (window_limit / 256) * 256;
+            if (L.prec_lo > L.prec_hi) L.prec_lo = L.prec_hi;
+            L.prec_lo = (L.prec_lo / 2) * 2;
+            if ((L.prec_hi - L.prec_lo) % 256) L.prec_lo = L.prec_hi - ((L.prec_hi - L.prec_lo) / 256) * 256;
+        }
     }
     std::vector<ChunkDesc> fast;
     long s0 = 0;
@@ -589,13 +597,23 @@ static void adopt_layout(bj_ctx* c, const Layout& L) {
 // The mixed-precision table set of one frequency axis (the full grid, or the compressed node axis): layout, Horner
 // records (fix-up / time marginalisation / amplitude correction), FP64 window, tensor-core tables; uploads them into c.
 static int build_mixed_set(bj_ctx* c, const bj_config* cfg, const Axis& ax, const bj_extras* ex,
-                           const std::vector<double>& bw, const double* eps, bool uniform_ok, bool tm, Layout& L) {
+                           const std::vector<double>& bw, const double* eps, bool uniform_ok, bool tm, Layout& L,
+                           long uniform_prefix = -1, double prefix_df = 0.0) {
     double share = 0.9, frac = 0.08;
     if (const char* ev = getenv("BAJES_B200_PRECISE_SHARE")) share = atof(ev);
     if (const char* ev = getenv("BAJES_B200_PRECISE_FRAC")) frac = atof(ev);
+    if (c->shadow) {
+        // on a compressed axis the plain low-frequency bins are a third of the table, not 2 % of it: the window that holds
+        // 90 % of their weight would double the cost.  16 % of the nodes (profiles/r02_compress_window.txt: worst walker
+        // in 2e6 0.42 tol at +7 % time; 8 %: 0.51, 40 %: 0.35 at +23 %)
+        frac = 0.16;
+        if (const char* ev = getenv("BAJES_B200_CMP_PRECISE_SHARE")) share = atof(ev);
+        if (const char* ev = getenv("BAJES_B200_CMP_PRECISE_FRAC")) frac = atof(ev);
+    }
     if (tm || getenv("BAJES_B200_NO_TC")) frac = 0.0;
-    if (build_layout(L, ax.n, ax.f, ex, &bw, share, frac)) return fail(BJ_ERR_INVALID, "len_weights do not cover the band");
+    if (build_layout(L, ax.n, ax.f, ex, &bw, share, frac, uniform_prefix)) return fail(BJ_ERR_INVALID, "len_weights do not cover the band");
     adopt_layout(c, L);
+    if (uniform_prefix >= 0) c->window_df = prefix_df;
     std::vector<unsigned char> recm;
     int e2 = 0, bad = 0;
     switch (cfg->n_ifo) {
@@ -632,6 +650,7 @@ static int build_mixed_set(bj_ctx* c, const bj_config* cfg, const Axis& ax, cons
             for (long k = 0; k < ax.n && uniform; ++k)
                 uniform = std::fabs(ax.f[k] - (ax.f[0] + (double)k * df)) <= 1e-7 * df;
             if (uniform) c->grid_df = df;
+            if (uniform) c->window_df = df;
         }
         c->rot = c->grid_df > 0.0 && cfg->n_ifo >= 2 && !getenv("BAJES_B200_NO_ROT");
         if (c->rot) c->cfg.grid_df = c->grid_df;
@@ -889,8 +908,11 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
             std::vector<double> nf, nbw, nwt[BJ_MAX_IFO];
             int info[4] = {0, 0, 0, 0};
             build_compressed_axis(ax, cfg->n_ifo, bw, sl, nf, nwt, nbw, info);
-            // worth it only when the node axis is markedly shorter than the grid
-            if ((double)nf.size() > 0.7 * (double)n_bins) break;
+            // worth it only on long axes (a call on a short one is bound by its launches, and a compressed context
+            // launches more of them) and when the node axis is markedly shorter than the grid
+            long min_bins = 65536;
+            if (const char* ev = getenv("BAJES_B200_COMPRESS_MIN_BINS")) min_bins = atol(ev);
+            if (n_bins < min_bins || (double)nf.size() > (double)n_bins / 3.0) break;
             Axis cx;
             cx.n = (long)nf.size();
             cx.f = nf.data();
@@ -906,7 +928,13 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
             m->n_bins = cx.n;
             c->cmp[c->n_levels] = m;
             Layout Lc;
-            rc = build_mixed_set(m, cfg, cx, nullptr, nbw, c->calib, /*uniform_ok=*/false, false, Lc);
+            // the leading run of plain bins is a piece of the (uniform) grid: the FP64 window is placed there and
+            // evaluated by the fast window kernel
+            long prefix = 0;
+            while (prefix < cx.n && prefix < (long)n_bins && nf[prefix] == freqs[prefix]) ++prefix;
+            if (!(c->grid_df > 0.0)) prefix = -1;
+            if (prefix >= 0) for (long q = prefix; q < cx.n; ++q) nbw[q] = 0.0;     // the window is chosen among the plain bins
+            rc = build_mixed_set(m, cfg, cx, nullptr, nbw, c->calib, /*uniform_ok=*/false, false, Lc, prefix, c->grid_df);
             if (rc) { c->n_levels++; bj_destroy(c); return rc; }
             const int q0 = c->n_levels++;
             for (int q = 0; q < 4; ++q) c->cmp_info[q0][q] = info[q];
@@ -1079,12 +1107,12 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
         const int p1 = c1 < c->n_precise ? c1 : c->n_precise;
         const size_t smem64 = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
         dim3 pgrid((unsigned)(p1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
-        if (c->grid_df > 0.0 && !getenv("BAJES_B200_WINDOW_GENERIC")) {
+        if (c->window_df > 0.0 && !getenv("BAJES_B200_WINDOW_GENERIC")) {
             auto pk = fullgrid_window_kernel<NIFO, MODEL, SPCAL>;
             CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
             pk<<<pgrid, kThreads, smem64, st>>>(c->d_rec64 - (size_t)c->prec_lo * RS, c->d_chunks, c->d_coef,
                                                 c->cap_walkers, n_walkers, c->d_partial, c->d_coef_ex, c->dims,
-                                                c->d_spcal_freqs, c0, c->grid_df, sel);
+                                                c->d_spcal_freqs, c0, c->window_df, sel);
         } else {
             auto pk = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, SPCAL>;
             CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
@@ -1472,6 +1500,33 @@ extern "C" int bj_last_kernel_ms(bj_ctx* c, float* ms3) {
 extern "C" int bj_last_launch_info(bj_ctx* c, int32_t* info8) {
     if (!c || !info8) return fail(BJ_ERR_INVALID, "null argument");
     for (int i = 0; i < 8; ++i) info8[i] = c->launch_info[i];
+    return BJ_OK;
+}
+
+// host-only: the node axis build_compressed_axis makes of a weighted frequency axis (no device needed)
+extern "C" int bj_compress_axis_host(int64_t n_bins, const double* freqs, int32_t n_ifo, const double* const* weights_ri,
+                                     int32_t nodes_per_run, double reach_rad, double mchirp_min, double tau_max,
+                                     double margin, int64_t* out_n, double* out_freqs, double* const* out_weights_ri,
+                                     int32_t* info4) {
+    if (n_bins <= 0 || !freqs || !weights_ri || !out_n || !out_freqs || !out_weights_ri || n_ifo < 1 || n_ifo > BJ_MAX_IFO)
+        return fail(BJ_ERR_INVALID, "bad arguments");
+    CompressSpec sp = compress_spec(nullptr);
+    if (nodes_per_run > 0) sp.nodes = std::max(4, std::min(64, (int)nodes_per_run));
+    if (reach_rad > 0.0) sp.reach = reach_rad;
+    if (mchirp_min > 0.0) sp.mchirp_min = mchirp_min;
+    if (tau_max > 0.0) sp.tau_max = tau_max;
+    if (margin > 0.0) sp.margin = margin;
+    Axis ax;
+    ax.n = (long)n_bins;
+    ax.f = freqs;
+    for (int i = 0; i < n_ifo; ++i) ax.w[i] = weights_ri[i];
+    std::vector<double> bw((size_t)n_bins, 1.0), nf, nbw, nwt[BJ_MAX_IFO];
+    int info[4];
+    build_compressed_axis(ax, n_ifo, bw, sp, nf, nwt, nbw, info);
+    *out_n = (int64_t)nf.size();
+    memcpy(out_freqs, nf.data(), nf.size() * sizeof(double));
+    for (int i = 0; i < n_ifo; ++i) memcpy(out_weights_ri[i], nwt[i].data(), nwt[i].size() * sizeof(double));
+    if (info4) for (int q = 0; q < 4; ++q) info4[q] = info[q];
     return BJ_OK;
 }
 

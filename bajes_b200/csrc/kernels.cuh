@@ -317,19 +317,28 @@ __global__ void __launch_bounds__(128) classify_kernel(SteepTable tab, int n_ifo
     if (w >= n_walkers) return;
     const int c = lane < tab.n ? lane : 0;
     const double u = tab.u[c], L = tab.L[c];
+    // all loads first (independent, warp-uniform addresses), then the arithmetic
+    double a[16], b[7], tau[BJ_MAX_IFO];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = coef[(size_t)(C_A0 + j) * stride + w];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) b[j] = coef[(size_t)(C_B0 + j) * stride + w];
+    const double c8 = coef[(size_t)C_C8 * stride + w];
+#pragma unroll
+    for (int i = 0; i < BJ_MAX_IFO; ++i) tau[i] = i < n_ifo ? coef[(size_t)(C_TAU0 + i) * stride + w] : 0.0;
+    const double valid = coef[(size_t)C_VALID * stride + w];
     double up = 1.0, sa = 0.0, sb = 0.0;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 16; ++j) {
-        sa = fma(coef[(size_t)(C_A0 + j) * stride + w] * ((double)(j - 5) * (1.0 / 3.0)), up, sa);
-        if (j < 7) sb = fma(coef[(size_t)(C_B0 + j) * stride + w] * fma(L, (double)j * (1.0 / 3.0), 1.0), up, sb);
+        sa = fma(a[j] * ((double)(j - 5) * (1.0 / 3.0)), up, sa);
+        if (j < 7) sb = fma(b[j] * fma(L, (double)j * (1.0 / 3.0), 1.0), up, sb);
         up *= u;
     }
-    const double c8 = coef[(size_t)C_C8 * stride + w];
     const double slope = tab.inv_f[c] * (tab.w5[c] * sa + sb + c8 * u * u * u * (2.0 * L + L * L));
     double tmax = 0.0;
-    for (int i = 0; i < n_ifo; ++i) tmax = fmax(tmax, fabs(coef[(size_t)(C_TAU0 + i) * stride + w]));
+#pragma unroll
+    for (int i = 0; i < BJ_MAX_IFO; ++i) tmax = fmax(tmax, fabs(tau[i]));
     const double need = fabs(slope) + tmax;
-    const double valid = coef[(size_t)C_VALID * stride + w];
     int level = tab.n_levels;                      // n_levels = the full grid
     if (valid == 0.0) level = 0;
     else if (valid == 1.0) {

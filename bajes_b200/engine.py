@@ -139,6 +139,8 @@ EXPORTS = {
     "bj_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "bj_compress_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), _DP]),
     "bj_last_level_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "bj_compress_axis_host": (C.c_int, [C.c_int64, _DP, C.c_int32, _DPP, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.POINTER(C.c_int64), _DP, _DPP, C.POINTER(C.c_int32)]),
 }
 
 _lib = None
@@ -542,6 +544,24 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def compress_axis(freqs, weights, nodes_per_run=0, reach_rad=0.0, mchirp_min=0.0, tau_max=0.0, margin=0.0):
+    """Host-only mirror of the compressed frequency axis the full-grid context builds (capi.cu: build_compressed_axis):
+    ``weights`` = complex [n_ifo, n_bins] -> (node_freqs [n], node_weights complex [n_ifo, n], info dict).  No GPU needed."""
+    lib = load_library()
+    f = _as_f64(freqs)
+    w = [np.ascontiguousarray(np.asarray(x, dtype=np.complex128)).view(np.float64) for x in np.atleast_2d(weights)]
+    out_f = np.empty(f.size, dtype=np.float64)
+    out_w = [np.empty(2 * f.size, dtype=np.float64) for _ in w]
+    n = C.c_int64()
+    info = (C.c_int32 * 4)()
+    _check(lib, lib.bj_compress_axis_host(f.size, _ptr(f), len(w), _ptr_array(w), int(nodes_per_run), float(reach_rad),
+                                          float(mchirp_min), float(tau_max), float(margin), C.byref(n), _ptr(out_f),
+                                          _ptr_array(out_w), info), "bj_compress_axis_host")
+    m = int(n.value)
+    return (out_f[:m].copy(), np.stack([x[:2 * m].view(np.complex128) for x in out_w]),
+            {"nodes": int(info[0]), "kept_bins": int(info[1]), "blocks": int(info[2]), "nodes_per_block": int(info[3])})
 
 
 def polarizations(approx: str, seglen: float, freqs, x: np.ndarray, pmap: ParamMap, centre_shift=True, device=0):

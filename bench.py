@@ -5,8 +5,12 @@ bench.py -- headline benchmark of the batched GW likelihood (BASELINE.json metri
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--secondary all|none|C1,C3,..]
 
 HEADLINE (config C2: TaylorF2 3.5PN + 6PN tides BNS, H1/L1/V1, 128 s, 20-4096 Hz = 521 729 bins, 4096 walkers per GPU).
-A "step" is ONE batched ``GWLikelihood.log_like`` over the walker batch: prologue, FP64 window kernel (the heaviest
-1.6 % of the bins), fused tensor-core kernel (+ its early-exit fix-up launch), epilogue.
+A "step" is ONE batched ``GWLikelihood.log_like`` over the walker batch: prologue, classification of the walkers by
+phase slope, and per frequency table (compressed axes of DESIGN.md section 4.9, then the full grid) FP64 window kernel,
+fused tensor-core kernel, epilogue.  The metric counts the reference's bins (521 729 per walker); the default path
+evaluates them through ~22 600 Chebyshev nodes whose pre-summed data weights reproduce the bin sum to ~1e-11 (parity
+against the oracle and the all-FP64 full-grid kernel is part of the line); ``full_grid`` is the same step with every
+bin evaluated.
 
   value     walker*bins/s over all ranks, inputs resident in HBM, timed per step with CUDA events on the
             launching stream (L2 flushed between steps, outside the timed events), max over ranks
@@ -16,6 +20,9 @@ A "step" is ONE batched ``GWLikelihood.log_like`` over the walker batch: prologu
             (peer memory, flag-ordered) -> D2H
   strong    (N > 1) the same two numbers with the TOTAL batch fixed at 4096 walkers (a sampler's ensemble does not grow
             with the GPU count)
+  full_grid the same step with the compressed frequency axis switched off (every bin evaluated: the round-1 / round-2a
+            product path, still the path of contexts with calibration envelopes, PSD weights, short segments, and of
+            every walker outside the design of the compression), with its own roofline
   roofline  the fused kernel against the slower of the FP64-issue and SFU-issue rooflines (HBM is listed too, it is far
             from binding): achieved = algorithmic instructions per walker*bin x units / kernel
             time; peaks = DFMA and MUFU issue rates measured live on this GPU
@@ -52,7 +59,12 @@ METRIC = "likelihood evals/sec (walkers x freq bins / s)"
 UNIT = "walker*bins/s"
 DTYPE = ("f64 phase (DMMA) -> u32 binary angle -> f32 phasor (1 MUFU pair per bin, rotated to the other detectors) + f32 MAC "
          "-> f64 accumulate every 8 bins; all-f64 in the heaviest 1.6% of the bins")
+DTYPE_COMPRESSED = ("f64 data weights pre-summed onto Chebyshev nodes (long double) -> f64 phase (DMMA) -> u32 binary angle -> f32 "
+                    "phasor (MUFU pair per node and detector) + f32 MAC -> f64 accumulate every 8 nodes; all-f64 in the heaviest "
+                    "16% of the nodes")
 LAUNCHES_PER_STEP = 5      # prologue, FP64 window, fused tile kernel, fix-up (early exit), epilogue
+# compressed axes: prologue, classify, {window, tile, epilogue} per level (2), {window, tile, fix-up, epilogue} full grid
+LAUNCHES_PER_STEP_COMPRESSED = 12
 
 
 # Algorithmic instruction counts per walker*bin of the fused kernel:
@@ -83,6 +95,7 @@ def parse():
     ap.add_argument("--cpu-points", type=int, default=0, help="points of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", default="all", help="all | none | comma list of C1,C3,C4,C5")
+    ap.add_argument("--no-compress", action="store_true", help="evaluate every bin (compressed frequency axis off)")
     return ap.parse_args()
 
 
@@ -321,6 +334,65 @@ def make_evaluator(c, like, names, const, capacity):
 
     return ShardedEvaluator(lambda Xs: like.log_like_batch(Xs, names, const), ndim=len(names), device=c.dev,
                             local_eval_device=eval_dev, capacity=capacity)
+
+
+def build_roofline(cfg, args, nifo, W, units, info, k_s, peaks, pk, tensor_core, rot, traffic_key, comp):
+    """Roofline object of one step.  `units` = walker x (bins or nodes) the kernels evaluate; comp = None for the full grid,
+    else {"counts": walkers per table, "nodes": nodes per level, "n_bins": ..} for a context with compressed axes."""
+    fp64_pu, sfu_pu = instr_per_unit(cfg["approx"], nifo, args.sincos, tensor_core, rot)
+    if comp:
+        fp64_pu += nifo                    # non-uniform axis: the time-delay ramp is one DFMA per node and detector
+    n_wtiles = (W + 63) // 64 if tensor_core else (W + 127) // 128
+    # algorithmic bytes: every walker tile streams the static table once; coefficient block; partial sums
+    if comp:
+        tiles = [(comp["counts"][lv] + 63) // 64 for lv in range(3)]
+        alg_bytes = (tiles[0] * comp["nodes"][0] + tiles[1] * comp["nodes"][1] + tiles[2] * comp["n_bins"]) * info[6] * 8 \
+            + W * 71 * 8 + info[5] * 2 * nifo * W * 8
+    else:
+        alg_bytes = n_wtiles * (units // max(1, W)) * info[6] * 8 + W * 71 * 8 + info[5] * 2 * nifo * W * 8
+    traffic, traffic_note = measured_traffic(traffic_key)
+    lines = {"fp64": (fp64_pu, peaks["dfma"], "GDFMA/s"), "sfu": (sfu_pu, peaks["mufu"], "GMUFU/s")}
+    # the limiting roofline of the two the north star names = the one that needs the longer time
+    bound = max(lines, key=lambda k: lines[k][0] / lines[k][1])
+    ipu, peak, unit = lines[bound]
+    achieved = units * ipu / k_s
+    other = "sfu" if bound == "fp64" else "fp64"
+    K = 12 if cfg["approx"] == "TaylorF2_3.5PN" else 28
+    if comp:
+        kernel = ("classify_kernel + per table {fullgrid_window_kernel (FP64, heaviest nodes) + fullgrid_tile_kernel<%d ifo, %s, "
+                  "%s, non-uniform axis> + epilogue_kernel}: the time between the prologue's event and the last table's "
+                  "epilogue" % (nifo, cfg["approx"], args.sincos))
+        note = ("executed work: a call on ~22 600 nodes is no longer one long kernel -- fixed costs (classification, short "
+                "chunks of 256 nodes per CTA, one pass per table) and the FP64 window (16 % of the nodes at ~2.2x the cost per "
+                "node) share the interval; the full-grid kernel's own fraction is in full_grid.roofline")
+        units_note = ("walker x node pairs actually evaluated: %s walkers on the level-0 / level-1 / full-grid tables of %d / "
+                      "%d / %d nodes; the metric's %d walker x bins are %.1f times as many"
+                      % (comp["counts"], comp["nodes"][0], comp["nodes"][1], comp["n_bins"], W * comp["n_bins"],
+                         W * comp["n_bins"] / max(1, units)))
+    else:
+        kernel = ("fullgrid_window_kernel (FP64, heaviest bins) + fullgrid_%s_kernel<%d ifo, %s, %s%s>: the time between the "
+                  "prologue's and the epilogue's events"
+                  % ("tile" if tensor_core else "mixed" if args.sincos != "fp64" else "fp64", nifo, cfg["approx"], args.sincos,
+                     ", rotated detectors" if rot else ""))
+        note = ("what limits this kernel is neither pipe but instruction issue / register-operand bandwidth (DESIGN.md "
+                "section 4.1): with one MUFU pair per bin the SFU line no longer measures it; the FP64 line (12 of its 13.9 "
+                "FMAs per unit run as DMMA.8x8x4) is the larger of the two the north star names")
+        units_note = "walker x bins"
+    return {"bound": bound, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": unit,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "instr_per_unit": ipu,
+            "units_per_launch": units, "units": units_note, "kernel_ms": k_s * 1e3, "kernel": kernel,
+            "peak_source": "measured live by bj_measure_peak (register-resident DFMA / MUFU chains); "
+                           "MEASURED_PEAKS.json has no FP64 or SFU figure",
+            "note": note,
+            other: {"instr_per_unit": lines[other][0], "achieved": units * lines[other][0] / k_s / 1e9,
+                    "peak": lines[other][1] / 1e9, "unit": lines[other][2],
+                    "frac": units * lines[other][0] / k_s / lines[other][1]},
+            "tensor": ({"achieved": units * 2 * K / k_s / 1e12, "peak": 2 * peaks["dfma"] / 1e12,
+                        "unit": "TFLOP/s (FP64, DMMA)", "frac": units * K / k_s / peaks["dfma"]}
+                       if tensor_core else None),
+            "hbm": {"achieved": alg_bytes / k_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": alg_bytes / k_s / 1e9 / peaks["hbm"], "algorithmic_bytes": alg_bytes,
+                    "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in pk else "fallback"}}
 
 
 def port_parity(port_like, got, X, names, const, n):
@@ -619,8 +691,11 @@ def main():
     # ---- set-up (untimed): synthetic injection built with the product classes, likelihood on this GPU ------
     cl = syn.product_classes()
     net = syn.build_network(cfg, cl)
-    like = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], device=local, sincos=args.sincos)
+    like = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], device=local, sincos=args.sincos,
+                        compress=False if args.no_compress else None)
     assert like.engine.n_bins == nb
+    cinfo = [like.engine.compress_info(lv) for lv in range(2)]
+    compressed = cinfo[0]["nodes"] > 0
     names, const = syn.WALKER_NAMES, syn.constants(cfg)
     Xall, _ = syn.draw_walkers(cfg, W * world, 5, "narrow")
     Xmine = np.ascontiguousarray(Xall[rank * W:(rank + 1) * W])
@@ -671,6 +746,56 @@ def main():
         dist.all_gather_into_tensor(per_rank_all, per_rank)
     per_rank_all = per_rank_all.cpu().numpy().round(4).tolist()
     total_s = float(total_ms.item()) * 1e-3
+    level_counts = like.engine.last_level_counts() if compressed else None
+
+    # ---- the same step with every bin evaluated (compressed axis off), device resident + host pointers (rank-local) ----
+    full_grid = None
+    if compressed:
+        like_full = GWLikelihood(*net, cfg["srate"], cfg["seglen"], cfg["approx"], device=local, sincos=args.sincos,
+                                 compress=False)
+        shf = DeviceShardedLikelihood(like_full, names, const)
+        outf_dev = torch.empty(W, dtype=torch.float64, device=dev)
+        fk = []
+
+        def step_full():
+            shf.evaluate_local(x_dev, outf_dev)
+
+        for _ in range(3):
+            step_full()
+        fms = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_full()
+            b.record()
+            b.synchronize()
+            fms.append(a.elapsed_time(b))
+            fk.append(like_full.engine.last_kernel_ms()[1])
+        full_ms = max_over_ranks(c, float(np.mean(fms)))
+        d = (out_dev - outf_dev).abs() / (1e-6 * outf_dev.abs() + 1e-4)
+        d = torch.where(torch.isfinite(outf_dev), d, torch.zeros_like(d))
+        assert bool(torch.equal(torch.isfinite(out_dev), torch.isfinite(outf_dev)))
+        full_grid = {"value": W * world * nb / (full_ms * 1e-3), "unit": UNIT, "ms_per_step": full_ms,
+                     "kernel_ms": float(np.mean(fk)), "evals_per_s": W * world / (full_ms * 1e-3),
+                     "compressed_vs_full_grid_max_err_over_tol": float(d.max().item()),
+                     "dtype": DTYPE}
+        fpm = like_full.param_map(names, const)
+        flib = engine.load_library()
+
+        def step_full_host():
+            rc = flib.bj_loglike(like_full.engine._h, C.cast(x_pin.data_ptr(), C.POINTER(C.c_double)), W, len(names),
+                                 C.byref(fpm.c), C.cast(out_pin.data_ptr(), C.POINTER(C.c_double)))
+            assert rc == 0, flib.bj_last_error()
+
+        if world == 1:
+            hms = wall(step_full_host, args.steps, 3)
+            full_grid["e2e"] = {"value": W * nb / (hms * 1e-3), "unit": UNIT, "ms_per_step": hms,
+                                "h2d_bytes_per_step": int(Xmine.nbytes), "d2h_bytes_per_step": int(W * 8),
+                                "path": "bj_loglike (host pointers)"}
+        full_info = like_full.engine.last_launch_info()
+        full_kernel_s = float(np.mean(fk)) * 1e-3
+        like_full.engine.close()
 
     # ---- end-to-end through the public API, host buffers in / out inside the timed region ----------------------
     pmap = like.param_map(names, const)
@@ -765,44 +890,22 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------
-    units_per_launch = W * nb
     info = like.engine.last_launch_info()
     tensor_core = info[2] == 256           # fullgrid_tile_kernel: 256 threads = 64 walkers per CTA
     rot = tensor_core and nifo > 1 and not os.environ.get("BAJES_B200_NO_ROT")
-    fp64_pu, sfu_pu = instr_per_unit(cfg["approx"], nifo, args.sincos, tensor_core, rot)
     k_s = float(np.mean(kern_ms)) * 1e-3
-    n_wtiles = (W + 63) // 64 if tensor_core else (W + 127) // 128
-    # algorithmic bytes: every walker tile streams the static table once; coefficient block; partial sums
-    alg_bytes = n_wtiles * nb * info[6] * 8 + W * 70 * 8 + info[5] * 2 * nifo * W * 8
-    traffic, traffic_note = measured_traffic(args.config + ":" + args.sincos)
-    lines = {"fp64": (fp64_pu, peaks["dfma"], "GDFMA/s"), "sfu": (sfu_pu, peaks["mufu"], "GMUFU/s")}
-    # the limiting roofline of the two the north star names = the one that needs the longer time
-    bound = max(lines, key=lambda k: lines[k][0] / lines[k][1])
-    ipu, peak, unit = lines[bound]
-    achieved = units_per_launch * ipu / k_s
-    other = "sfu" if bound == "fp64" else "fp64"
-    K = 12 if cfg["approx"] == "TaylorF2_3.5PN" else 28
-    roofline = {"bound": bound, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": unit,
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "instr_per_unit": ipu,
-                "units_per_launch": units_per_launch, "kernel_ms": k_s * 1e3,
-                "kernel": "fullgrid_window_kernel (FP64, heaviest bins) + fullgrid_%s_kernel<%d ifo, %s, %s%s>: the time between "
-                          "the prologue's and the epilogue's events" % (
-                              "tile" if tensor_core else "mixed" if args.sincos != "fp64" else "fp64", nifo, cfg["approx"],
-                              args.sincos, ", rotated detectors" if rot else ""),
-                "peak_source": "measured live by bj_measure_peak (register-resident DFMA / MUFU chains); "
-                               "MEASURED_PEAKS.json has no FP64 or SFU figure",
-                "note": "what limits this kernel is neither pipe but instruction issue / register-operand bandwidth "
-                        "(DESIGN.md section 4.1): with one MUFU pair per bin the SFU line no longer measures it; the FP64 line "
-                        "(12 of its 13.9 FMAs per unit run as DMMA.8x8x4) is the larger of the two the north star names",
-                other: {"instr_per_unit": lines[other][0], "achieved": units_per_launch * lines[other][0] / k_s / 1e9,
-                        "peak": lines[other][1] / 1e9, "unit": lines[other][2],
-                        "frac": units_per_launch * lines[other][0] / k_s / lines[other][1]},
-                "tensor": ({"achieved": units_per_launch * 2 * K / k_s / 1e12, "peak": 2 * peaks["dfma"] / 1e12,
-                            "unit": "TFLOP/s (FP64, DMMA)", "frac": units_per_launch * K / k_s / peaks["dfma"]}
-                           if tensor_core else None),
-                "hbm": {"achieved": alg_bytes / k_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": alg_bytes / k_s / 1e9 / peaks["hbm"], "algorithmic_bytes": alg_bytes,
-                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in pk else "fallback"}}
+    if compressed:
+        # the full-grid step has its own roofline; the compressed step is measured on the units it EXECUTES
+        full_grid["roofline"] = build_roofline(cfg, args, nifo, W, W * nb, full_info, full_kernel_s, peaks, pk, True, rot,
+                                               args.config + ":" + args.sincos, None)
+        nodes = [ci["nodes"] for ci in cinfo]
+        units = level_counts[0] * nodes[0] + level_counts[1] * nodes[1] + level_counts[2] * nb
+        roofline = build_roofline(cfg, args, nifo, W, units, info, k_s, peaks, pk, tensor_core, False,
+                                  args.config + ":" + args.sincos + ":compressed",
+                                  {"counts": list(level_counts), "nodes": nodes, "n_bins": nb})
+    else:
+        roofline = build_roofline(cfg, args, nifo, W, W * nb, info, k_s, peaks, pk, tensor_core, rot,
+                                  args.config + ":" + args.sincos, None)
 
     value = W * world * nb * args.steps / total_s
     e2e_value = W * world * nb * args.steps / e2e_s
@@ -824,14 +927,23 @@ def main():
         tol = 1e-6 * np.abs(ref) + 1e-4
         cpu["parity_max_err_over_tol"] = float(np.max(np.abs(mine - ref) / tol))
 
+    wl = workload(cfg, args, W)
+    if compressed:
+        wl["frequency_axis"] = ("compressed (default): %d bins -> %d Chebyshev nodes for walkers with chirp mass >= %.2f and "
+                                "|delay + time_shift| <= %.2f s (level 1: %d nodes up to %.2f s; outside: every bin); all %d "
+                                "walkers of this batch: %s on level 0 / level 1 / full grid.  `value` counts the reference's "
+                                "bins; full_grid is the same step with every bin evaluated"
+                                % (nb, cinfo[0]["nodes"], cinfo[0]["mchirp_min"], cinfo[0]["tau_max"], cinfo[1]["nodes"],
+                                   cinfo[1]["tau_max"], W, list(level_counts)))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE if args.sincos != "fp64" else "f64", "data": "synthetic",
-            "config": workload(cfg, args, W), "evals_per_s": value / nb,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.sincos == "fp64" else DTYPE_COMPRESSED if compressed else DTYPE, "data": "synthetic",
+            "config": wl, "evals_per_s": value / nb, "full_grid": full_grid,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "path": e2e_path},
             "strong_scaling": strong,
-            "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "gpu_launches": (LAUNCHES_PER_STEP_COMPRESSED if compressed else LAUNCHES_PER_STEP) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
             "parity_max_err_over_tol": None if cpu is None else cpu["parity_max_err_over_tol"],
             "sincos": args.sincos, "wall_s_timed_region": t_wall,
             "per_rank_ms": {"step_and_fused_kernel": per_rank_all},

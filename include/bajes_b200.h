@@ -284,6 +284,14 @@ int bj_last_launch_info(bj_ctx* ctx, int32_t* info8);
  * spec4 = {mchirp_min, tau_max, reach in rad, slope margin}. */
 #define BJ_COMPRESS_LEVELS 2
 int bj_compress_info(bj_ctx* ctx, int32_t level, int32_t* info4, double* spec4);
+/* Host-only (no device needed): the node axis made of a weighted frequency axis -- weights_ri[i] = interleaved (re, im)
+ * per bin and detector.  out_freqs / out_weights_ri[i] must hold n_bins (2 n_bins) doubles; *out_n = number of nodes.
+ * Non-positive nodes_per_run / reach_rad / mchirp_min / tau_max / margin = the library defaults (32, 10, 0.5, 0.11, 1.3).
+ * For any g(f) whose phase slope respects the design, sum_j W_j g(f_j) reproduces sum_k w_k g(f_k) to ~1e-11 of
+ * sum_k |w_k g(f_k)| (tests/test_compress_host.py). */
+int bj_compress_axis_host(int64_t n_bins, const double* freqs, int32_t n_ifo, const double* const* weights_ri,
+                          int32_t nodes_per_run, double reach_rad, double mchirp_min, double tau_max, double margin,
+                          int64_t* out_n, double* out_freqs, double* const* out_weights_ri, int32_t* info4);
 /* walkers of the last call per table: counts3 = {level 0, level 1, full grid}.  Synchronises the device. */
 int bj_last_level_counts(bj_ctx* ctx, int64_t* counts3);
 
