@@ -1768,6 +1768,8 @@ epilogue_kernel(DeviceConfig cfg, EpilogueTables tab, ExtrasDims dims, const dou
     for (int j = 0; j < 2 * nifo; ++j) {
         double acc = 0.0;
         if (mode != 2) {
+            // (the adds stay in ascending chunk order; unrolling only lets the loads of four chunks fly together)
+#pragma unroll 4
             for (int ch = chunk_begin + slice; ch < chunk_end; ch += kEpiSlices) {
                 double v = partial[((size_t)ch * (2 * nifo) + j) * stride + wc];
                 if (dims.nweights > 0)
