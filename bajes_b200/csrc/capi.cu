@@ -90,6 +90,8 @@ struct bj_ctx {
     double* d_rec64 = nullptr;    // FP64 records of the window's slots [prec_lo, prec_hi)
     long prec_lo = 0, prec_hi = 0;
     void* d_tile_data = nullptr;
+    void* d_tile_data_plain = nullptr;   // the same records in the per-detector layout (contexts with compressed axes: launch_multi)
+    int table_exp = 0;                   // 2^-e scale of the mixed-precision tables
     double* d_freqs = nullptr;
     double* d_gram = nullptr;
     int bins_per_chunk = 0;
@@ -626,6 +628,7 @@ static int build_mixed_set(bj_ctx* c, const bj_config* cfg, const Axis& ax, cons
     const double ar = 1.0 + eps[0], ai = -eps[1];
     const double den = ar * ar + ai * ai;
     const double sc = std::ldexp(1.0, e2);
+    c->table_exp = e2;
     c->cfg.dh_fix_re = sc * ar / den;
     c->cfg.dh_fix_im = -sc * ai / den;
     if (c->n_precise > 0) {
@@ -896,7 +899,7 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
 
     // ---- compressed frequency axes (mixed-precision modes, tensor-core tables, no extras, no time marginalisation) ----
     CompressSpec sp = compress_spec(ex);
-    if (sp.on && cfg->sincos != BJ_SINCOS_FP64 && c->d_tile_basis && nsp == 0 && nw == 0 && !tm) {
+    if (sp.on && cfg->sincos != BJ_SINCOS_FP64 && c->d_tile_basis && c->grid_df > 0.0 && nsp == 0 && nw == 0 && !tm) {
         // level 0: the design; level 1: time shifts up to ~1 s (the default prior of the reference's pipeline,
         // pipe/scripts/bajes_pipe:526) -- samplers start there and end in level 0
         double taus[kMaxLevels] = {sp.tau_max, std::fmax(1.1, 2.0 * sp.tau_max)};
@@ -943,6 +946,17 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
                 const double f = freqs[0] * std::pow(freqs[n_bins - 1] / freqs[0], (double)q / (double)(kSteepChecks - 1));
                 c->steep.budget[q0][q] = design_budget(sl, f);
             }
+        }
+        if (c->n_levels > 0 && c->rot) {
+            // launch_multi evaluates every table with the per-detector record layout: a second copy of the grid's data
+            // records (the rotation layout interleaves the two rotated detectors)
+            std::vector<unsigned char> rect;
+            std::vector<double> basis;
+            if (cfg->approx == BJ_APPROX_TAYLORF2_35PN) build_records_tile<MODEL_35>(basis, rect, L, ax, cfg->seglen, cfg->n_ifo, c->table_exp, false);
+            else                                        build_records_tile<MODEL_GENERIC>(basis, rect, L, ax, cfg->seglen, cfg->n_ifo, c->table_exp, false);
+            cudaError_t et = cudaMalloc(&c->d_tile_data_plain, rect.size());
+            if (et == cudaSuccess) et = cudaMemcpy(c->d_tile_data_plain, rect.data(), rect.size(), cudaMemcpyHostToDevice);
+            if (et != cudaSuccess) { bj_destroy(c); return fail(BJ_ERR_CUDA, "uploading the per-detector data records failed: %s", cudaGetErrorString(et)); }
         }
         if (c->n_levels > 0) {
             // check frequencies of classify_kernel: log-spaced over the band, both ends included
@@ -991,6 +1005,7 @@ extern "C" int bj_destroy(bj_ctx* c) {
     cudaFree(c->d_rec);
     cudaFree(c->d_tile_basis);
     cudaFree(c->d_tile_data);
+    cudaFree(c->d_tile_data_plain);
     cudaFree(c->d_rec64);
     cudaFree(c->d_freqs);
     cudaFree(c->d_gram);
@@ -1112,7 +1127,7 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
             CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
             pk<<<pgrid, kThreads, smem64, st>>>(c->d_rec64 - (size_t)c->prec_lo * RS, c->d_chunks, c->d_coef,
                                                 c->cap_walkers, n_walkers, c->d_partial, c->d_coef_ex, c->dims,
-                                                c->d_spcal_freqs, c0, c->window_df, sel);
+                                                c->d_spcal_freqs, c0, c->window_df, sel, MultiTable{});
         } else {
             auto pk = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, SPCAL>;
             CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
@@ -1142,7 +1157,7 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
         tkern<<<tgrid, kTileThreads, smem_t, st>>>((const unsigned char*)c->d_tile_basis, (const unsigned char*)c->d_tile_data,
                                                    (const unsigned char*)c->d_rec, RB, c->d_chunks, c->d_coef,
                                                    c->cap_walkers, n_walkers, c->d_partial, c0, c->grid_df,
-                                                   c->d_coef_ex, c->dims, sel);
+                                                   c->d_coef_ex, c->dims, sel, MultiTable{});
         note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1204,9 +1219,100 @@ static int launch_epilogue(bj_ctx* c, long n_walkers, cudaStream_t st, double* l
                            int c1, double* sums_io, Sel sel = Sel{nullptr, nullptr}) {
     epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers), kEpiWalkers * kEpiSlices, 0, st>>>(
         c->cfg, epilogue_tables(c), c->dims, c->d_partial, c->d_coef, c->d_coef_ex, c->cap_walkers, n_walkers, logl,
-        parts, mode, c0, c1, sums_io, sel);
+        parts, mode, c0, c1, sums_io, sel, MultiTable{});
     CUDA_TRY(cudaGetLastError());
     return BJ_OK;
+}
+
+// ---- contexts with compressed axes: ONE launch per kernel type over all tables (kernels.cuh: MultiTable) -----------------
+static MultiTable multi_table(const bj_ctx* c) {
+    MultiTable mt;
+    memset(&mt, 0, sizeof(mt));
+    mt.n = c->n_levels + 1;
+    mt.list_stride = c->cap_walkers;
+    mt.lists = c->d_lists;
+    mt.counts = c->d_counts;
+    for (int lv = 0; lv <= c->n_levels; ++lv) {
+        const bj_ctx* m = lv < c->n_levels ? c->cmp[lv] : c;
+        TableRef& T = mt.t[lv];
+        T.basis = (const unsigned char*)m->d_tile_basis;
+        T.data = (const unsigned char*)(m->d_tile_data_plain ? m->d_tile_data_plain : m->d_tile_data);
+        T.rec_ul = (const unsigned char*)m->d_rec;
+        T.rec64 = m->d_rec64 ? m->d_rec64 - (size_t)m->prec_lo * (4 + 2 * c->cfg.n_ifo) : nullptr;
+        T.chunks = m->d_chunks;
+        T.n_chunks = m->n_chunks;
+        T.n_precise = m->n_precise;
+        T.dh_fix_re = m->cfg.dh_fix_re;
+        T.dh_fix_im = m->cfg.dh_fix_im;
+    }
+    return mt;
+}
+
+template <int NIFO, int MODEL, int SC>
+static int launch_multi(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl, double* parts) {
+    const MultiTable mt = multi_table(c);
+    constexpr int RB = RecM<NIFO>::kBytes;
+    constexpr int RS = Rec<NIFO>::kDoubles;
+    int max_precise = 0, max_fast = 0;
+    for (int lv = 0; lv < mt.n; ++lv) {
+        max_precise = std::max(max_precise, mt.t[lv].n_precise);
+        max_fast = std::max(max_fast, mt.t[lv].n_chunks - mt.t[lv].n_precise);
+    }
+    const Sel none = {nullptr, nullptr};
+    if (max_precise > 0) {
+        const size_t smem64 = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
+        auto pk = fullgrid_window_kernel<NIFO, MODEL, false>;
+        CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+        dim3 pgrid((unsigned)max_precise, (unsigned)((n_walkers + kThreads - 1) / kThreads + mt.n - 1));
+        pk<<<pgrid, kThreads, smem64, st>>>(nullptr, nullptr, c->d_coef, c->cap_walkers, n_walkers, c->d_partial, nullptr,
+                                            c->dims, nullptr, 0, c->grid_df, none, mt);
+        CUDA_TRY(cudaGetLastError());
+    }
+    {
+        // the non-uniform-axis instantiation serves every table, the full grid included (FP64 ramp per node and detector)
+        constexpr int RT = TileRec<MODEL>::kBasisBytes + TileRec<MODEL>::kDataBytes;
+        const size_t smem_t = (size_t)kStagesT * TileRec<MODEL>::kTileBins * RT + kStagesT * sizeof(uint64_t);
+        auto tkern = fullgrid_tile_kernel<NIFO, MODEL, SC, false, false, false>;
+        CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        dim3 tgrid((unsigned)max_fast, (unsigned)((n_walkers + kTileWalkers - 1) / kTileWalkers + mt.n - 1));
+        tkern<<<tgrid, kTileThreads, smem_t, st>>>(nullptr, nullptr, nullptr, RB, nullptr, c->d_coef, c->cap_walkers, n_walkers,
+                                                   c->d_partial, 0, 0.0, nullptr, c->dims, none, mt);
+        CUDA_TRY(cudaGetLastError());
+        note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
+    }
+    {
+        // wide-phase fix-up on the full grid (classify_kernel sends such walkers there): early exit unless one is flagged
+        const size_t smem = (size_t)kStages * kTileBins * RB + kStages * sizeof(uint64_t);
+        auto fixup = fullgrid_mixed_kernel<NIFO, MODEL, SC, true, false>;
+        CUDA_TRY(cudaFuncSetAttribute(fixup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)(c->n_chunks - c->n_precise), (unsigned)((n_walkers + kThreads - 1) / kThreads));
+        fixup<<<grid, kThreads, smem, st>>>((const unsigned char*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
+                                            c->d_partial, nullptr, c->dims, c->n_precise);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[2], st));
+    epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers + mt.n - 1), kEpiWalkers * kEpiSlices, 0, st>>>(
+        c->cfg, epilogue_tables(c), c->dims, c->d_partial, c->d_coef, nullptr, c->cap_walkers, n_walkers, logl, parts, 0, 0, 0,
+        nullptr, none, mt);
+    CUDA_TRY(cudaGetLastError());
+    return BJ_OK;
+}
+template <int NIFO, int MODEL>
+static int launch_multi_s(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl, double* parts) {
+    if (c->sincos == BJ_SINCOS_MUFU) return launch_multi<NIFO, MODEL, BJ_SINCOS_MUFU>(c, n_walkers, st, logl, parts);
+    return launch_multi<NIFO, MODEL, BJ_SINCOS_POLY32>(c, n_walkers, st, logl, parts);
+}
+template <int NIFO>
+static int launch_multi_m(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl, double* parts) {
+    if (c->cfg.approx == BJ_APPROX_TAYLORF2_35PN) return launch_multi_s<NIFO, MODEL_35>(c, n_walkers, st, logl, parts);
+    return launch_multi_s<NIFO, MODEL_GENERIC>(c, n_walkers, st, logl, parts);
+}
+static int launch_multi_n(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl, double* parts) {
+    switch (c->cfg.n_ifo) {
+        case 1: return launch_multi_m<1>(c, n_walkers, st, logl, parts);
+        case 2: return launch_multi_m<2>(c, n_walkers, st, logl, parts);
+        default: return launch_multi_m<3>(c, n_walkers, st, logl, parts);
+    }
 }
 
 template <int NIFO, int MODEL, int SC>
@@ -1323,7 +1429,8 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
     const unsigned nblk_pro = (unsigned)((n_walkers + kProWalkers - 1) / kProWalkers);
     const dim3 blk_pro(kProWalkers, 1 + BJ_MAX_IFO);
     CUDA_TRY(cudaEventRecord(c->ev[0], st));
-    prologue_kernel<<<nblk_pro, blk_pro, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
+    prologue_kernel<<<nblk_pro, blk_pro, 0, st>>>(c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers,
+                                                  c->n_levels > 0 ? c->d_counts : nullptr);
     if (c->d_coef_ex)
         prologue_extras_kernel<<<nblk, tpb, 0, st>>>(c->cfg, c->dims, *emap, x_dev, ndim, n_walkers, c->d_coef,
                                                      c->d_coef_ex, c->cap_walkers);
@@ -1343,32 +1450,15 @@ static int run_device(bj_ctx* c, const double* x_dev, long n_walkers, int ndim, 
         CUDA_TRY(cudaEventRecord(c->ev[2], st));
     } else if (c->kind == KIND_FULLGRID && c->n_levels > 0) {
         // compressed frequency axes: classify_kernel sorts the walkers into one work list per table (levels of growing
-        // design budget, then the full grid); the bin kernels and the epilogue then run once per list on that list's
-        // table.  Grids are sized for the whole batch; CTAs beyond the end of their list return at once.  The lists are
-        // disjoint, so the passes share the partial-sum buffer.
+        // design budget, then the full grid); ONE launch of each bin kernel and of the epilogue then serves all lists, every
+        // CTA on the table of the list its walker tile belongs to (launch_multi).  The lists are disjoint, so the tables
+        // share the partial-sum buffer.
         c->last_walkers = n_walkers;
-        CUDA_TRY(cudaMemsetAsync(c->d_counts, 0, (kMaxLevels + 1) * sizeof(int), st));
         classify_kernel<<<(unsigned)((n_walkers + 3) / 4), 128, 0, st>>>(c->steep, c->cfg.n_ifo, c->d_coef, c->cap_walkers,
                                                                         n_walkers, c->d_lists, c->d_counts);
         CUDA_TRY(cudaGetLastError());
-        for (int lv = 0; lv <= c->n_levels; ++lv) {
-            bj_ctx* m = lv < c->n_levels ? c->cmp[lv] : c;
-            if (m != c) {
-                m->d_coef = c->d_coef;
-                m->d_partial = c->d_partial;
-                m->d_coef_ex = nullptr;
-                m->cap_walkers = c->cap_walkers;
-                m->d_gram = c->d_gram;
-                m->d_dd_band = c->d_dd_band;
-            }
-            const Sel sel = {c->d_lists + (size_t)lv * c->cap_walkers, c->d_counts + lv};
-            rc = launch_fullgrid(m, n_walkers, st, 0, m->n_chunks, sel);
-            if (rc) return rc;
-            if (lv == 0) for (int q = 0; q < 8; ++q) c->launch_info[q] = m->launch_info[q];
-            if (lv == c->n_levels) CUDA_TRY(cudaEventRecord(c->ev[2], st));
-            rc = launch_epilogue(m, n_walkers, st, out_logl_dev, out_parts_dev, 0, 0, m->n_chunks, nullptr, sel);
-            if (rc) return rc;
-        }
+        rc = launch_multi_n(c, n_walkers, st, out_logl_dev, out_parts_dev);
+        if (rc) return rc;
     } else if (c->kind == KIND_FULLGRID) {
         rc = launch_fullgrid(c, n_walkers, st, 0, c->n_chunks);
         if (rc) return rc;
@@ -1429,7 +1519,7 @@ extern "C" int bj_partial_device(bj_ctx* c, const double* x_dev, int64_t n_walke
     to_dev_map(map, pm);
     const unsigned nblk = (unsigned)((n_walkers + 127) / 128);
     prologue_kernel<<<(unsigned)((n_walkers + kProWalkers - 1) / kProWalkers), dim3(kProWalkers, 1 + BJ_MAX_IFO), 0, st>>>(
-        c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers);
+        c->cfg, pm, x_dev, ndim, n_walkers, c->d_coef, c->cap_walkers, nullptr);
     if (c->d_coef_ex)
         prologue_extras_kernel<<<nblk, 128, 0, st>>>(c->cfg, c->dims, *emap, x_dev, ndim, n_walkers, c->d_coef,
                                                      c->d_coef_ex, c->cap_walkers);
@@ -1503,6 +1593,20 @@ extern "C" int bj_last_launch_info(bj_ctx* c, int32_t* info8) {
     return BJ_OK;
 }
 
+extern "C" int bj_last_levels(bj_ctx* c, int64_t n_walkers, int32_t* levels) {
+    if (!c || !levels || n_walkers < 0) return fail(BJ_ERR_INVALID, "bad arguments");
+    if (c->n_levels == 0 || n_walkers > c->last_walkers) {
+        for (int64_t w = 0; w < n_walkers; ++w) levels[w] = kMaxLevels;
+        return BJ_OK;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<double> lv((size_t)n_walkers);
+    CUDA_TRY(cudaMemcpy(lv.data(), c->d_coef + (size_t)C_STEEP * c->cap_walkers, lv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t w = 0; w < n_walkers; ++w) levels[w] = (int)lv[w] >= c->n_levels ? kMaxLevels : (int)lv[w];
+    return BJ_OK;
+}
+
 // host-only: the node axis build_compressed_axis makes of a weighted frequency axis (no device needed)
 extern "C" int bj_compress_axis_host(int64_t n_bins, const double* freqs, int32_t n_ifo, const double* const* weights_ri,
                                      int32_t nodes_per_run, double reach_rad, double mchirp_min, double tau_max,
@@ -1571,7 +1675,7 @@ extern "C" int bj_project_waveform(bj_ctx* c, const double* x_host, int32_t ndim
     ParamMapDev pm;
     to_dev_map(map, pm);
     cudaMemcpyAsync(d_x, x_host, ndim * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-    prologue_kernel<<<1, dim3(kProWalkers, 1 + BJ_MAX_IFO), 0, c->stream>>>(c->cfg, pm, d_x, ndim, 1, c->d_coef, c->cap_walkers);
+    prologue_kernel<<<1, dim3(kProWalkers, 1 + BJ_MAX_IFO), 0, c->stream>>>(c->cfg, pm, d_x, ndim, 1, c->d_coef, c->cap_walkers, nullptr);
     const unsigned nblk = (unsigned)((c->n_bins + 255) / 256);
     waveform_kernel<<<nblk, 256, 0, c->stream>>>(c->cfg, c->d_freqs, c->n_bins, c->d_coef, c->cap_walkers, d_h);
     cudaMemcpyAsync(out_h_host, d_h, (size_t)c->cfg.n_ifo * c->n_bins * sizeof(double2), cudaMemcpyDeviceToHost,
@@ -1620,7 +1724,7 @@ extern "C" int bj_polarizations(int device, int approx, double seglen, int centr
     if (e == cudaSuccess) e = cudaMemcpy(d_x, x_host, ndim * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_f, freqs, (size_t)n_freqs * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        prologue_kernel<<<1, dim3(kProWalkers, 1 + BJ_MAX_IFO)>>>(cfg, pm, d_x, ndim, 1, d_coef, 1);
+        prologue_kernel<<<1, dim3(kProWalkers, 1 + BJ_MAX_IFO)>>>(cfg, pm, d_x, ndim, 1, d_coef, 1, nullptr);
         polarizations_kernel<<<(unsigned)((n_freqs + 255) / 256), 256>>>(seglen, centre_shift, d_f, n_freqs, d_coef, 1,
                                                                          d_hp, d_hc);
         e = cudaGetLastError();

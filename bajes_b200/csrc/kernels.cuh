@@ -225,10 +225,14 @@ __global__ void calibrate_kernel(double* out) {
 // One walker = 1 + BJ_MAX_IFO threads: role 0 derives the source's phase / amplitude coefficients, role 1 + i the antenna
 // pattern, delay and rotation constants of detector i (all independent given the walker's row), then role 0 combines the
 // validity flags.  A call with few walkers is latency-bound in this kernel: the split shortens its dependent chain ~2x.
+constexpr int kSteepChecks = 32;   // check frequencies of classify_kernel
+constexpr int kMaxLevels = 2;      // compressed axes per context
 constexpr int kProWalkers = 32;
 __global__ void __launch_bounds__(kProWalkers * (1 + BJ_MAX_IFO))
 prologue_kernel(DeviceConfig cfg, ParamMapDev pm, const double* __restrict__ x, int ndim, long n_walkers,
-                double* __restrict__ coef, long stride) {
+                double* __restrict__ coef, long stride, int* __restrict__ list_counts) {
+    // work-list counters of classify_kernel (contexts with compressed axes), zeroed here to save a memset node
+    if (list_counts && blockIdx.x == 0 && threadIdx.y == 0 && threadIdx.x <= kMaxLevels) list_counts[threadIdx.x] = 0;
     __shared__ double s_tau[BJ_MAX_IFO][kProWalkers];
     __shared__ int s_ok[BJ_MAX_IFO][kProWalkers];
     const int lane = threadIdx.x, role = threadIdx.y;
@@ -287,6 +291,11 @@ __global__ void prologue_extras_kernel(DeviceConfig cfg, ExtrasDims dims, ExtraM
     if (!walker_extras(cfg, dims, em, x + w * ndim, coef_ex, stride, w)) coef[C_VALID * stride + w] = 0.0;
 }
 
+// per-chunk description: records [start, start + len) of the table, all in one (weight band, calibration segment) cell
+struct ChunkDesc {
+    int start, len, band, seg;
+};
+
 // ---- compressed frequency axes: which table evaluates which walker ----------------------------------------------------
 // A compressed axis (capi.cu: build_compressed_axis) replaces runs of bins by Chebyshev nodes whose spacing is chosen for
 // a DESIGN bound on the phase slope  |d(Phi/2pi)/df| + |tau_i| <= budget(f) = margin t_N(f; mchirp_min) + tau_max.  A
@@ -298,8 +307,6 @@ __global__ void prologue_extras_kernel(DeviceConfig cfg, ExtrasDims dims, ExtraM
 // is too wide for the binary-angle trick, C_VALID == 2, or anything is NaN) to the list of the full grid.  Every bin
 // kernel then runs once per list, on that list's table (Sel below); walkers that return -inf anyway go to level 0.
 // The order of a list varies from run to run (atomics), the results do not: no kernel mixes walkers.
-constexpr int kSteepChecks = 32;
-constexpr int kMaxLevels = 2;
 struct SteepTable {
     int n, n_levels;
     double u[kSteepChecks], L[kSteepChecks], w5[kSteepChecks], inv_f[kSteepChecks];
@@ -310,6 +317,38 @@ struct Sel {
     const int* idx;
     const int* count;
 };
+// One launch over ALL tables of a context with compressed axes: CTA (x, y) serves chunk x of the table that owns walker
+// tile y, tiles being numbered table after table (the lists' lengths are only known on the device).  The grid is sized
+// for the worst case -- ceil(W / tile) + n - 1 tiles, the longest chunk list -- and surplus CTAs return at once.
+struct TableRef {
+    const unsigned char* basis;      // tensor-core tables (kernels.cuh: TileRec)
+    const unsigned char* data;
+    const unsigned char* rec_ul;     // Horner records (u, L of a bin: amplitude correction)
+    const double* rec64;             // FP64 window records, offset so that chunk.start indexes them
+    const ChunkDesc* chunks;
+    int n_chunks, n_precise;
+    double dh_fix_re, dh_fix_im;
+};
+struct MultiTable {
+    int n;                           // 0: single-table launch, the explicit kernel arguments apply
+    long list_stride;
+    const int* lists;                // [n][list_stride]
+    const int* counts;               // [n]
+    TableRef t[kMaxLevels + 1];
+};
+__device__ __forceinline__ bool resolve_tile(const MultiTable& mt, int tile, int by, int& lv, long& entry0, long& n_sel) {
+    int t0 = 0;
+    for (lv = 0; lv < mt.n; ++lv) {
+        n_sel = (long)mt.counts[lv];
+        const int nt = (int)((n_sel + tile - 1) / tile);
+        if (by < t0 + nt) {
+            entry0 = (long)(by - t0) * tile;
+            return true;
+        }
+        t0 += nt;
+    }
+    return false;
+}
 __global__ void __launch_bounds__(128) classify_kernel(SteepTable tab, int n_ifo, double* __restrict__ coef, long stride,
                                                        long n_walkers, int* __restrict__ lists, int* __restrict__ counts) {
     const int lane = threadIdx.x & 31;
@@ -354,10 +393,6 @@ __global__ void __launch_bounds__(128) classify_kernel(SteepTable tab, int n_ifo
     }
 }
 
-// per-chunk description: records [start, start + len) of the table, all in one (weight band, calibration segment) cell
-struct ChunkDesc {
-    int start, len, band, seg;
-};
 
 // ---- the fused full-grid kernel -----------------------------------------------------------------
 // One CTA = kThreads walkers (one per thread, coefficients in registers) x one frequency chunk.
@@ -625,16 +660,29 @@ __global__ void __launch_bounds__(kThreads, 2) fullgrid_window_kernel(const doub
                                                                       long n_walkers, double* __restrict__ partial,
                                                                       const double* __restrict__ coef_ex, ExtrasDims dims,
                                                                       const double* __restrict__ spcal_freqs, int chunk0,
-                                                                      double df, Sel sel) {
+                                                                      double df, Sel sel,
+                                                                      const __grid_constant__ MultiTable mt) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     constexpr int NR = NIFO > 1 ? NIFO - 1 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileBins * RS * 8);
 
-    const long n_sel = sel.idx ? (long)*sel.count : n_walkers;
-    if ((long)blockIdx.y * kThreads >= n_sel) return;
-    const long entry = (long)blockIdx.y * kThreads + threadIdx.x;
+    long n_sel, entry0 = (long)blockIdx.y * kThreads;
+    if (mt.n > 0) {
+        int lv;
+        if (!resolve_tile(mt, kThreads, (int)blockIdx.y, lv, entry0, n_sel)) return;
+        const TableRef& T = mt.t[lv];
+        if ((int)blockIdx.x >= T.n_precise) return;
+        rec = T.rec64;
+        chunks = T.chunks;
+        chunk0 = 0;
+        sel.idx = mt.lists + (size_t)lv * mt.list_stride;
+    } else {
+        n_sel = sel.idx ? (long)*sel.count : n_walkers;
+        if (entry0 >= n_sel) return;
+    }
+    const long entry = entry0 + threadIdx.x;
     const bool live = entry < n_sel;
     const long wl = sel.idx ? (long)sel.idx[live ? entry : n_sel - 1] : (live ? entry : n_sel - 1);
     const long wi = wl;
@@ -1470,7 +1518,7 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
                                                                   long n_walkers, double* __restrict__ partial,
                                                                   int chunk0, double df,
                                                                   const double* __restrict__ coef_ex, ExtrasDims dims,
-                                                                  Sel sel) {
+                                                                  Sel sel, const __grid_constant__ MultiTable mt) {
     using R = TileRec<MODEL>;
     constexpr int RB = R::kDataBytes, BB = R::kBasisBytes;
     constexpr int kStageBytes = R::kTileBins * (BB + RB);
@@ -1481,9 +1529,23 @@ __global__ void __launch_bounds__(kTileThreads, 512 / kTileThreads) fullgrid_til
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     // work list (Sel): entry -> walker; a CTA beyond the end of the list has nothing to do
-    const long n_sel = sel.idx ? (long)*sel.count : n_walkers;
-    if ((long)blockIdx.y * kTileWalkers >= n_sel) return;
-    const long entry = (long)blockIdx.y * kTileWalkers + warp * 8 + g;
+    long n_sel, entry0 = (long)blockIdx.y * kTileWalkers;
+    if (mt.n > 0) {
+        int lv;
+        if (!resolve_tile(mt, kTileWalkers, (int)blockIdx.y, lv, entry0, n_sel)) return;
+        const TableRef& T = mt.t[lv];
+        if ((int)blockIdx.x >= T.n_chunks - T.n_precise) return;
+        tab_basis = T.basis;
+        tab_data = T.data;
+        rec_ul = T.rec_ul;
+        chunks = T.chunks;
+        chunk0 = T.n_precise;
+        sel.idx = mt.lists + (size_t)lv * mt.list_stride;
+    } else {
+        n_sel = sel.idx ? (long)*sel.count : n_walkers;
+        if (entry0 >= n_sel) return;
+    }
+    const long entry = entry0 + warp * 8 + g;
     const bool live = entry < n_sel;
     const long wl = sel.idx ? (long)sel.idx[live ? entry : n_sel - 1] : (live ? entry : n_sel - 1);
     const long wi = wl;
@@ -1753,33 +1815,62 @@ __global__ void __launch_bounds__(kEpiWalkers * kEpiSlices)
 epilogue_kernel(DeviceConfig cfg, EpilogueTables tab, ExtrasDims dims, const double* __restrict__ partial,
                 const double* __restrict__ coef, const double* __restrict__ coef_ex, long stride, long n_walkers,
                 double* __restrict__ logl, double* __restrict__ sums, int mode, int chunk_begin, int chunk_end,
-                double* __restrict__ sums_io, Sel sel) {
+                double* __restrict__ sums_io, Sel sel, const __grid_constant__ MultiTable mt) {
     __shared__ double red[kEpiSlices][2 * BJ_MAX_IFO][kEpiWalkers];
     const int lane_w = threadIdx.x % kEpiWalkers, slice = threadIdx.x / kEpiWalkers;
-    const long n_sel = sel.idx ? (long)*sel.count : n_walkers;
-    if ((long)blockIdx.x * kEpiWalkers >= n_sel) return;
-    const long entry = (long)blockIdx.x * kEpiWalkers + lane_w;
+    long n_sel, entry0 = (long)blockIdx.x * kEpiWalkers;
+    if (mt.n > 0) {
+        int lv;
+        if (!resolve_tile(mt, kEpiWalkers, (int)blockIdx.x, lv, entry0, n_sel)) return;
+        const TableRef& T = mt.t[lv];
+        tab.chunks = T.chunks;
+        tab.n_chunks = T.n_chunks;
+        chunk_begin = 0;
+        chunk_end = T.n_chunks;
+        cfg.dh_fix_re = T.dh_fix_re;
+        cfg.dh_fix_im = T.dh_fix_im;
+        sel.idx = mt.lists + (size_t)lv * mt.list_stride;
+    } else {
+        n_sel = sel.idx ? (long)*sel.count : n_walkers;
+        if (entry0 >= n_sel) return;
+    }
+    const long entry = entry0 + lane_w;
     const bool live = entry < n_sel;
     const long w = sel.idx ? (long)sel.idx[live ? entry : n_sel - 1] : (live ? entry : n_sel - 1);
     const long wc = w;
     const int nifo = cfg.n_ifo;
     // stage 1: slice s adds chunks s, s + kEpiSlices, ... in ascending order (fixed tree: bits do not depend on W);
-    // with PSD weights every chunk lies in one band and is scaled by 1 / w_band (detector.py:529)
-    for (int j = 0; j < 2 * nifo; ++j) {
-        double acc = 0.0;
+    // with PSD weights every chunk lies in one band and is scaled by 1 / w_band (detector.py:529).  All 2 n_ifo sums of a
+    // chunk are loaded together and two chunks per round, so that ~12 loads are in flight (a call with few walkers is
+    // bound by this chain); every sum still receives its terms in ascending chunk order.
+    {
+        double acc[2 * BJ_MAX_IFO];
+#pragma unroll
+        for (int j = 0; j < 2 * BJ_MAX_IFO; ++j) acc[j] = 0.0;
         if (mode != 2) {
-            // (the adds stay in ascending chunk order; unrolling only lets the loads of four chunks fly together)
-#pragma unroll 4
+#pragma unroll 2
             for (int ch = chunk_begin + slice; ch < chunk_end; ch += kEpiSlices) {
-                double v = partial[((size_t)ch * (2 * nifo) + j) * stride + wc];
-                if (dims.nweights > 0)
-                    v *= coef_ex[ex_invw_slot(dims, nifo, j >> 1, tab.chunks[ch].band) * stride + wc];
-                acc += v;
+                double v[2 * BJ_MAX_IFO];
+#pragma unroll
+                for (int j = 0; j < 2 * BJ_MAX_IFO; ++j)
+                    v[j] = j < 2 * nifo ? partial[((size_t)ch * (2 * nifo) + j) * stride + wc] : 0.0;
+                if (dims.nweights > 0) {
+                    const int band = tab.chunks[ch].band;
+#pragma unroll
+                    for (int j = 0; j < 2 * BJ_MAX_IFO; ++j)
+                        if (j < 2 * nifo) v[j] *= coef_ex[ex_invw_slot(dims, nifo, j >> 1, band) * stride + wc];
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * BJ_MAX_IFO; ++j) acc[j] += v[j];
             }
         } else if (slice == 0) {
-            acc = sums_io[(size_t)j * n_walkers + wc];
+#pragma unroll
+            for (int j = 0; j < 2 * BJ_MAX_IFO; ++j)
+                if (j < 2 * nifo) acc[j] = sums_io[(size_t)j * n_walkers + wc];
         }
-        red[slice][j][lane_w] = acc;
+#pragma unroll
+        for (int j = 0; j < 2 * BJ_MAX_IFO; ++j)
+            if (j < 2 * nifo) red[slice][j][lane_w] = acc[j];
     }
     __syncthreads();
     if (slice != 0 || !live) return;

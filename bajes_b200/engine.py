@@ -139,6 +139,7 @@ EXPORTS = {
     "bj_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "bj_compress_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), _DP]),
     "bj_last_level_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "bj_last_levels": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
     "bj_compress_axis_host": (C.c_int, [C.c_int64, _DP, C.c_int32, _DPP, C.c_int32, C.c_double, C.c_double, C.c_double,
                                         C.c_double, C.POINTER(C.c_int64), _DP, _DPP, C.POINTER(C.c_int32)]),
 }
@@ -527,6 +528,13 @@ class Engine:
         return {"nodes": int(info[0]), "kept_bins": int(info[1]), "blocks": int(info[2]), "nodes_per_block": int(info[3]),
                 "mchirp_min": float(spec[0]), "tau_max": float(spec[1]), "reach_rad": float(spec[2]),
                 "margin": float(spec[3]), "n_bins": int(self.n_bins)}
+
+    def last_levels(self, n_walkers: int) -> np.ndarray:
+        """Table index of every walker of the last call (0, 1 = compressed levels, 2 = full grid).  Synchronises."""
+        out = np.empty(int(n_walkers), dtype=np.int32)
+        _check(self._lib, self._lib.bj_last_levels(self._h, int(n_walkers), out.ctypes.data_as(C.POINTER(C.c_int32))),
+               "bj_last_levels")
+        return out
 
     def last_level_counts(self):
         """Walkers of the last call per table: (level 0, level 1, full grid).  Synchronises."""

@@ -63,8 +63,8 @@ DTYPE_COMPRESSED = ("f64 data weights pre-summed onto Chebyshev nodes (long doub
                     "phasor (MUFU pair per node and detector) + f32 MAC -> f64 accumulate every 8 nodes; all-f64 in the heaviest "
                     "16% of the nodes")
 LAUNCHES_PER_STEP = 5      # prologue, FP64 window, fused tile kernel, fix-up (early exit), epilogue
-# compressed axes: prologue, classify, {window, tile, epilogue} per level (2), {window, tile, fix-up, epilogue} full grid
-LAUNCHES_PER_STEP_COMPRESSED = 12
+# compressed axes: prologue, classify, then ONE window, tile, fix-up (early exit) and epilogue launch over all tables
+LAUNCHES_PER_STEP_COMPRESSED = 6
 
 
 # Algorithmic instruction counts per walker*bin of the fused kernel:

@@ -284,6 +284,8 @@ int bj_last_launch_info(bj_ctx* ctx, int32_t* info8);
  * spec4 = {mchirp_min, tau_max, reach in rad, slope margin}. */
 #define BJ_COMPRESS_LEVELS 2
 int bj_compress_info(bj_ctx* ctx, int32_t level, int32_t* info4, double* spec4);
+/* table of every walker of the last call: levels[w] = 0, 1 (compressed levels) or 2 (full grid).  Synchronises. */
+int bj_last_levels(bj_ctx* ctx, int64_t n_walkers, int32_t* levels);
 /* Host-only (no device needed): the node axis made of a weighted frequency axis -- weights_ri[i] = interleaved (re, im)
  * per bin and detector.  out_freqs / out_weights_ri[i] must hold n_bins (2 n_bins) doubles; *out_n = number of nodes.
  * Non-positive nodes_per_run / reach_rad / mchirp_min / tau_max / margin = the library defaults (32, 10, 0.5, 0.11, 1.3).

