@@ -631,11 +631,43 @@ def secondary_c5(c, like, cfg, names, const):
         return s, trace, time.perf_counter() - t0, pool
 
     s, trace, wall_s, pool = run(ev)
-    same = None
+
+    # bajes' own sampler kernel: parallel-tempered ensemble (restatement of _PTMCMC pinned bit for bit to the unmodified
+    # reference, bajes_b200/ptmcmc.py), 4 temperatures x 1024 walkers = 4096 points per sampler step, two batched calls
+    def run_pt(evaluator):
+        from bajes_b200.ptmcmc import PTEnsembleSampler
+        target = ShardedLikelihood(like, evaluator) if evaluator is not None else like
+        ntemps, nw, pt_steps = 4, 1024, 20
+        pt = PTEnsembleSampler(nw, Posterior(target, BoxPrior(names, bounds, const, periodic=[1 if n in ("psi", "phi_ref") else 0
+                                                                                              for n in names])),
+                               ntemps=ntemps, random=np.random.default_rng(11), rng="vector")
+        start = p0[:ntemps * nw].reshape(ntemps, nw, len(names)).copy()
+        pt.sample(iterations=1, p0=start, store=False)
+        torch.cuda.synchronize(c.dev)
+        t0 = time.perf_counter()
+        pt.sample(iterations=pt_steps, store=False)
+        torch.cuda.synchronize(c.dev)
+        return pt, time.perf_counter() - t0, pt_steps
+
+    pt, pt_wall, pt_steps = run_pt(ev)
+    same = pt_same = None
     if ev is not None:
         ev.shutdown()
         s1, _, _, _ = run(None)                    # the same seeded chain on this GPU alone
         same = bool(np.array_equal(s1.pos, s.pos) and np.array_equal(s1.logp, s.logp))
+        pt1, _, _ = run_pt(None)
+        pt_same = bool(np.array_equal(pt1._p0, pt._p0) and np.array_equal(pt1._loglikelihood0, pt._loglikelihood0))
+    pt_eval = pt.ntemps * pt.nwalkers * pt_steps
+    ptmcmc = {"workload": "parallel-tempered ensemble (bajes_b200.ptmcmc.PTEnsembleSampler = bajes' _PTMCMC kernel, "
+                          "bajes/inf/sampler/ptmcmc.py:184-470, stretch move), %d temperatures x %d walkers, %d steps, one batched "
+                          "log_likeprior call per half-ensemble of all temperatures" % (pt.ntemps, pt.nwalkers, pt_steps),
+              "value": pt_eval / pt_wall, "unit": "likelihood evaluations/s (end to end)", "s_per_sampler_step": pt_wall / pt_steps,
+              "batched_calls": pt.n_batched_calls, "betas": [float(b) for b in pt.betas],
+              "acceptance_per_temperature": [float(v) for v in pt.acceptance_fraction.mean(axis=1)],
+              "tswap_acceptance": [float(v) for v in pt.tswap_acceptance_fraction],
+              "lnL_max_cold_chain": float(np.max(pt._loglikelihood0[0])), "chain_bit_identical_to_one_gpu": pt_same,
+              "pinned_by": "tests/test_ptmcmc.py: bit-identical to the unmodified reference sampler (build container) and to "
+                           "tests/golden/ptmcmc_trace.npz (its recorded run) in rng='reference' mode; this run draws in arrays"}
     idx = np.arange(0, walkers, 64)
     fresh = like.log_like_batch(s.pos[idx], names, const) + prior.log_prior(None)
     nb = like.engine.n_bins
@@ -654,9 +686,10 @@ def secondary_c5(c, like, cfg, names, const):
             "chain_bit_identical_to_one_gpu": same, "parity_max_err_over_tol": None,
             "parity_note": "the likelihood is the headline's (parity there); here the check is that the chain is bit-identical "
                            "for any number of GPUs and that stored log-posteriors equal fresh evaluations",
-            "n_gpus": c.world,
-            "note": "bajes' own samplers are not installable offline on the GPU box; the reference's ptmcmc driven through the "
-                    "same adapter is run in the build container (tests/test_sampler_adapters.py, scripts/run_c5_ptmcmc.py)"}
+            "n_gpus": c.world, "ptmcmc": ptmcmc,
+            "note": "bajes' sampler packages are not installable offline on the GPU box.  The UNMODIFIED reference ptmcmc driven "
+                    "through the same adapter runs in the build container (tests/test_sampler_adapters.py) and its recorded call "
+                    "trace is replayed on the GPU (tests/test_gpu_parity.py); `ptmcmc` is its kernel restated in this repo"}
 
 
 # ---------------------------------------------------------------------------------------------------------
