@@ -12,6 +12,7 @@
 
 #include "kernels.cuh"
 #include "roq_relbin.cuh"
+#include "roq_basis.cuh"
 #include "timemarg.cuh"
 
 using namespace bj;
@@ -1733,6 +1734,135 @@ extern "C" int bj_polarizations(int device, int approx, double seglen, int centr
     if (e == cudaSuccess) e = cudaMemcpy(out_hc_host, d_hc, (size_t)n_freqs * sizeof(double2), cudaMemcpyDeviceToHost);
     cudaFree(d_x); cudaFree(d_f); cudaFree(d_coef); cudaFree(d_hp); cudaFree(d_hc);
     if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "bj_polarizations: %s", cudaGetErrorString(e));
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROQ basis construction (roq_basis.cuh): training bank and reduced-basis greedy, device-resident
+// ------------------------------------------------------------------------------------------------
+extern "C" int bj_wavebank(int device, int approx, int64_t n_freqs, const double* freqs_host, const double* x_host,
+                           int64_t n_points, int32_t ndim, const bj_param_map* map, int32_t quadratic, void* out_dev) {
+    if (!freqs_host || !x_host || !out_dev || n_freqs <= 0 || n_points <= 0 || ndim <= 0) return fail(BJ_ERR_INVALID, "null / empty argument");
+    if (approx < 0 || approx > BJ_APPROX_TAYLORF2_55PN_75PNTIDES2020)
+        return fail(BJ_ERR_UNSUPPORTED, "approximant id %d is not a TaylorF2 variant", approx);
+    bj_param_map m = *map;
+    const int sky[] = {BJ_P_RA, BJ_P_DEC, BJ_P_PSI, BJ_P_TIME_SHIFT, BJ_P_T_GPS};
+    for (int sl : sky)
+        if (m.column[sl] == BJ_COL_ABSENT) { m.column[sl] = BJ_COL_CONST; m.value[sl] = 0.0; }
+    int rc = check_map(&m, ndim);
+    if (rc) return rc;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(BJ_ERR_NO_DEVICE, "no CUDA device visible: bajes_b200 has no CPU fallback");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.approx = approx;
+    cfg.n_ifo = 0;
+    ParamMapDev pm;
+    to_dev_map(&m, pm);
+    const long stride = pad_walkers((long)n_points);
+    double *d_x = nullptr, *d_f = nullptr, *d_coef = nullptr;
+    cudaError_t e = cudaMalloc(&d_x, (size_t)n_points * ndim * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_f, (size_t)n_freqs * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_coef, (size_t)C_NUM * stride * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_x, x_host, (size_t)n_points * ndim * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_f, freqs_host, (size_t)n_freqs * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        prologue_kernel<<<(unsigned)((n_points + kProWalkers - 1) / kProWalkers), dim3(kProWalkers, 1 + BJ_MAX_IFO)>>>(
+            cfg, pm, d_x, ndim, (long)n_points, d_coef, stride, nullptr);
+        // grid.y is limited to 65 535 rows per launch
+        for (int64_t w0 = 0; w0 < n_points && e == cudaSuccess; w0 += 32768) {
+            const long nw = (long)std::min<int64_t>(32768, n_points - w0);
+            dim3 grid((unsigned)((n_freqs + 255) / 256), (unsigned)nw);
+            wavebank_kernel<<<grid, 256>>>(d_f, (long)n_freqs, d_coef + w0, stride, nw, quadratic,
+                                           (double2*)out_dev + (size_t)w0 * n_freqs);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_x); cudaFree(d_f); cudaFree(d_coef);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "bj_wavebank: %s", cudaGetErrorString(e));
+    return BJ_OK;
+}
+
+extern "C" int bj_rb_greedy(int device, int64_t n_train, int64_t n_freqs, void* train_dev, const double* weights_host,
+                            double df, double tol, int32_t n_prebuilt, int32_t max_basis, void* basis_dev, int32_t* out_picks,
+                            double* out_sigmas, int32_t* out_n, float* out_ms) {
+    if (!train_dev || !weights_host || !basis_dev || !out_picks || !out_sigmas || !out_n || n_train <= 0 || n_freqs <= 0 ||
+        max_basis <= 0 || n_prebuilt < 0 || n_prebuilt > max_basis)
+        return fail(BJ_ERR_INVALID, "null / empty argument");
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) {
+        cudaGetLastError();
+        return fail(BJ_ERR_NO_DEVICE, "no CUDA device visible: bajes_b200 has no CPU fallback");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    double2* R = (double2*)train_dev;
+    double2* B = (double2*)basis_dev;
+    double *d_w = nullptr, *d_sig2 = nullptr, *d_val = nullptr;
+    int* d_pick = nullptr;
+    cudaError_t e = cudaMalloc(&d_w, (size_t)n_freqs * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_sig2, (size_t)n_train * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_val, sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_pick, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(d_w, weights_host, (size_t)n_freqs * sizeof(double), cudaMemcpyHostToDevice);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+    const double four_df = 4.0 * df;
+    int n = n_prebuilt, np_out = 0;
+    std::vector<char> taken((size_t)n_train, 0);
+    if (e == cudaSuccess) {
+        cudaEventRecord(ev0);
+        // a prebuilt basis (roq.py:512-520): the training rows are first reduced to their residuals against it
+        for (int j = 0; j < n_prebuilt; ++j)
+            rb_project_kernel<<<(unsigned)n_train, kRbThreads>>>(R, (long)n_freqs, d_w, four_df, B + (size_t)j * n_freqs, d_sig2,
+                                                                  nullptr);
+        if (n_prebuilt == 0) rb_norm_kernel<<<(unsigned)n_train, kRbThreads>>>(R, (long)n_freqs, d_w, four_df, d_sig2);
+        // rb_greedy (roq.py:537-612): the worst-approximated training function joins the basis until its error is below
+        // tol, or it has been picked before (accuracy cannot be reached), or max_basis is full.  The reference seeds the
+        // basis with training function 0 (:508-511): the first pick is forced to row 0.
+        while (n < max_basis) {
+            int pick = 0;
+            double val = 0.0;
+            if (n == 0) {        // (only without a prebuilt basis)
+                const int zero = 0;
+                cudaMemcpy(d_pick, &zero, sizeof(int), cudaMemcpyHostToDevice);
+                cudaMemcpy(d_val, d_sig2, sizeof(double), cudaMemcpyDeviceToDevice);
+            } else {
+                rb_argmax_kernel<<<1, 1024>>>(d_sig2, (long)n_train, d_pick, d_val);
+            }
+            e = cudaMemcpy(&pick, d_pick, sizeof(int), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(&val, d_val, sizeof(double), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) break;
+            const double sigma = std::sqrt(std::fmax(val, 0.0));
+            if (n > 0 && (sigma <= tol || taken[pick] || !(val > 0.0))) {
+                out_sigmas[np_out] = sigma;      // the error at which the loop ended
+                break;
+            }
+            taken[pick] = 1;
+            out_picks[np_out] = pick;
+            out_sigmas[np_out] = sigma;
+            ++np_out;
+            rb_take_kernel<<<(unsigned)((n_freqs + 255) / 256), 256>>>(R, (long)n_freqs, d_pick, d_val, B + (size_t)n * n_freqs);
+            rb_project_kernel<<<(unsigned)n_train, kRbThreads>>>(R, (long)n_freqs, d_w, four_df, B + (size_t)n * n_freqs, d_sig2,
+                                                                  nullptr);
+            ++n;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) break;
+        }
+        cudaEventRecord(ev1);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
+        if (e == cudaSuccess && out_ms) cudaEventElapsedTime(out_ms, ev0, ev1);
+    }
+    *out_n = n;
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    cudaFree(d_w); cudaFree(d_sig2); cudaFree(d_val); cudaFree(d_pick);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "bj_rb_greedy: %s", cudaGetErrorString(e));
     return BJ_OK;
 }
 

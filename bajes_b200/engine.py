@@ -134,6 +134,10 @@ EXPORTS = {
     "bj_peer_scatter": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int64, C.c_void_p]),
     "bj_peer_wait": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_void_p]),
+    "bj_wavebank": (C.c_int, [C.c_int, C.c_int, C.c_int64, _DP, _DP, C.c_int64, C.c_int32, C.POINTER(bj_param_map), C.c_int32,
+                              C.c_void_p]),
+    "bj_rb_greedy": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, _DP, C.c_double, C.c_double, C.c_int32, C.c_int32,
+                               C.c_void_p, C.POINTER(C.c_int32), _DP, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "bj_measure_peak": (C.c_int, [C.c_int, C.c_int, _DP]),
     "bj_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bj_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

@@ -232,6 +232,24 @@ typedef struct {
 int bj_roq_create(bj_ctx** out, const bj_config* cfg, const bj_roq_tables* tab);
 /* bj_loglike / bj_loglike_device / bj_destroy work on ROQ contexts too. */
 
+/* ROQ basis CONSTRUCTION.  The reference ships only the run-time side of ROQ; its own construction code is commented out
+ * (pipe/utils/roq.py:16-662).  These two entry points follow it: the training set (h_plus of TaylorF2 on the in-band axis,
+ * no centre shift, :471-473; quadratic != 0: |h_plus|^2) and the reduced-basis greedy selection by projection error under
+ * (a, b) = 4 df sum_k w_k conj(a_k) b_k  (rb_greedy :537-612, inner_product :654-662 -- Hermitian here: the commented code
+ * keeps the real part only, which makes e and i e orthogonal and the complex DEIM that follows singular; tests/test_roq_basis.py).
+ * DEIM (:614-652) and the interpolant stay on the host (bajes_b200/roq_basis.py).
+ *   bj_wavebank : x_host [n_points][ndim] -> out_dev, DEVICE memory, complex128 [n_points][n_freqs]
+ *   bj_rb_greedy: train_dev [n_train][n_freqs] complex128 DEVICE memory, overwritten by the residuals; basis_dev
+ *                 [max_basis][n_freqs] holds n_prebuilt basis vectors on entry (roq.py:512-520: the rows are first reduced to
+ *                 their residuals against them) and receives the orthonormal basis; out_picks / out_sigmas [max_basis + 1] the training
+ *                 row picked at every step and its error before the pick (the entry after the last pick: the error at which
+ *                 the loop ended); *out_n the basis size; *out_ms (optional) device time of the loop. */
+int bj_wavebank(int device, int approx, int64_t n_freqs, const double* freqs_host, const double* x_host, int64_t n_points,
+                int32_t ndim, const bj_param_map* map, int32_t quadratic, void* out_dev);
+int bj_rb_greedy(int device, int64_t n_train, int64_t n_freqs, void* train_dev, const double* weights_host, double df,
+                 double tol, int32_t n_prebuilt, int32_t max_basis, void* basis_dev, int32_t* out_picks, double* out_sigmas,
+                 int32_t* out_n, float* out_ms);
+
 /* ------------------------------------------------------------------------------------------
  * Relative-binning likelihood (GWBinningLikelihood.log_like, pipe/utils/binning.py:248-306).
  * Static inputs: bin-edge frequencies fbin[n_edges], fiducial waveform at the edges per
