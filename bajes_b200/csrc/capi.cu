@@ -606,9 +606,11 @@ static int build_mixed_set(bj_ctx* c, const bj_config* cfg, const Axis& ax, cons
     if (const char* ev = getenv("BAJES_B200_PRECISE_SHARE")) share = atof(ev);
     if (const char* ev = getenv("BAJES_B200_PRECISE_FRAC")) frac = atof(ev);
     if (c->shadow) {
-        // on a compressed axis the plain low-frequency bins are a third of the table, not 2 % of it: the window that holds
-        // 90 % of their weight would double the cost.  16 % of the nodes (profiles/r02_compress_window.txt: worst walker
-        // in 2e6 0.42 tol at +7 % time; 8 %: 0.51, 40 %: 0.35 at +23 %)
+        // on a compressed axis the plain low-frequency bins are a third to a half of the table, not 2 % of it: the window that
+        // holds 90 % of their weight would double the cost.  16 % of the nodes (profiles/r02_compress_window.txt, 22 560 nodes:
+        // worst walker in 2e6 0.42 tol at +7 % time; 8 %: 0.51, 40 %: 0.35 at +23 %; profiles/r02_compress_window_13312.txt,
+        // the default 13 312 nodes, 4e6 walkers: 0.52 / 0.54 / 0.54 / 0.56 tol for 16 / 22 / 27 / 35 % -- the tail no longer
+        // depends on it)
         frac = 0.16;
         if (const char* ev = getenv("BAJES_B200_CMP_PRECISE_SHARE")) share = atof(ev);
         if (const char* ev = getenv("BAJES_B200_CMP_PRECISE_FRAC")) frac = atof(ev);
@@ -682,7 +684,7 @@ static int build_mixed_set(bj_ctx* c, const bj_config* cfg, const Axis& ax, cons
 //
 // <d|h>_i = sum_k w_ik g_i(f_k) with static weights w_ik = (4/T) conj(d_ik)/S_ik f_k^(-7/6) e^{i pi f_k T} and the walker's
 // SMOOTH factor g_i(f) = Q(f) e^{-2 pi i [Phi(f)/2pi + f tau_i]}.  On a run of bins [a, b] over which the phase of g turns
-// by at most `reach` radians to either side of the centre, g is reproduced to ~1e-11 by its Chebyshev interpolant on n
+// by at most `reach` radians to either side of the centre, g is reproduced to ~1e-12 by its Chebyshev interpolant on n
 // nodes f_j, so
 //     sum_{k in run} w_ik g_i(f_k) = sum_j [ sum_k w_ik l_j(f_k) ] g_i(f_j) = sum_j W_ij g_i(f_j)
 // with the Lagrange cardinal functions l_j: the run's bins collapse into n "bins" with weights W_ij that the very same
@@ -697,7 +699,9 @@ struct CompressSpec {
     double reach, mchirp_min, tau_max, margin;
 };
 static CompressSpec compress_spec(const bj_extras* ex) {
-    CompressSpec sp = {1, 32, 10.0, 0.5, 0.11, 1.3};
+    // 64 nodes per run of +-32 rad: the Chebyshev truncation error 2 (reach/2)^n / n! is ~1e-12 there, and longer runs leave
+    // fewer nodes (C2: 17 728; 32 nodes of +-10 rad: 22 560) at the same worst-walker error (profiles/r02_compress_nodes.txt)
+    CompressSpec sp = {1, 64, 32.0, 0.8, 0.11, 1.3};
     if (ex && ex->compress != 0) {
         sp.on = ex->compress > 0;
         if (ex->compress_mchirp_min > 0.0) sp.mchirp_min = ex->compress_mchirp_min;
@@ -903,12 +907,15 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
     if (sp.on && cfg->sincos != BJ_SINCOS_FP64 && c->d_tile_basis && c->grid_df > 0.0 && nsp == 0 && nw == 0 && !tm) {
         // level 0: the design; level 1: time shifts up to ~1 s (the default prior of the reference's pipeline,
         // pipe/scripts/bajes_pipe:526) -- samplers start there and end in level 0
+        // and lighter systems: half the design's chirp mass
         double taus[kMaxLevels] = {sp.tau_max, std::fmax(1.1, 2.0 * sp.tau_max)};
+        double mcs[kMaxLevels] = {sp.mchirp_min, 0.5 * sp.mchirp_min};
         int want = sp.tau_max >= 1.1 ? 1 : kMaxLevels;
         if (const char* ev = getenv("BAJES_B200_COMPRESS_LEVELS")) want = std::max(1, std::min(kMaxLevels, atoi(ev)));
         for (int lv = 0; lv < want; ++lv) {
             CompressSpec sl = sp;
             sl.tau_max = taus[lv];
+            sl.mchirp_min = mcs[lv];
             std::vector<double> nf, nbw, nwt[BJ_MAX_IFO];
             int info[4] = {0, 0, 0, 0};
             build_compressed_axis(ax, cfg->n_ifo, bw, sl, nf, nwt, nbw, info);

@@ -48,7 +48,7 @@ class GWLikelihood(Likelihood):
                  device=0, sincos="mufu", compress=None, **kwargs):
         """``compress`` (no counterpart in the reference): None = library default (the compressed frequency axis is
         used where it pays), False = evaluate every bin, or {"mchirp_min": .., "tau_max": ..} = the design bounds of
-        the compression (chirp mass in solar masses, |geocentric delay + time_shift| in s; defaults 0.5 / 0.11).  Points
+        the compression (chirp mass in solar masses, |geocentric delay + time_shift| in s; defaults 0.8 / 0.11).  Points
         outside the design are evaluated on the full grid in the same call: the option changes speed, never results
         beyond the parity tolerance."""
         super(GWLikelihood, self).__init__()

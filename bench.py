@@ -263,7 +263,7 @@ def workload(cfg, args, walkers):
 def source_sha():
     """hash of the kernel sources: profiles/traffic.json carries the hash it was measured at"""
     h = hashlib.sha1()
-    for name in ("kernels.cuh", "walker.cuh", "roq_relbin.cuh", "capi.cu"):
+    for name in ("kernels.cuh", "walker.cuh", "roq_relbin.cuh", "roq_basis.cuh", "capi.cu"):
         with open(os.path.join(ROOT, "bajes_b200", "csrc", name), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:12]

@@ -146,7 +146,8 @@ typedef struct {
      * |geocentric delay + time_shift| <= compress_tau_max (s).  Walkers outside the design are detected per call and
      * evaluated on the full grid, so results never leave the parity tolerance; only speed depends on the design.
      * compress: 0 = default (on, unless BAJES_B200_COMPRESS=0), 1 = on, -1 = off.  Zero / negative bounds = defaults
-     * (0.5 solar masses, 0.11 s).  Ignored with spcal / weights / time marginalisation / sincos fp64 (full grid only). */
+     * (0.8 solar masses -- two 0.92 M_sun stars, below the lightest neutron stars known -- and 0.11 s = the Earth's
+     * light-travel time + 90 ms of time shift; the second level admits half the chirp mass and 1.1 s).  Ignored with spcal / weights / time marginalisation / sincos fp64 (full grid only). */
     int32_t compress;
     int32_t reserved2;
     double  compress_mchirp_min;
@@ -296,8 +297,8 @@ int bj_last_kernel_ms(bj_ctx* ctx, float* ms3);
 /* static description of the last launch: grid, block, dynamic smem, bins per chunk, #chunks */
 int bj_last_launch_info(bj_ctx* ctx, int32_t* info8);
 /* Compressed frequency axes of a full-grid context (bj_extras.compress*).  A context holds up to BJ_COMPRESS_LEVELS node
- * axes of growing design budget (level 0: the design; level 1: |tau| up to max(1.1 s, 2 tau_max), the default time-shift
- * prior of the reference's pipeline) and the full grid; every call sorts its walkers into the first table that covers them.
+ * axes of growing design budget (level 0: the design; level 1: half its chirp mass, |tau| up to max(1.1 s, 2 tau_max) -- the
+ * default time-shift prior of the reference's pipeline) and the full grid; every call sorts its walkers into the first table that covers them.
  * info4 = {nodes, nodes that are plain bins, compressed runs, nodes per run} (all 0 when `level` does not exist),
  * spec4 = {mchirp_min, tau_max, reach in rad, slope margin}. */
 #define BJ_COMPRESS_LEVELS 2
@@ -306,7 +307,7 @@ int bj_compress_info(bj_ctx* ctx, int32_t level, int32_t* info4, double* spec4);
 int bj_last_levels(bj_ctx* ctx, int64_t n_walkers, int32_t* levels);
 /* Host-only (no device needed): the node axis made of a weighted frequency axis -- weights_ri[i] = interleaved (re, im)
  * per bin and detector.  out_freqs / out_weights_ri[i] must hold n_bins (2 n_bins) doubles; *out_n = number of nodes.
- * Non-positive nodes_per_run / reach_rad / mchirp_min / tau_max / margin = the library defaults (32, 10, 0.5, 0.11, 1.3).
+ * Non-positive nodes_per_run / reach_rad / mchirp_min / tau_max / margin = the library defaults (64, 32, 0.8, 0.11, 1.3).
  * For any g(f) whose phase slope respects the design, sum_j W_j g(f_j) reproduces sum_k w_k g(f_k) to ~1e-11 of
  * sum_k |w_k g(f_k)| (tests/test_compress_host.py). */
 int bj_compress_axis_host(int64_t n_bins, const double* freqs, int32_t n_ifo, const double* const* weights_ri,

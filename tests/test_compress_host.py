@@ -17,11 +17,11 @@ from oracle import bajes_port as port, harness
 GT = 4.92549094830932e-6      # taylorf2.py:6
 
 
-def design_budget(f, mchirp_min=0.5, tau_max=0.11, margin=1.3):
+def design_budget(f, mchirp_min=0.8, tau_max=0.11, margin=1.3):
     return margin * 5.0 / 256.0 * (mchirp_min * GT) ** (-5.0 / 3.0) * (np.pi * f) ** (-8.0 / 3.0) + tau_max
 
 
-def numpy_axis(f, w, n=32, reach=10.0, **kw):
+def numpy_axis(f, w, n=64, reach=32.0, **kw):
     """independent restatement: greedy runs, first-kind Chebyshev nodes, Lagrange cardinal sums (plain products)"""
     nf, nw = [], []
     k, N = 0, len(f)
@@ -67,7 +67,7 @@ def test_node_axis_matches_an_independent_numpy_construction(axis):
     f, w = axis
     nf, nw, info = engine.compress_axis(f, w)
     rf, rw = numpy_axis(f, w)
-    assert info["nodes"] == len(nf) == len(rf) and info["nodes_per_block"] == 32
+    assert info["nodes"] == len(nf) == len(rf) and info["nodes_per_block"] == 64
     assert np.all(np.diff(nf) > 0), "node frequencies must ascend"
     assert np.allclose(nf, rf, rtol=1e-14, atol=0)
     scale = np.max(np.abs(rw))
@@ -76,11 +76,11 @@ def test_node_axis_matches_an_independent_numpy_construction(axis):
     kept = 0
     while kept < len(nf) and nf[kept] == f[kept]:
         kept += 1
-    assert kept >= 32 and np.array_equal(nw[:, :kept], w[:, :kept])
+    assert kept >= 64 and np.array_equal(nw[:, :kept], w[:, :kept])
     assert len(nf) < len(f) / 4
 
 
-@pytest.mark.parametrize("mchirp,tau", [(0.5, 0.109), (0.7, -0.1), (1.2, 0.003), (30.0, 0.05)])
+@pytest.mark.parametrize("mchirp,tau", [(0.8, 0.109), (0.9, -0.1), (1.2, 0.003), (30.0, 0.05)])
 def test_bin_sum_is_reproduced_inside_the_design(axis, mchirp, tau):
     f, w = axis
     nf, nw, _ = engine.compress_axis(f, w)

@@ -61,7 +61,7 @@ def test_walkers_outside_the_design_are_routed_to_the_table_that_covers_them(c2)
     X[0::6, it] = 0.4            # beyond level 0 (0.11 s), inside level 1 (1.1 s)
     X[1::6, it] = -0.9
     X[2::6, it] = 1.7            # beyond both: full grid
-    X[3::6, im] = 0.35           # lighter than the design: full grid
+    X[3::6, im] = 0.3            # lighter than both levels (0.8 / 0.4): full grid
     X[4, im] = 0.02              # sub-solar: wide-phase path on the full grid
     got = comp.log_like_batch(X, names, const)
     c0, c1, cf = comp.engine.last_level_counts()
