@@ -10,4 +10,4 @@ for line in open('gpurun_out/r02_bench_${N}gpu.json'):
         for k,v in d['secondary'].items(): print(k, v.get('value'), v.get('e2e',{}).get('value'), v.get('parity_max_err_over_tol'), v.get('chain_bit_identical_to_one_gpu'))
         print(d['secondary']['C5']['ptmcmc']['value'], d['secondary']['C5']['ptmcmc']['chain_bit_identical_to_one_gpu'])
 P
-python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -3
+if [ "$2" = "test" ]; then python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -3; fi
