@@ -153,6 +153,10 @@ def cfg_bins(cfg):
 # clocks sampler (nvidia-smi, 50 ms) -- runs during the timed region
 # ---------------------------------------------------------------------------------------------------------
 class Clocks:
+    """SM clock, throttle reasons and power of this rank's GPU, sampled INSIDE the timed region but BETWEEN the event-timed
+    steps: one in-process NVML query after every step's synchronisation (a step is ~0.3 ms now; a polling nvidia-smi
+    process holds a driver lock for longer than that whenever it fires, and did show up as 0.1 ms on the sampling rank's
+    mean step).  Falls back to an ``nvidia-smi -lms`` subprocess when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
@@ -161,14 +165,32 @@ class Clocks:
         self.rows = []
         self.proc = None
         self.first = 0
+        self.nv = None
+        self.samples = []
 
     def start(self):
-        """Launch the sampler and wait until it delivers: nvidia-smi attaches to every GPU of the box when it starts
-        (seconds on an 8-GPU node, and kernel launches of all ranks stall meanwhile), so that must be over before the
-        timed region begins."""
         if os.environ.get("BENCH_NO_CLOCKS"):
             return
         try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = (pynvml, h)
+            self.sample()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            # nvidia-smi attaches to every GPU of the box when it starts (seconds on an 8-GPU node, and kernel launches of
+            # all ranks stall meanwhile), so that must be over before the timed region begins
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -180,15 +202,45 @@ class Clocks:
         except Exception:
             self.proc = None
 
+    def sample(self):
+        """one NVML query (between two timed steps)"""
+        if self.nv is None:
+            return
+        nv, h = self.nv
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            self.samples.append((float(sm), float(mx), int(mask), float(pw)))
+        except Exception:
+            pass
+
     def mark(self):
         """Start of the timed region: only samples from here on (and the one just before) are reported."""
         self.first = max(0, len(self.rows) - 1)
+        self.first_sample = max(0, len(self.samples) - 1)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            nv, _ = self.nv
+            rows = self.samples[getattr(self, "first_sample", 0):]
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, b in bits.items() if any(r[2] & b for r in rows))
+            return {"sm_mhz": float(np.median([r[0] for r in rows])) if rows else None,
+                    "sm_max_mhz": max(r[1] for r in rows) if rows else None, "reasons": reasons,
+                    "power_w_max": max(r[3] for r in rows) if rows else None, "samples": len(rows),
+                    "source": "NVML in process, one query after every timed step"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.08)
@@ -210,7 +262,8 @@ class Clocks:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "source": "nvidia-smi -lms 50"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -767,6 +820,8 @@ def main():
         b.record()
         b.synchronize()
         kern_ms.append(like.engine.last_kernel_ms()[1])
+        if rank == 0:
+            clocks.sample()                        # between two timed steps
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
