@@ -107,3 +107,25 @@ def test_inner_products_and_single_point_api_on_the_node_axis(c2):
         assert abs(dh_a - dh_b) <= 1e-4 + 1e-6 * abs(dh_b)
         assert abs(hh_a - hh_b) <= 1e-9 * abs(hh_b)
     assert comp.log_like(dict(p)) == comp.log_like_batch(x.reshape(1, -1), names, const)[0]
+
+
+@pytest.mark.parametrize("n_ifo,marg,approx", [(1, False, "TaylorF2_3.5PN"), (2, True, "TaylorF2_5.5PN_3.5PNQM_7.5PNTides"),
+                                               (3, True, "TaylorF2_3.5PN")])
+def test_smaller_networks_and_phase_marginalisation_on_the_node_axis(c2, n_ifo, marg, approx):
+    """the other instantiations of the unified launch: one and two detectors, the generic (K = 28) phase basis, ln I0"""
+    cfg, gold, net, names, const = c2
+    ifos, datas, dets, noises, f = net
+    sub = (ifos[:n_ifo], {k: datas[k] for k in ifos[:n_ifo]}, {k: dets[k] for k in ifos[:n_ifo]},
+           {k: noises[k] for k in ifos[:n_ifo]}, f)
+    comp = _like(cfg, sub, approx=approx, marg_phi_ref=marg)
+    ref = _like(cfg, sub, approx=approx, marg_phi_ref=marg, sincos="fp64")
+    assert comp.engine.compress_info(0)["nodes"] > 0
+    Xn, _ = syn.draw_walkers(cfg, 1500, 61, "narrow")
+    Xw, _ = syn.draw_walkers(cfg, 1500, 62, "wide")
+    X = np.concatenate([Xn, Xw])
+    X[5::50, names.index("time_shift")] = 0.5          # some on level 1
+    X[7::50, names.index("mchirp")] = 0.2              # some on the full grid
+    r = _ratio(comp.log_like_batch(X, names, const), ref.log_like_batch(X, names, const))
+    counts = comp.engine.last_level_counts()
+    print("%d detector(s), marg_phi=%s, %s: %.3f tol, tables %s" % (n_ifo, marg, approx, r, counts))
+    assert r <= 0.8 and min(counts) > 0
