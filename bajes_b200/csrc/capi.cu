@@ -141,6 +141,11 @@ struct bj_ctx {
     int cmp_info[kMaxLevels][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // nodes, nodes that are plain bins, blocks, nodes per block
     double cmp_spec[kMaxLevels][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};   // mchirp_min, tau_max, reach, margin
     long last_walkers = 0;
+    // focus table (bj_focus): all-FP64 node records around a fiducial point; host copies of the grid's weights to build it
+    std::vector<double> h_freqs, h_wts[BJ_MAX_IFO];
+    bj_ctx* focus = nullptr;          // owns d_rec (FP64 records), d_chunks
+    double* d_fid = nullptr;          // {A_0..15, B_0..6, C8, tau_0..2} of the fiducial point
+    int focus_info[4] = {0, 0, 0, 0};
 };
 
 static int check_config(const bj_config* cfg) {
@@ -697,11 +702,14 @@ static int build_mixed_set(bj_ctx* c, const bj_config* cfg, const Axis& ax, cons
 struct CompressSpec {
     int on, nodes;
     double reach, mchirp_min, tau_max, margin;
+    int focus = 0;       // budget relative to a fiducial point (bj_focus): a (f / f0)^(-5/3) + b + c (f / f1)^(2/3)
+    double focus_a = 0.0, focus_b = 0.0, focus_c = 0.0, focus_f0 = 1.0, focus_f1 = 1.0;
 };
 static CompressSpec compress_spec(const bj_extras* ex) {
     // 64 nodes per run of +-32 rad: the Chebyshev truncation error 2 (reach/2)^n / n! is ~1e-12 there, and longer runs leave
     // fewer nodes (C2: 17 728; 32 nodes of +-10 rad: 22 560) at the same worst-walker error (profiles/r02_compress_nodes.txt)
-    CompressSpec sp = {1, 64, 32.0, 0.8, 0.11, 1.3};
+    CompressSpec sp;
+    sp.on = 1; sp.nodes = 64; sp.reach = 32.0; sp.mchirp_min = 0.8; sp.tau_max = 0.11; sp.margin = 1.3;
     if (ex && ex->compress != 0) {
         sp.on = ex->compress > 0;
         if (ex->compress_mchirp_min > 0.0) sp.mchirp_min = ex->compress_mchirp_min;
@@ -716,6 +724,8 @@ static CompressSpec compress_spec(const bj_extras* ex) {
 }
 // seconds: the design bound on |d(Phi/2pi)/df| + |tau_i| at frequency f  (gt: taylorf2.py:6)
 static double design_budget(const CompressSpec& sp, double f) {
+    if (sp.focus)
+        return sp.focus_a * std::pow(f / sp.focus_f0, -5.0 / 3.0) + sp.focus_b + sp.focus_c * std::pow(f / sp.focus_f1, 2.0 / 3.0);
     const double t = 5.0 / 256.0 * std::pow(sp.mchirp_min * 4.92549094830932e-6, -5.0 / 3.0) * std::pow(M_PI * f, -8.0 / 3.0);
     return sp.margin * t + sp.tau_max;
 }
@@ -967,6 +977,10 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
             if (et != cudaSuccess) { bj_destroy(c); return fail(BJ_ERR_CUDA, "uploading the per-detector data records failed: %s", cudaGetErrorString(et)); }
         }
         if (c->n_levels > 0) {
+            c->h_freqs.assign(freqs, freqs + n_bins);
+            for (int i = 0; i < cfg->n_ifo; ++i) c->h_wts[i] = wts[i];
+        }
+        if (c->n_levels > 0) {
             // check frequencies of classify_kernel: log-spaced over the band, both ends included
             c->steep.n = kSteepChecks;
             c->steep.n_levels = c->n_levels;
@@ -977,7 +991,8 @@ extern "C" int bj_create_ex(bj_ctx** out, const bj_config* cfg, int64_t n_bins, 
                 c->steep.w5[q] = std::pow(f, -5.0 / 3.0);
                 c->steep.inv_f[q] = 1.0 / f;
             }
-            if (cudaMalloc(&c->d_counts, (kMaxLevels + 1) * sizeof(int)) != cudaSuccess) {
+            c->steep.focus = 0;
+            if (cudaMalloc(&c->d_counts, (kMaxLevels + 2) * sizeof(int)) != cudaSuccess) {
                 bj_destroy(c);
                 return fail(BJ_ERR_CUDA, "allocating the work-list counters failed");
             }
@@ -1008,6 +1023,13 @@ extern "C" int bj_destroy(bj_ctx* c) {
         delete m;
         c->cmp[lv] = nullptr;
     }
+    if (c->focus) {
+        cudaFree(c->focus->d_rec);
+        cudaFree(c->focus->d_chunks);
+        delete c->focus;
+        c->focus = nullptr;
+    }
+    cudaFree(c->d_fid);
     cudaFree(c->d_lists);
     cudaFree(c->d_counts);
     cudaFree(c->d_rec);
@@ -1059,11 +1081,12 @@ static int ensure_workspace(bj_ctx* c, long n_walkers) {
     if (c->kind == KIND_FULLGRID) {
         int nch = c->n_chunks;
         for (int lv = 0; lv < c->n_levels; ++lv) nch = std::max(nch, c->cmp[lv]->n_chunks);
+        if (c->focus) nch = std::max(nch, c->focus->n_chunks);
         part = (size_t)nch * 2 * c->cfg.n_ifo * cap;
     }
     if (c->n_levels > 0) {
         cudaFree(c->d_lists); c->d_lists = nullptr;
-        CUDA_TRY(cudaMalloc(&c->d_lists, (size_t)(c->n_levels + 1) * cap * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&c->d_lists, (size_t)(c->n_levels + 2) * cap * sizeof(int)));
     }
     if (part) CUDA_TRY(cudaMalloc(&c->d_partial, part * sizeof(double)));
     CUDA_TRY(cudaMalloc(&c->d_logl, (size_t)cap * sizeof(double)));
@@ -1115,7 +1138,7 @@ static int launch_fullgrid_fp64(bj_ctx* c, long n_walkers, cudaStream_t st, int 
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(c1 - c0), (unsigned)((n_walkers + kThreads - 1) / kThreads));
     kern<<<grid, kThreads, smem, st>>>((const double*)c->d_rec, c->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
-                                       c->d_partial, c->d_coef_ex, c->dims, c->d_spcal_freqs, c0, sel);
+                                       c->d_partial, c->d_coef_ex, c->dims, c->d_spcal_freqs, c0, sel, nullptr);
     CUDA_TRY(cudaGetLastError());
     note_launch(c, grid, smem, RS, MODEL);
     return BJ_OK;
@@ -1141,7 +1164,7 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
             CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
             pk<<<pgrid, kThreads, smem64, st>>>(c->d_rec64 - (size_t)c->prec_lo * RS, c->d_chunks, c->d_coef,
                                                 c->cap_walkers, n_walkers, c->d_partial, c->d_coef_ex, c->dims,
-                                                c->d_spcal_freqs, c0, sel);
+                                                c->d_spcal_freqs, c0, sel, nullptr);
         }
         CUDA_TRY(cudaGetLastError());
         c0 = p1;
@@ -1233,13 +1256,24 @@ static int launch_epilogue(bj_ctx* c, long n_walkers, cudaStream_t st, double* l
 }
 
 // ---- contexts with compressed axes: ONE launch per kernel type over all tables (kernels.cuh: MultiTable) -----------------
-static MultiTable multi_table(const bj_ctx* c) {
+static MultiTable multi_table(const bj_ctx* c, bool for_epilogue) {
     MultiTable mt;
     memset(&mt, 0, sizeof(mt));
     mt.n = c->n_levels + 1;
     mt.list_stride = c->cap_walkers;
     mt.lists = c->d_lists;
     mt.counts = c->d_counts;
+    if (c->focus) {
+        // the focus table is list n_levels + 1: evaluated by its own FP64 launch (no window / tile chunks), finished by the
+        // common epilogue (FP64 records are unscaled: <d|h> correction 1)
+        mt.n = c->n_levels + 2;
+        TableRef& F = mt.t[c->n_levels + 1];
+        F.chunks = c->focus->d_chunks;
+        F.n_chunks = for_epilogue ? c->focus->n_chunks : 0;
+        F.n_precise = 0;
+        F.dh_fix_re = 1.0;
+        F.dh_fix_im = 0.0;
+    }
     for (int lv = 0; lv <= c->n_levels; ++lv) {
         const bj_ctx* m = lv < c->n_levels ? c->cmp[lv] : c;
         TableRef& T = mt.t[lv];
@@ -1258,7 +1292,7 @@ static MultiTable multi_table(const bj_ctx* c) {
 
 template <int NIFO, int MODEL, int SC>
 static int launch_multi(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl, double* parts) {
-    const MultiTable mt = multi_table(c);
+    const MultiTable mt = multi_table(c, false);
     constexpr int RB = RecM<NIFO>::kBytes;
     constexpr int RS = Rec<NIFO>::kDoubles;
     int max_precise = 0, max_fast = 0;
@@ -1298,10 +1332,24 @@ static int launch_multi(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl
                                             c->d_partial, nullptr, c->dims, c->n_precise);
         CUDA_TRY(cudaGetLastError());
     }
+    if (c->focus) {
+        // walkers next to the fiducial point: a few hundred nodes, all FP64 (fullgrid_kernel with the fiducial subtracted)
+        bj_ctx* f = c->focus;
+        const size_t smem64 = (size_t)kStages * kTileBins * RS * 8 + kStages * sizeof(uint64_t);
+        auto fk = fullgrid_kernel<NIFO, MODEL, BJ_SINCOS_FP64, false>;
+        CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+        const int lf = c->n_levels + 1;
+        const Sel sf = {c->d_lists + (size_t)lf * c->cap_walkers, c->d_counts + lf};
+        dim3 fgrid((unsigned)f->n_chunks, (unsigned)((n_walkers + kThreads - 1) / kThreads));
+        fk<<<fgrid, kThreads, smem64, st>>>((const double*)f->d_rec, f->d_chunks, c->d_coef, c->cap_walkers, n_walkers,
+                                            c->d_partial, nullptr, c->dims, nullptr, 0, sf, c->d_fid);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaEventRecord(c->ev[2], st));
-    epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers + mt.n - 1), kEpiWalkers * kEpiSlices, 0, st>>>(
+    const MultiTable me = multi_table(c, true);
+    epilogue_kernel<<<(unsigned)((n_walkers + kEpiWalkers - 1) / kEpiWalkers + me.n - 1), kEpiWalkers * kEpiSlices, 0, st>>>(
         c->cfg, epilogue_tables(c), c->dims, c->d_partial, c->d_coef, nullptr, c->cap_walkers, n_walkers, logl, parts, 0, 0, 0,
-        nullptr, none, mt);
+        nullptr, none, me);
     CUDA_TRY(cudaGetLastError());
     return BJ_OK;
 }
@@ -1611,7 +1659,177 @@ extern "C" int bj_last_levels(bj_ctx* c, int64_t n_walkers, int32_t* levels) {
     CUDA_TRY(cudaDeviceSynchronize());
     std::vector<double> lv((size_t)n_walkers);
     CUDA_TRY(cudaMemcpy(lv.data(), c->d_coef + (size_t)C_STEEP * c->cap_walkers, lv.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int64_t w = 0; w < n_walkers; ++w) levels[w] = (int)lv[w] >= c->n_levels ? kMaxLevels : (int)lv[w];
+    for (int64_t w = 0; w < n_walkers; ++w)
+        levels[w] = (int)lv[w] > c->n_levels ? kMaxLevels + 1 : (int)lv[w] == c->n_levels ? kMaxLevels : (int)lv[w];
+    return BJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Focus table: the compressed axis taken to its limit around ONE point (the region a converged sampler lives in).
+// With the fiducial point's phase P_fid(f) and delays tau_fid,i folded into the data weights,
+//     w'_ik = w_ik exp(-2 pi i [P_fid(f_k) + f_k tau_fid,i]),
+// a walker's smooth factor is g'_i = Q exp(-2 pi i [(P - P_fid)(f) + f (tau_i - tau_fid,i)]): the kernels subtract the
+// fiducial's coefficients (the phase is linear in them, so this costs nothing per node), and the design bound is on the
+// slope RELATIVE to the fiducial,  |d(P - P_fid)/df| + max_i |tau_i - tau_fid,i| <= a (f / f_lo)^(-5/3) + b + c (f / f_hi)^(2/3)
+// -- seconds, not the minutes of a chirp (a: masses and spins move the low-frequency end, b: sky position and time shift,
+// c: tidal deformabilities act at the top of the band): the whole band collapses into a few runs of 64 nodes (C2: 521 729
+// bins -> ~700), which are evaluated in FP64 throughout.  classify_kernel sends a walker there only if it respects that bound at every check
+// frequency; everybody else is routed as before.  Relative binning (binning.py) is the first-order version of this with no
+// bound and no fallback; this is exact to the truncation of the Chebyshev interpolant (~1e-12).
+// ------------------------------------------------------------------------------------------------
+static void drop_focus(bj_ctx* c) {
+    if (c->focus) {
+        cudaFree(c->focus->d_rec);
+        cudaFree(c->focus->d_chunks);
+        delete c->focus;
+        c->focus = nullptr;
+    }
+    c->steep.focus = 0;
+    for (int q = 0; q < 4; ++q) c->focus_info[q] = 0;
+}
+
+extern "C" int bj_unfocus(bj_ctx* c) {
+    if (!c) return fail(BJ_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    drop_focus(c);
+    return BJ_OK;
+}
+
+extern "C" int bj_focus(bj_ctx* c, const double* x_host, int32_t ndim, const bj_param_map* map, double slope_a,
+                        double slope_b, double slope_c, int32_t* info4) {
+    if (!c || !x_host) return fail(BJ_ERR_INVALID, "null argument");
+    if (c->kind != KIND_FULLGRID || c->n_levels == 0)
+        return fail(BJ_ERR_UNSUPPORTED, "a focus table needs a full-grid context with compressed axes");
+    int rc = check_map(map, ndim);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    drop_focus(c);
+    if (!(slope_a > 0.0)) slope_a = 0.25;
+    if (!(slope_b > 0.0)) slope_b = 2e-3;
+    if (!(slope_c >= 0.0)) slope_c = 0.03;
+    // the fiducial point's coefficient vector, from the prologue itself
+    ParamMapDev pm;
+    to_dev_map(map, pm);
+    double *d_x = nullptr, *d_coef = nullptr;
+    std::vector<double> coef(C_NUM, 0.0);
+    cudaError_t e = cudaMalloc(&d_x, ndim * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_coef, (size_t)C_NUM * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_x, x_host, ndim * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        prologue_kernel<<<1, dim3(kProWalkers, 1 + BJ_MAX_IFO)>>>(c->cfg, pm, d_x, ndim, 1, d_coef, 1, nullptr);
+        e = cudaMemcpy(coef.data(), d_coef, C_NUM * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_x);
+    cudaFree(d_coef);
+    if (e != cudaSuccess) return fail(BJ_ERR_CUDA, "bj_focus: %s", cudaGetErrorString(e));
+    if (coef[C_VALID] != 1.0) return fail(BJ_ERR_INVALID, "the fiducial point is unphysical or needs the wide-phase path");
+    const int nifo = c->cfg.n_ifo;
+    const long N = (long)c->h_freqs.size();
+    double fid[24 + BJ_MAX_IFO];
+    for (int j = 0; j < 16; ++j) fid[j] = coef[C_A0 + j];
+    for (int j = 0; j < 7; ++j) fid[16 + j] = coef[C_B0 + j];
+    fid[23] = coef[C_C8];
+    for (int i = 0; i < BJ_MAX_IFO; ++i) fid[24 + i] = i < nifo ? coef[C_TAU0 + i] : 0.0;
+    // heterodyned weights (long double: P_fid ~ 1e4..1e5 turns, wanted to 1e-12 of a turn)
+    std::vector<double> hw[BJ_MAX_IFO];
+    for (int i = 0; i < nifo; ++i) hw[i].assign((size_t)2 * N, 0.0);
+    for (long k = 0; k < N; ++k) {
+        const long double f = c->h_freqs[k];
+        const long double u = cbrtl(f), L = logl(f), w5 = 1.0L / (u * u * u * u * u);
+        long double up = 1.0L, sa = 0.0L, sb = 0.0L;
+        for (int j = 0; j < 16; ++j) {
+            sa += (long double)fid[j] * up;
+            if (j < 7) sb += (long double)fid[16 + j] * up;
+            up *= u;
+        }
+        const long double P = w5 * sa + L * sb + L * L * (long double)fid[23] * u * u * u;
+        for (int i = 0; i < nifo; ++i) {
+            long double t = P + f * (long double)fid[24 + i];
+            t -= rintl(t);
+            const long double cs = cosl(-2.0L * M_PIl * t), sn = sinl(-2.0L * M_PIl * t);
+            const long double wr = c->h_wts[i][2 * k], wi = c->h_wts[i][2 * k + 1];
+            hw[i][2 * k] = (double)(wr * cs - wi * sn);
+            hw[i][2 * k + 1] = (double)(wr * sn + wi * cs);
+        }
+    }
+    Axis ax;
+    ax.n = N;
+    ax.f = c->h_freqs.data();
+    for (int i = 0; i < nifo; ++i) ax.w[i] = hw[i].data();
+    // runs from the focus budget: build_compressed_axis with budget(f) = a (f / f_lo)^(-5/3) + b
+    CompressSpec sp = compress_spec(nullptr);
+    sp.focus = 1;
+    sp.focus_a = slope_a;
+    sp.focus_b = slope_b;
+    sp.focus_c = slope_c;
+    sp.focus_f0 = c->h_freqs[0];
+    sp.focus_f1 = c->h_freqs[N - 1];
+    std::vector<double> bw((size_t)N, 1.0), nf, nbw, nwt[BJ_MAX_IFO];
+    int info[4] = {0, 0, 0, 0};
+    build_compressed_axis(ax, nifo, bw, sp, nf, nwt, nbw, info);
+    Axis cx;
+    cx.n = (long)nf.size();
+    cx.f = nf.data();
+    for (int i = 0; i < nifo; ++i) cx.w[i] = nwt[i].data();
+    bj_ctx* m = new bj_ctx();
+    m->kind = KIND_FULLGRID;
+    m->shadow = true;
+    m->device = c->device;
+    m->cfg = c->cfg;
+    memset(&m->dims, 0, sizeof(m->dims));
+    m->n_bins = cx.n;
+    Layout L;
+    // all FP64: no window, chunks of one TMA tile (64 records) -- a few hundred nodes make few CTAs as it is
+    if (build_layout(L, cx.n, cx.f, nullptr, nullptr, 0.0, 0.0)) { delete m; return fail(BJ_ERR_INVALID, "focus layout"); }
+    {
+        std::vector<ChunkDesc> small;
+        for (const ChunkDesc& cd : L.chunks)
+            for (int a0 = 0; a0 < cd.len; a0 += kTileBins) {
+                ChunkDesc s = cd;
+                s.start = cd.start + a0;
+                s.len = std::min(kTileBins, cd.len - a0);
+                small.push_back(s);
+            }
+        L.chunks = small;
+    }
+    adopt_layout(m, L);
+    std::vector<double> rec;
+    switch (nifo) {
+        case 1: build_records<1>(rec, L, cx, c->cfg.seglen); break;
+        case 2: build_records<2>(rec, L, cx, c->cfg.seglen); break;
+        default: build_records<3>(rec, L, cx, c->cfg.seglen); break;
+    }
+    for (double v : rec)
+        if (!std::isfinite(v)) { delete m; return fail(BJ_ERR_INVALID, "non-finite focus table entry"); }
+    e = cudaMalloc(&m->d_rec, rec.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_rec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = upload(&m->d_chunks, L.chunks);
+    if (e == cudaSuccess && !c->d_fid) e = cudaMalloc(&c->d_fid, sizeof(fid));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_fid, fid, sizeof(fid), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(m->d_rec);
+        cudaFree(m->d_chunks);
+        delete m;
+        return fail(BJ_ERR_CUDA, "uploading the focus table failed: %s", cudaGetErrorString(e));
+    }
+    c->focus = m;
+    c->steep.focus = 1;
+    for (int q = 0; q < 24 + BJ_MAX_IFO; ++q) c->steep.fid[q] = fid[q];
+    for (int q = 0; q < kSteepChecks; ++q) {
+        const double f = c->h_freqs[0] * std::pow(c->h_freqs[N - 1] / c->h_freqs[0], (double)q / (double)(kSteepChecks - 1));
+        c->steep.budget_focus[q] = design_budget(sp, f);
+    }
+    for (int q = 0; q < 4; ++q) c->focus_info[q] = info[q];
+    if (info4) for (int q = 0; q < 4; ++q) info4[q] = info[q];
+    // the partial-sum buffer may have to grow for the focus table's chunk count
+    if (c->cap_walkers > 0 && m->n_chunks > 0) {
+        const long keep = c->cap_walkers;
+        c->cap_walkers = 0;
+        rc = ensure_workspace(c, keep);
+        if (rc) return rc;
+    }
     return BJ_OK;
 }
 
@@ -1651,15 +1869,16 @@ extern "C" int bj_compress_info(bj_ctx* c, int32_t level, int32_t* info4, double
 
 extern "C" int bj_last_level_counts(bj_ctx* c, int64_t* counts3) {
     if (!c || !counts3) return fail(BJ_ERR_INVALID, "null argument");
-    for (int q = 0; q <= kMaxLevels; ++q) counts3[q] = 0;
+    for (int q = 0; q <= kMaxLevels + 1; ++q) counts3[q] = 0;
     if (c->n_levels == 0 || c->last_walkers <= 0) return BJ_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    int h[kMaxLevels + 1];
+    int h[kMaxLevels + 2];
     CUDA_TRY(cudaMemcpy(h, c->d_counts, sizeof(h), cudaMemcpyDeviceToHost));
-    // levels that do not exist stay 0; the full grid is always reported last
+    // levels that do not exist stay 0; the full grid is always reported third, the focus table fourth
     for (int q = 0; q < c->n_levels; ++q) counts3[q] = h[q];
     counts3[kMaxLevels] = h[c->n_levels];
+    counts3[kMaxLevels + 1] = c->focus ? h[c->n_levels + 1] : 0;
     return BJ_OK;
 }
 

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kProWalkers * (1 + BJ_MAX_IFO))
 prologue_kernel(DeviceConfig cfg, ParamMapDev pm, const double* __restrict__ x, int ndim, long n_walkers,
                 double* __restrict__ coef, long stride, int* __restrict__ list_counts) {
     // work-list counters of classify_kernel (contexts with compressed axes), zeroed here to save a memset node
-    if (list_counts && blockIdx.x == 0 && threadIdx.y == 0 && threadIdx.x <= kMaxLevels) list_counts[threadIdx.x] = 0;
+    if (list_counts && blockIdx.x == 0 && threadIdx.y == 0 && threadIdx.x <= kMaxLevels + 1) list_counts[threadIdx.x] = 0;
     __shared__ double s_tau[BJ_MAX_IFO][kProWalkers];
     __shared__ int s_ok[BJ_MAX_IFO][kProWalkers];
     const int lane = threadIdx.x, role = threadIdx.y;
@@ -311,6 +311,11 @@ struct SteepTable {
     int n, n_levels;
     double u[kSteepChecks], L[kSteepChecks], w5[kSteepChecks], inv_f[kSteepChecks];
     double budget[kMaxLevels][kSteepChecks];
+    // focus table (capi.cu: bj_focus): budget on the slope RELATIVE to a fiducial point, whose coefficients and delays are
+    // fid = {A_0..15, B_0..6, C8, tau_0..2}; focus == 0: none.  Its work list is number n_levels + 1.
+    int focus;
+    double budget_focus[kSteepChecks];
+    double fid[24 + BJ_MAX_IFO];
 };
 // work list of one table: idx[0 .. *count) are walker indices (idx == nullptr: all walkers, in order)
 struct Sel {
@@ -334,7 +339,7 @@ struct MultiTable {
     long list_stride;
     const int* lists;                // [n][list_stride]
     const int* counts;               // [n]
-    TableRef t[kMaxLevels + 1];
+    TableRef t[kMaxLevels + 2];      // compressed levels, the full grid, the focus table
 };
 __device__ __forceinline__ bool resolve_tile(const MultiTable& mt, int tile, int by, int& lv, long& entry0, long& n_sel) {
     int t0 = 0;
@@ -378,8 +383,25 @@ __global__ void __launch_bounds__(128) classify_kernel(SteepTable tab, int n_ifo
 #pragma unroll
     for (int i = 0; i < BJ_MAX_IFO; ++i) tmax = fmax(tmax, fabs(tau[i]));
     const double need = fabs(slope) + tmax;
+    bool in_focus = false;
+    if (tab.focus) {
+        double upf = 1.0, saf = 0.0, sbf = 0.0, dtau = 0.0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            saf = fma((a[j] - tab.fid[j]) * ((double)(j - 5) * (1.0 / 3.0)), upf, saf);
+            if (j < 7) sbf = fma((b[j] - tab.fid[16 + j]) * fma(L, (double)j * (1.0 / 3.0), 1.0), upf, sbf);
+            upf *= u;
+        }
+        const double rel = tab.inv_f[c] * (tab.w5[c] * saf + sbf + (c8 - tab.fid[23]) * u * u * u * (2.0 * L + L * L));
+#pragma unroll
+        for (int i = 0; i < BJ_MAX_IFO; ++i)
+            if (i < n_ifo) dtau = fmax(dtau, fabs(tau[i] - tab.fid[24 + i]));
+        const bool badf = lane < tab.n && !(fabs(rel) + dtau <= tab.budget_focus[c]);
+        in_focus = !__any_sync(0xffffffffu, badf);
+    }
     int level = tab.n_levels;                      // n_levels = the full grid
     if (valid == 0.0) level = 0;
+    else if (valid == 1.0 && in_focus) level = tab.n_levels + 1;
     else if (valid == 1.0) {
         for (int lv = tab.n_levels - 1; lv >= 0; --lv) {
             const bool bad = lane < tab.n && !(need <= tab.budget[lv][c]);
@@ -524,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
                                                                  long n_walkers, double* __restrict__ partial,
                                                                  const double* __restrict__ coef_ex, ExtrasDims dims,
                                                                  const double* __restrict__ spcal_freqs, int chunk0,
-                                                                 Sel sel) {
+                                                                 Sel sel, const double* __restrict__ fid) {
     constexpr int RS = Rec<NIFO>::kDoubles;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
@@ -552,6 +574,19 @@ __global__ void __launch_bounds__(kThreads, 4) fullgrid_kernel(const double* __r
     w.q6l = coef[C_Q6L * stride + wl];
 #pragma unroll
     for (int i = 0; i < NIFO; ++i) w.tau[i] = coef[(C_TAU0 + i) * stride + wl];
+    if (fid) {
+        // focus table (capi.cu: bj_focus): the fiducial phase and delays live in the data weights -- the walker is evaluated
+        // relative to them.  fid = {A_0..15, B_0..6, C8, tau_0..}
+#pragma unroll
+        for (int j = 0; j < WalkerRegs<NIFO, MODEL>::NA; ++j) w.a[j] -= fid[j];
+        w.a10 -= fid[10];
+        w.a12 -= fid[12];
+#pragma unroll
+        for (int j = 0; j < WalkerRegs<NIFO, MODEL>::NBQ; ++j) w.bq[j] -= fid[16 + j];
+        w.c8 -= fid[23];
+#pragma unroll
+        for (int i = 0; i < NIFO; ++i) w.tau[i] -= fid[24 + i];
+    }
 
     double zr[NIFO], zi[NIFO];
 #pragma unroll

@@ -144,6 +144,9 @@ EXPORTS = {
     "bj_compress_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), _DP]),
     "bj_last_level_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "bj_last_levels": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
+    "bj_focus": (C.c_int, [C.c_void_p, _DP, C.c_int32, C.POINTER(bj_param_map), C.c_double, C.c_double, C.c_double,
+                           C.POINTER(C.c_int32)]),
+    "bj_unfocus": (C.c_int, [C.c_void_p]),
     "bj_compress_axis_host": (C.c_int, [C.c_int64, _DP, C.c_int32, _DPP, C.c_int32, C.c_double, C.c_double, C.c_double,
                                         C.c_double, C.POINTER(C.c_int64), _DP, _DPP, C.POINTER(C.c_int32)]),
 }
@@ -386,6 +389,7 @@ class Engine:
         self.n_ifo = n_ifo
         self.kind = kind
         self.n_bins = n_bins
+        self._focused = False
 
     # -- constructors --------------------------------------------------------------------------
     @classmethod
@@ -541,10 +545,26 @@ class Engine:
         return out
 
     def last_level_counts(self):
-        """Walkers of the last call per table: (level 0, level 1, full grid).  Synchronises."""
-        n = (C.c_int64 * 3)()
+        """Walkers of the last call per table: (level 0, level 1, full grid); with a focus table a fourth entry counts the
+        walkers it evaluated.  Synchronises."""
+        n = (C.c_int64 * 4)()
         _check(self._lib, self._lib.bj_last_level_counts(self._h, n), "bj_last_level_counts")
-        return tuple(int(v) for v in n)
+        out = tuple(int(v) for v in n)
+        return out if self._focused else out[:3]
+
+    def focus(self, x: np.ndarray, pmap: "ParamMap", slope_a: float = 0.0, slope_b: float = 0.0,
+              slope_c: float = -1.0) -> Dict[str, int]:
+        """Build the focus table around the point ``x`` (include/bajes_b200.h: bj_focus).  Returns its node counts."""
+        x = _as_f64(x).reshape(-1)
+        info = (C.c_int32 * 4)()
+        _check(self._lib, self._lib.bj_focus(self._h, _ptr(x), x.size, C.byref(pmap.c), float(slope_a), float(slope_b),
+                                             float(slope_c), info), "bj_focus")
+        self._focused = True
+        return {"nodes": int(info[0]), "kept_bins": int(info[1]), "blocks": int(info[2]), "nodes_per_block": int(info[3])}
+
+    def unfocus(self) -> None:
+        _check(self._lib, self._lib.bj_unfocus(self._h), "bj_unfocus")
+        self._focused = False
 
     def close(self):
         if getattr(self, "_h", None):

@@ -204,6 +204,26 @@ class GWLikelihood(Likelihood):
         return self._multi_pass(X, [_engine.ParamMap(names, const, ifos=g, nspcal=self.nspcal, nweights=self.nweights)
                                     for g in self._groups])[0]
 
+    def focus(self, params, names=None, const=None, slope_a=0.0, slope_b=0.0, slope_c=-1.0):
+        """Tell the likelihood where the sampler is (no counterpart in the reference): builds the FOCUS table around one
+        point -- ``params`` a dict, or a row of values with ``names`` / ``const`` as in ``log_like_batch`` -- so that points
+        whose phase evolution stays within ``slope_a (f/f_min)^(-5/3) + slope_b + slope_c (f/f_max)^(2/3)`` seconds of the
+        fiducial's (defaults 0.25 / 2e-3 / 0.03: the posterior of a long signal, tides free) are evaluated on a few hundred
+        all-FP64 nodes.  Everything else is routed as
+        before; results never depend on the focus beyond the parity tolerance.  Returns the node counts."""
+        if len(self._groups) != 1:
+            raise NotImplementedError("focus tables for networks of more than %d detectors" % _engine.BJ_MAX_IFO)
+        if isinstance(params, dict):
+            sub = _physical_subset(params)
+            pmap, x = _engine.ParamMap.from_dict(sub)
+        else:
+            x = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+            pmap = self.param_map(list(names), const)
+        return self.engine.focus(x, pmap, slope_a, slope_b, slope_c)
+
+    def unfocus(self):
+        self.engine.unfocus()
+
     def _multi_pass(self, X, pmaps):
         """Networks of more than BJ_MAX_IFO detectors: one pass per group of detectors on the same device-resident
         batch; per-pass logL (without phase marginalisation) and per-detector <d|h>, <h|h> are combined as

@@ -303,7 +303,7 @@ int bj_last_launch_info(bj_ctx* ctx, int32_t* info8);
  * spec4 = {mchirp_min, tau_max, reach in rad, slope margin}. */
 #define BJ_COMPRESS_LEVELS 2
 int bj_compress_info(bj_ctx* ctx, int32_t level, int32_t* info4, double* spec4);
-/* table of every walker of the last call: levels[w] = 0, 1 (compressed levels) or 2 (full grid).  Synchronises. */
+/* table of every walker of the last call: levels[w] = 0, 1 (compressed levels), 2 (full grid) or 3 (focus).  Synchronises. */
 int bj_last_levels(bj_ctx* ctx, int64_t n_walkers, int32_t* levels);
 /* Host-only (no device needed): the node axis made of a weighted frequency axis -- weights_ri[i] = interleaved (re, im)
  * per bin and detector.  out_freqs / out_weights_ri[i] must hold n_bins (2 n_bins) doubles; *out_n = number of nodes.
@@ -313,8 +313,21 @@ int bj_last_levels(bj_ctx* ctx, int64_t n_walkers, int32_t* levels);
 int bj_compress_axis_host(int64_t n_bins, const double* freqs, int32_t n_ifo, const double* const* weights_ri,
                           int32_t nodes_per_run, double reach_rad, double mchirp_min, double tau_max, double margin,
                           int64_t* out_n, double* out_freqs, double* const* out_weights_ri, int32_t* info4);
-/* walkers of the last call per table: counts3 = {level 0, level 1, full grid}.  Synchronises the device. */
-int bj_last_level_counts(bj_ctx* ctx, int64_t* counts3);
+/* walkers of the last call per table: counts4 = {level 0, level 1, full grid, focus table}.  Synchronises the device. */
+int bj_last_level_counts(bj_ctx* ctx, int64_t* counts4);
+/* Focus table: the compressed axis taken to its limit around ONE point -- the region a converged sampler lives in.  The
+ * fiducial point's phase and per-detector delays are folded into the data weights, the kernels evaluate every walker
+ * RELATIVE to it (the phase is linear in the per-walker coefficients: the subtraction is free), and the design bound is on
+ * the relative slope,  |d(P - P_fid)/df| + max_i |tau_i - tau_fid,i| <= slope_a (f / f_lo)^(-5/3) + slope_b + slope_c
+ * (f / f_hi)^(2/3)  seconds (a: masses and spins, b: sky position and time shift, c: tidal deformabilities; non-positive a, b
+ * / negative c = defaults 0.25, 2e-3, 0.03): the band collapses into a few runs of 64 nodes (C2: 521 729 bins -> ~700),
+ * evaluated in FP64 throughout.  Only walkers that respect the bound at every check frequency are evaluated there; all
+ * others are routed exactly as without a focus (and get the same bits).  Relative binning (pipe/utils/binning.py) is the
+ * first-order, unbounded version of this idea; this one is exact to the Chebyshev truncation (~1e-12).
+ * x_host [ndim] = the fiducial point (same parameter map as the batches); info4 as bj_compress_info.  bj_unfocus drops it. */
+int bj_focus(bj_ctx* ctx, const double* x_host, int32_t ndim, const bj_param_map* map, double slope_a, double slope_b,
+             double slope_c, int32_t* info4);
+int bj_unfocus(bj_ctx* ctx);
 
 #ifdef __cplusplus
 }

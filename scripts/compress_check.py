@@ -62,6 +62,7 @@ def main():
     t2 = time.time()
     ref = GWLikelihood(*net, cfg["srate"], cfg["seglen"], approx, sincos="fp64")
     info = comp.engine.compress_info()
+    info0_nodes = info["nodes"]
     print("context: compressed %.2f s, full grid %.2f s" % (t1 - t0, t2 - t1), flush=True)
     for lv in range(2):
         info = comp.engine.compress_info(lv)
@@ -92,6 +93,23 @@ def main():
           "table %s" % (len(Xs), ratio(g2, r2), comp.engine.last_level_counts()), flush=True)
     mo = timed(comp, Xs, names, const)
     print("         kernels %.4f ms for that batch" % mo[1])
+    if info0_nodes:
+        foc = comp.focus(syn.injection_params(cfg))
+        gf = comp.log_like_batch(X, names, const)
+        cnt = comp.engine.last_level_counts()
+        lv = comp.engine.last_levels(len(X))
+        print("focus table around the injection: %d nodes in %d runs; walkers per table (level 0, level 1, full grid, focus) %s; "
+              "vs fp64: focused walkers %.4f tol, all %.3f tol" % (foc["nodes"], foc["blocks"], cnt, ratio(gf[lv == 3], r[lv == 3]),
+                                                                    ratio(gf, r)), flush=True)
+        for w in sorted({W, 64}):
+            Xf = X[:W // 2][:w] if w <= W // 2 else np.concatenate([X[:W // 2]] * 2)[:w]      # posterior-scale walkers only
+            mc = timed(comp, Xf, names, const)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                comp.log_like_batch(Xf, names, const)
+            print("W=%5d posterior-scale walkers, focused: prologue %.4f kernels %.4f epilogue %.4f ms; end to end %.4f ms; tables %s"
+                  % (w, mc[0], mc[1], mc[2], (time.perf_counter() - t0) / 20 * 1e3, comp.engine.last_level_counts()), flush=True)
+        comp.unfocus()
     for w in sorted({W, 64}):
         mc = timed(comp, X[:w], names, const)
         mf = timed(full, X[:w], names, const)

@@ -129,3 +129,36 @@ def test_smaller_networks_and_phase_marginalisation_on_the_node_axis(c2, n_ifo, 
     counts = comp.engine.last_level_counts()
     print("%d detector(s), marg_phi=%s, %s: %.3f tol, tables %s" % (n_ifo, marg, approx, r, counts))
     assert r <= 0.8 and min(counts) > 0
+
+
+def test_focus_table_around_a_point(c2):
+    """the compressed axis taken to its limit around one point: posterior-scale walkers on a few hundred FP64 nodes"""
+    cfg, gold, net, names, const = c2
+    like, ref = _like(cfg, net), _like(cfg, net, sincos="fp64")
+    inj = syn.injection_params(cfg)
+    Xn, _ = syn.draw_walkers(cfg, 3000, 71, "narrow")
+    Xw, _ = syn.draw_walkers(cfg, 1000, 72, "wide")
+    X = np.concatenate([Xn, Xw])
+    before = like.log_like_batch(X, names, const)
+    info = like.focus(inj)
+    assert 64 <= info["nodes"] <= 1024 and info["kept_bins"] == 0, info
+    got = like.log_like_batch(X, names, const)
+    c0, c1, cf, cfoc = like.engine.last_level_counts()
+    assert c0 + c1 + cf + cfoc == len(X) and cfoc >= 2900, (c0, c1, cf, cfoc)
+    want = ref.log_like_batch(X, names, const)
+    levels = like.engine.last_levels(len(X))
+    in_focus = levels == 3
+    # focused walkers: all FP64 on ~300 nodes -- far inside the tolerance; the others took the path they took before
+    assert _ratio(got[in_focus], want[in_focus]) <= 0.05
+    assert np.array_equal(got[~in_focus], before[~in_focus])
+    assert _ratio(got, want) <= 1.0
+    # the focus follows the sampler: a fiducial elsewhere leaves these walkers on the ordinary tables, bit for bit
+    far = dict(inj)
+    far["mchirp"] = inj["mchirp"] * 1.01
+    like.focus(far)
+    again = like.log_like_batch(X, names, const)
+    assert like.engine.last_level_counts()[3] < 50
+    lv2 = like.engine.last_levels(len(X)) == 3
+    assert np.array_equal(again[~lv2], before[~lv2])
+    like.unfocus()
+    assert np.array_equal(like.log_like_batch(X, names, const), before) and len(like.engine.last_level_counts()) == 3
