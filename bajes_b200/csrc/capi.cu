@@ -1781,15 +1781,18 @@ extern "C" int bj_focus(bj_ctx* c, const double* x_host, int32_t ndim, const bj_
     memset(&m->dims, 0, sizeof(m->dims));
     m->n_bins = cx.n;
     Layout L;
-    // all FP64: no window, chunks of one TMA tile (64 records) -- a few hundred nodes make few CTAs as it is
+    // all FP64: no window; chunks of 16 records -- a few hundred nodes make few CTAs as it is, and a thread walks its
+    // chunk serially through ~250 dependent FP64 instructions per node (64-record chunks: 0.5 waves of CTAs, 50 us)
     if (build_layout(L, cx.n, cx.f, nullptr, nullptr, 0.0, 0.0)) { delete m; return fail(BJ_ERR_INVALID, "focus layout"); }
     {
+        int per = 16;
+        if (const char* ev = getenv("BAJES_B200_FOCUS_CHUNK")) per = std::max(2, std::min(kTileBins, atoi(ev) & ~1));
         std::vector<ChunkDesc> small;
         for (const ChunkDesc& cd : L.chunks)
-            for (int a0 = 0; a0 < cd.len; a0 += kTileBins) {
+            for (int a0 = 0; a0 < cd.len; a0 += per) {
                 ChunkDesc s = cd;
                 s.start = cd.start + a0;
-                s.len = std::min(kTileBins, cd.len - a0);
+                s.len = std::min(per, cd.len - a0);
                 small.push_back(s);
             }
         L.chunks = small;
