@@ -162,3 +162,26 @@ def test_focus_table_around_a_point(c2):
     assert np.array_equal(again[~lv2], before[~lv2])
     like.unfocus()
     assert np.array_equal(like.log_like_batch(X, names, const), before) and len(like.engine.last_level_counts()) == 3
+
+
+def test_focus_with_two_detectors_generic_phase_basis_and_phase_marginalisation(c2):
+    cfg, gold, net, names, const = c2
+    ifos, datas, dets, noises, f = net
+    sub = (ifos[:2], {k: datas[k] for k in ifos[:2]}, {k: dets[k] for k in ifos[:2]}, {k: noises[k] for k in ifos[:2]}, f)
+    approx = "TaylorF2_5.5PN_7.5PNTides2020"
+    like = _like(cfg, sub, approx=approx, marg_phi_ref=True)
+    ref = _like(cfg, sub, approx=approx, marg_phi_ref=True, sincos="fp64")
+    X, _ = syn.draw_walkers(cfg, 2000, 81, "narrow")
+    # the fiducial as a row of the batch (names / const form of the call)
+    info = like.focus(X[0], names=names, const=const)
+    assert 64 <= info["nodes"] <= 2048
+    got = like.log_like_batch(X, names, const)
+    counts = like.engine.last_level_counts()
+    assert counts[3] >= 1900, counts
+    assert _ratio(got, ref.log_like_batch(X, names, const)) <= 0.3
+    # per-detector inner products of a focused point come out of the same epilogue
+    p = {k: float(v) for k, v in zip(names, X[1])}
+    p.update(const)
+    a, b = like.inner_products(dict(p)), ref.inner_products(dict(p))
+    for ifo in like.ifos:
+        assert abs(a[ifo][0] - b[ifo][0]) <= 1e-6 + 1e-9 * abs(b[ifo][0]) and abs(a[ifo][1] - b[ifo][1]) <= 1e-9 * abs(b[ifo][1])
