@@ -128,6 +128,8 @@ struct bj_ctx {
     double* d_logl = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_tile[2] = {nullptr, nullptr};      // around the launch of the dominant (tile) kernel of the last call
+    bool tile_timed = false;
     bool timed = false;
     bool shadow = false;          // a compressed level of another context: owns static tables only
     int launch_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -192,6 +194,7 @@ static int init_common(bj_ctx* c, const bj_config* cfg) {
     for (int i = 0; i < BJ_MAX_IFO; ++i) c->cfg.det[i] = cfg->det[i];
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreate(&c->ev_tile[i]));
     return BJ_OK;
 }
 
@@ -1057,6 +1060,8 @@ extern "C" int bj_destroy(bj_ctx* c) {
     c->relbin.release();
     for (int i = 0; i < 4; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (c->ev_tile[i]) cudaEventDestroy(c->ev_tile[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return BJ_OK;
@@ -1185,10 +1190,12 @@ static int launch_fullgrid_mixed(bj_ctx* c, long n_walkers, cudaStream_t st, int
         }
         CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         dim3 tgrid((unsigned)(c1 - c0), (unsigned)((n_walkers + kTileWalkers - 1) / kTileWalkers));
+        if (!c->shadow) { CUDA_TRY(cudaEventRecord(c->ev_tile[0], st)); }
         tkern<<<tgrid, kTileThreads, smem_t, st>>>((const unsigned char*)c->d_tile_basis, (const unsigned char*)c->d_tile_data,
                                                    (const unsigned char*)c->d_rec, RB, c->d_chunks, c->d_coef,
                                                    c->cap_walkers, n_walkers, c->d_partial, c0, c->grid_df,
                                                    c->d_coef_ex, c->dims, sel, MultiTable{});
+        if (!c->shadow) { CUDA_TRY(cudaEventRecord(c->ev_tile[1], st)); c->tile_timed = true; }
         note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1317,8 +1324,11 @@ static int launch_multi(bj_ctx* c, long n_walkers, cudaStream_t st, double* logl
         auto tkern = fullgrid_tile_kernel<NIFO, MODEL, SC, false, false, false>;
         CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         dim3 tgrid((unsigned)max_fast, (unsigned)((n_walkers + kTileWalkers - 1) / kTileWalkers + mt.n - 1));
+        CUDA_TRY(cudaEventRecord(c->ev_tile[0], st));
         tkern<<<tgrid, kTileThreads, smem_t, st>>>(nullptr, nullptr, nullptr, RB, nullptr, c->d_coef, c->cap_walkers, n_walkers,
                                                    c->d_partial, 0, 0.0, nullptr, c->dims, none, mt);
+        CUDA_TRY(cudaEventRecord(c->ev_tile[1], st));
+        c->tile_timed = true;
         CUDA_TRY(cudaGetLastError());
         note_launch(c, tgrid, smem_t, RT / 8, MODEL, kTileThreads);
     }
@@ -1640,6 +1650,29 @@ extern "C" int bj_last_kernel_ms(bj_ctx* c, float* ms3) {
     if (!c->timed) return fail(BJ_ERR_INVALID, "no call has been timed yet");
     CUDA_TRY(cudaEventSynchronize(c->ev[3]));
     for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms3[i], c->ev[i], c->ev[i + 1]));
+    return BJ_OK;
+}
+
+extern "C" int bj_last_tile_ms(bj_ctx* c, float* ms) {
+    if (!c || !ms) return fail(BJ_ERR_INVALID, "null argument");
+    if (!c->tile_timed) return fail(BJ_ERR_INVALID, "no call has launched the tile kernel yet");
+    CUDA_TRY(cudaEventSynchronize(c->ev_tile[1]));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->ev_tile[0], c->ev_tile[1]));
+    return BJ_OK;
+}
+
+extern "C" int bj_table_info(bj_ctx* c, int32_t table, int64_t* out4) {
+    if (!c || !out4) return fail(BJ_ERR_INVALID, "null argument");
+    const bj_ctx* m = nullptr;
+    if (table >= 0 && table < c->n_levels) m = c->cmp[table];
+    else if (table == kMaxLevels) m = c;
+    else if (table == kMaxLevels + 1) m = c->focus;
+    for (int q = 0; q < 4; ++q) out4[q] = 0;
+    if (!m || c->kind != KIND_FULLGRID) return BJ_OK;
+    out4[0] = m->n_bins_kernel;
+    out4[1] = m->prec_hi - m->prec_lo;
+    out4[2] = m->n_chunks;
+    out4[3] = m->n_precise;
     return BJ_OK;
 }
 

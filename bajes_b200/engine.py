@@ -141,6 +141,8 @@ EXPORTS = {
     "bj_measure_peak": (C.c_int, [C.c_int, C.c_int, _DP]),
     "bj_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bj_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "bj_last_tile_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "bj_table_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "bj_compress_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), _DP]),
     "bj_last_level_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "bj_last_levels": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
@@ -520,6 +522,18 @@ class Engine:
         ms = (C.c_float * 3)()
         _check(self._lib, self._lib.bj_last_kernel_ms(self._h, ms), "bj_last_kernel_ms")
         return [ms[0], ms[1], ms[2]]
+
+    def last_tile_ms(self) -> float:
+        """Duration of the tile kernel of the last call alone (CUDA events around its launch).  Synchronises."""
+        ms = C.c_float()
+        _check(self._lib, self._lib.bj_last_tile_ms(self._h, C.byref(ms)), "bj_last_tile_ms")
+        return float(ms.value)
+
+    def table_info(self, table: int) -> Dict[str, int]:
+        """table 0, 1 = compressed levels, 2 = full grid, 3 = focus: {"slots", "window_slots", "chunks", "window_chunks"}"""
+        out = (C.c_int64 * 4)()
+        _check(self._lib, self._lib.bj_table_info(self._h, int(table), out), "bj_table_info")
+        return {"slots": int(out[0]), "window_slots": int(out[1]), "chunks": int(out[2]), "window_chunks": int(out[3])}
 
     def last_launch_info(self):
         info = (C.c_int32 * 8)()

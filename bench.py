@@ -393,9 +393,11 @@ def make_evaluator(c, like, names, const, capacity):
                             local_eval_device=eval_dev, capacity=capacity)
 
 
-def build_roofline(cfg, args, nifo, W, units, info, k_s, peaks, pk, tensor_core, rot, traffic_key, comp):
-    """Roofline object of one step.  `units` = walker x (bins or nodes) the kernels evaluate; comp = None for the full grid,
-    else {"counts": walkers per table, "nodes": nodes per level, "n_bins": ..} for a context with compressed axes."""
+def build_roofline(cfg, args, nifo, W, units, info, k_s, peaks, pk, tensor_core, rot, traffic_key, comp, interval_s=None,
+                   interval_units=None):
+    """Roofline object of the dominant (tile) kernel.  `units` = walker x (bins or nodes) IT evaluates, k_s its own duration;
+    comp = None for the full grid, else {"counts": walkers per table, "nodes": tile-kernel nodes per table, "n_bins": ..} for a
+    context with compressed axes.  interval_s / interval_units: everything between the prologue's and the epilogue's events."""
     fp64_pu, sfu_pu = instr_per_unit(cfg["approx"], nifo, args.sincos, tensor_core, rot)
     if comp:
         fp64_pu += nifo                    # non-uniform axis: the time-delay ramp is one DFMA per node and detector
@@ -416,26 +418,29 @@ def build_roofline(cfg, args, nifo, W, units, info, k_s, peaks, pk, tensor_core,
     other = "sfu" if bound == "fp64" else "fp64"
     K = 12 if cfg["approx"] == "TaylorF2_3.5PN" else 28
     if comp:
-        kernel = ("classify_kernel + per table {fullgrid_window_kernel (FP64, heaviest nodes) + fullgrid_tile_kernel<%d ifo, %s, "
-                  "%s, non-uniform axis> + epilogue_kernel}: the time between the prologue's event and the last table's "
-                  "epilogue" % (nifo, cfg["approx"], args.sincos))
-        note = ("executed work: a call on ~22 600 nodes is no longer one long kernel -- fixed costs (classification, short "
-                "chunks of 256 nodes per CTA, one pass per table) and the FP64 window (16 % of the nodes at ~2.2x the cost per "
-                "node) share the interval; the full-grid kernel's own fraction is in full_grid.roofline")
-        units_note = ("walker x node pairs actually evaluated: %s walkers on the level-0 / level-1 / full-grid tables of %d / "
-                      "%d / %d nodes; the metric's %d walker x bins are %.1f times as many"
-                      % (comp["counts"], comp["nodes"][0], comp["nodes"][1], comp["n_bins"], W * comp["n_bins"],
-                         W * comp["n_bins"] / max(1, units)))
+        kernel = ("fullgrid_tile_kernel<%d ifo, %s, %s, non-uniform axis>, ONE launch over all tables: CUDA events around the "
+                  "launch (bj_last_tile_ms)" % (nifo, cfg["approx"], args.sincos))
+        note = ("executed work of the tile kernel alone.  The step is no longer one long kernel: `interval` is everything "
+                "between the prologue's and the epilogue's events -- classification, the FP64 window (16 % of the nodes at "
+                "~2.7x the cost per node), this kernel, the early-exit fix-up launch; the full-grid kernel's own fraction is "
+                "in full_grid.roofline")
+        units_note = ("walker x node pairs the tile kernel evaluates: %s walkers on the level-0 / level-1 / full-grid tables, "
+                      "%d / %d / %d slots each outside the FP64 window" % (comp["counts"], comp["nodes"][0], comp["nodes"][1],
+                                                                          comp["n_bins"]))
     else:
-        kernel = ("fullgrid_window_kernel (FP64, heaviest bins) + fullgrid_%s_kernel<%d ifo, %s, %s%s>: the time between the "
-                  "prologue's and the epilogue's events"
+        kernel = ("fullgrid_%s_kernel<%d ifo, %s, %s%s>: CUDA events around the launch (bj_last_tile_ms); `interval` adds the FP64 "
+                  "window kernel and the early-exit fix-up launch"
                   % ("tile" if tensor_core else "mixed" if args.sincos != "fp64" else "fp64", nifo, cfg["approx"], args.sincos,
                      ", rotated detectors" if rot else ""))
         note = ("what limits this kernel is neither pipe but instruction issue / register-operand bandwidth (DESIGN.md "
                 "section 4.1): with one MUFU pair per bin the SFU line no longer measures it; the FP64 line (12 of its 13.9 "
                 "FMAs per unit run as DMMA.8x8x4) is the larger of the two the north star names")
-        units_note = "walker x bins"
-    return {"bound": bound, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": unit,
+        units_note = "walker x bins outside the FP64 window"
+    interval = None
+    if interval_s:
+        interval = {"ms": interval_s * 1e3, "units": interval_units,
+                    "frac_if_all_units_ran_at_tile_cost": interval_units * ipu / interval_s / peak}
+    return {"bound": bound, "interval": interval, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": unit,
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "instr_per_unit": ipu,
             "units_per_launch": units, "units": units_note, "kernel_ms": k_s * 1e3, "kernel": kernel,
             "peak_source": "measured live by bj_measure_peak (register-resident DFMA / MUFU chains); "
@@ -813,7 +818,7 @@ def main():
         step_device()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = []
+    kern_ms, tile_ms = [], []
     barrier()
     clocks.mark()
     t_wall0 = time.perf_counter()
@@ -824,6 +829,7 @@ def main():
         b.record()
         b.synchronize()
         kern_ms.append(like.engine.last_kernel_ms()[1])
+        tile_ms.append(like.engine.last_tile_ms())
         if rank == 0:
             clocks.sample()                        # between two timed steps
     barrier()
@@ -847,7 +853,7 @@ def main():
                                  compress=False)
         shf = DeviceShardedLikelihood(like_full, names, const)
         outf_dev = torch.empty(W, dtype=torch.float64, device=dev)
-        fk = []
+        fk, ftile = [], []
 
         def step_full():
             shf.evaluate_local(x_dev, outf_dev)
@@ -864,6 +870,7 @@ def main():
             b.synchronize()
             fms.append(a.elapsed_time(b))
             fk.append(like_full.engine.last_kernel_ms()[1])
+            ftile.append(like_full.engine.last_tile_ms())
         full_ms = max_over_ranks(c, float(np.mean(fms)))
         d = (out_dev - outf_dev).abs() / (1e-6 * outf_dev.abs() + 1e-4)
         d = torch.where(torch.isfinite(outf_dev), d, torch.zeros_like(d))
@@ -887,6 +894,8 @@ def main():
                                 "path": "bj_loglike (host pointers)"}
         full_info = like_full.engine.last_launch_info()
         full_kernel_s = float(np.mean(fk)) * 1e-3
+        full_tile_s = float(np.mean(ftile)) * 1e-3
+        full_tab = like_full.engine.table_info(2)
         like_full.engine.close()
 
     # ---- the same step with a FOCUS table around the injection (what a converged sampler gets) ------
@@ -1030,23 +1039,30 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------
+    # the tile kernel alone: its own CUDA events (bj_last_tile_ms) and the units IT evaluates (table slots minus the FP64
+    # window's); the whole interval between prologue and epilogue is reported beside it
     info = like.engine.last_launch_info()
     tensor_core = info[2] == 256           # fullgrid_tile_kernel: 256 threads = 64 walkers per CTA
     rot = tensor_core and nifo > 1 and not os.environ.get("BAJES_B200_NO_ROT")
     k_s = float(np.mean(kern_ms)) * 1e-3
+    t_s = float(np.mean(tile_ms)) * 1e-3
     if compressed:
-        # the full-grid step has its own roofline; the compressed step is measured on the units it EXECUTES
-        full_grid["roofline"] = build_roofline(cfg, args, nifo, W, W * nb, full_info, full_kernel_s, peaks, pk, True, rot,
-                                               args.config + ":" + args.sincos, None)
-        nodes = [ci["nodes"] for ci in cinfo]
-        units = level_counts[0] * nodes[0] + level_counts[1] * nodes[1] + level_counts[2] * nb
-        roofline = build_roofline(cfg, args, nifo, W, units, info, k_s, peaks, pk, tensor_core, False,
+        ft = full_tab
+        full_grid["roofline"] = build_roofline(cfg, args, nifo, W, W * (ft["slots"] - ft["window_slots"]), full_info,
+                                               full_tile_s, peaks, pk, True, rot, args.config + ":" + args.sincos, None,
+                                               interval_s=full_kernel_s, interval_units=W * nb)
+        tabs = [like.engine.table_info(t) for t in range(3)]
+        fast = [t["slots"] - t["window_slots"] for t in tabs]
+        units = sum(level_counts[lv] * fast[lv] for lv in range(3))
+        all_units = sum(level_counts[lv] * tabs[lv]["slots"] for lv in range(3))
+        roofline = build_roofline(cfg, args, nifo, W, units, info, t_s, peaks, pk, tensor_core, False,
                                   args.config + ":" + args.sincos + ":compressed",
-                                  {"counts": list(level_counts), "nodes": nodes, "n_bins": nb})
+                                  {"counts": list(level_counts), "nodes": fast, "n_bins": fast[2]},
+                                  interval_s=k_s, interval_units=all_units)
     else:
-        roofline = build_roofline(cfg, args, nifo, W, W * nb, info, k_s, peaks, pk, tensor_core, rot,
-                                  args.config + ":" + args.sincos, None)
-
+        tab = like.engine.table_info(2)
+        roofline = build_roofline(cfg, args, nifo, W, W * (tab["slots"] - tab["window_slots"]), info, t_s, peaks, pk,
+                                  tensor_core, rot, args.config + ":" + args.sincos, None, interval_s=k_s, interval_units=W * nb)
     value = W * world * nb * args.steps / total_s
     e2e_value = W * world * nb * args.steps / e2e_s
 

@@ -294,6 +294,11 @@ int bj_measure_peak(int device, int which, double* out);
 /* timing of the last bj_loglike* call on this context, measured with CUDA events on the
  * launching stream: ms[0] = prologue, ms[1] = main kernel, ms[2] = epilogue.  Synchronises. */
 int bj_last_kernel_ms(bj_ctx* ctx, float* ms3);
+/* duration of the dominant (tensor-core tile) kernel of the last call alone, CUDA events around its launch.  Synchronises. */
+int bj_last_tile_ms(bj_ctx* ctx, float* ms);
+/* table: 0, 1 = compressed levels, 2 = the full grid, 3 = the focus table.  out4 = {table slots, slots of the FP64 window,
+ * chunks, chunks of the FP64 window} (zeros when the table does not exist): the tile kernel evaluates slots - window slots. */
+int bj_table_info(bj_ctx* ctx, int32_t table, int64_t* out4);
 /* static description of the last launch: grid, block, dynamic smem, bins per chunk, #chunks */
 int bj_last_launch_info(bj_ctx* ctx, int32_t* info8);
 /* Compressed frequency axes of a full-grid context (bj_extras.compress*).  A context holds up to BJ_COMPRESS_LEVELS node
