@@ -138,3 +138,49 @@ def test_inner_products_of_the_oracle_on_the_node_axis():
         a, b = dh(p, f, w), dh(p, nf, nw)
         # <d|h> ~ 1e1..1e4 here; the logL tolerance floor is 1e-4
         assert np.max(np.abs(a - b)) <= 1e-9, (p["mchirp"], p["time_shift"], np.abs(a - b))
+
+
+def test_heterodyned_weights_collapse_the_band_for_walkers_near_a_fiducial():
+    """the idea behind the focus table (capi.cu: bj_focus), with the oracle port's waveforms: fold the fiducial waveform's
+    phase into the data weights and the factor left over for a nearby walker is so smooth that an axis designed for
+    *seconds* of slope reproduces its <d|h> -- while the same axis is useless for the un-heterodyned weights"""
+    cfg = dict(syn.CONFIGS["C2_small"])
+    cfg.update(seglen=64.0, srate=4096.0)
+    like = harness.port_likelihood(cfg)
+    ifos, T = like.ifos, cfg["seglen"]
+    f = like.dets[ifos[0]].freqs
+    const = syn.constants(cfg)
+    inj = syn.injection_params(cfg)
+
+    def strain(p, freqs):
+        wave = port.WaveformPort(freqs, cfg["srate"], T, cfg["approx"])
+        hphc = wave.compute_hphc(dict(p))
+        out = []
+        for i in ifos:
+            d = like.dets[i]
+            keep = d.freqs
+            d.freqs = freqs
+            out.append(d.project_fdwave(hphc, dict(p)) * np.exp(-1j * np.pi * freqs * T))
+            d.freqs = keep
+        return np.array(out)
+
+    w = np.stack([4.0 / T * np.conj(like.dets[i].data) / like.dets[i].psd * np.exp(1j * np.pi * f * T) for i in ifos])
+    h_fid = strain(inj, f)
+    w_het = w * h_fid / np.abs(h_fid)                        # weights carry the fiducial's phase (per detector)
+    # an axis for 0.3 s of slope at f_min falling as the Newtonian chirp, plus 2 ms: a heavy-binary design used as a stand-in
+    # for the focus budget a (f/f_lo)^(-5/3) + b
+    kw = dict(mchirp_min=12.0, tau_max=2e-3)
+    nf, nw_het, info = engine.compress_axis(f, w_het, **kw)
+    _, nw_raw, _ = engine.compress_axis(f, w, **kw)
+    assert info["nodes"] < len(f) / 100 and info["kept_bins"] == 0, info
+    hn_fid = strain(inj, nf)
+    X, names = syn.draw_walkers(cfg, 4, 5, "narrow")
+    for x in X:
+        p = {k: float(v) for k, v in zip(names, x)}
+        p.update(const)
+        exact = np.sum(w * strain(p, f), axis=1)
+        hn = strain(p, nf)
+        het = np.sum(nw_het * hn * np.abs(hn_fid) / hn_fid, axis=1)      # walker relative to the fiducial, at the nodes
+        raw = np.sum(nw_raw * hn, axis=1)
+        assert np.max(np.abs(het - exact)) <= 1e-8, np.abs(het - exact)
+        assert np.max(np.abs(raw - exact)) > 1.0                          # without the heterodyne the axis is far too sparse
