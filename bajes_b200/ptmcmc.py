@@ -77,6 +77,9 @@ def apply_bounds_batch(Q, periodic, bounds):
     """Row-wise ``apply_bounds`` (utils.py:168-198): periodic wrap or reflection of every out-of-bounds coordinate, element
     by element with the reference's own expressions (so the bits agree); in-bounds coordinates are untouched."""
     Q = np.array(Q, dtype=np.float64, copy=True)
+    b = np.asarray(bounds, dtype=np.float64)
+    if not (np.any(Q < b[:, 0]) or np.any(Q > b[:, 1])):         # the common case: nothing to move (list_in_bounds, :171)
+        return Q
     for i, (per, (lo, up)) in enumerate(zip(periodic, bounds)):
         x = Q[..., i]
         below, above = x < lo, x > up
