@@ -126,6 +126,7 @@ struct bj_ctx {
     double* d_x = nullptr;
     long cap_x = 0;
     double* d_logl = nullptr;
+    long cap_logl = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_tile[2] = {nullptr, nullptr};      // around the launch of the dominant (tile) kernel of the last call
@@ -1076,7 +1077,6 @@ static int ensure_workspace(bj_ctx* c, long n_walkers) {
     CUDA_TRY(cudaDeviceSynchronize());
     cudaFree(c->d_coef); c->d_coef = nullptr;
     cudaFree(c->d_partial); c->d_partial = nullptr;
-    cudaFree(c->d_logl); c->d_logl = nullptr;
     cudaFree(c->d_coef_ex); c->d_coef_ex = nullptr;
     c->cap_walkers = 0;
     CUDA_TRY(cudaMalloc(&c->d_coef, (size_t)C_NUM * cap * sizeof(double)));
@@ -1094,7 +1094,6 @@ static int ensure_workspace(bj_ctx* c, long n_walkers) {
         CUDA_TRY(cudaMalloc(&c->d_lists, (size_t)(c->n_levels + 2) * cap * sizeof(int)));
     }
     if (part) CUDA_TRY(cudaMalloc(&c->d_partial, part * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c->d_logl, (size_t)cap * sizeof(double)));
     c->cap_walkers = cap;
     return BJ_OK;
 }
@@ -1553,7 +1552,16 @@ extern "C" int bj_loglike_device_ex(bj_ctx* c, const double* x_dev, int64_t n_wa
     if (!c) return fail(BJ_ERR_INVALID, "null context");
     if (n_walkers == 0) return BJ_OK;
     if (n_walkers < 0 || ndim <= 0 || !x_dev || !out_logl_dev) return fail(BJ_ERR_INVALID, "bad batch arguments");
-    return run_device(c, x_dev, (long)n_walkers, ndim, map, emap, out_logl_dev, out_parts_dev, (cudaStream_t)stream);
+    // walkers are independent: batches beyond 2^21 are evaluated in slices (the walker-tile index of the bin kernels is a
+    // grid.y coordinate, limited to 65 535 tiles of 64)
+    const int64_t slice = 1LL << 21;
+    for (int64_t w0 = 0; w0 < n_walkers; w0 += slice) {
+        const long nw = (long)std::min(slice, n_walkers - w0);
+        int rc = run_device(c, x_dev + (size_t)w0 * ndim, nw, ndim, map, emap, out_logl_dev + w0,
+                            out_parts_dev ? out_parts_dev + (size_t)w0 * c->cfg.n_ifo * 3 : nullptr, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return BJ_OK;
 }
 
 // ---- frequency-axis split: local partial sums of a chunk range, and the epilogue on reduced sums -----------
@@ -1629,10 +1637,17 @@ extern "C" int bj_loglike_ex(bj_ctx* c, const double* x_host, int64_t n_walkers,
         CUDA_TRY(cudaMalloc(&c->d_x, (size_t)need * sizeof(double)));
         c->cap_x = need;
     }
-    int rc = ensure_workspace(c, (long)n_walkers);
-    if (rc) return rc;
+    if ((long)n_walkers > c->cap_logl) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(c->d_logl);
+        c->d_logl = nullptr;
+        c->cap_logl = 0;
+        const long cap = pad_walkers(std::max((long)n_walkers, 2 * c->cap_logl));
+        CUDA_TRY(cudaMalloc(&c->d_logl, (size_t)cap * sizeof(double)));
+        c->cap_logl = cap;
+    }
     CUDA_TRY(cudaMemcpyAsync(c->d_x, x_host, (size_t)need * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    rc = run_device(c, c->d_x, (long)n_walkers, ndim, map, emap, c->d_logl, nullptr, c->stream);
+    int rc = bj_loglike_device_ex(c, c->d_x, n_walkers, ndim, map, emap, c->d_logl, nullptr, c->stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_logl_host, c->d_logl, (size_t)n_walkers * sizeof(double), cudaMemcpyDeviceToHost,
                              c->stream));

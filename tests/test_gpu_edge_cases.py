@@ -231,3 +231,18 @@ def test_networks_of_more_than_three_detectors(ifos, marg):
     assert sorted(ip) == sorted(ifos)
     h = like.project_fdwave(dict(p))
     assert sorted(h) == sorted(ifos) and len(h[ifos[-1]]) == len(h[ifos[0]]) == like.engines[0].n_bins
+
+
+def test_batches_beyond_two_million_walkers_are_sliced():
+    """walker tiles are a grid.y coordinate (<= 65 535 tiles of 64): the C ABI evaluates larger batches in slices of 2^21;
+    every walker gets the bits it gets in a small call"""
+    cfg = dict(syn.CONFIGS["C1"])
+    cfg.update(f_max=128.0)                      # 433 bins: the batch, not the band, is what is large here
+    like, _ = _pair(cfg)
+    n = (1 << 21) + 4099
+    X, names = syn.draw_walkers(cfg, 4099, 7, "wide")
+    big = np.tile(X, (n // len(X) + 1, 1))[:n]
+    got = like.log_like_batch(big, names, syn.constants(cfg))
+    small = like.log_like_batch(X, names, syn.constants(cfg))
+    assert got.shape == (n,)
+    assert np.array_equal(got[:4099], small) and np.array_equal(got[-4099:], np.tile(small, 3)[(n - 4099) % 4099:][:4099])
