@@ -97,7 +97,11 @@ class PTEnsembleSampler(object):
     (``_chain_history [ntemps, nwalkers, iterations, dim]``, ``_loglikelihood_history``, ``_logposterior_history``)."""
 
     def __init__(self, nwalkers, posterior, ntemps=None, Tmax=None, betas=None, stretch=2.0, random=None, rng="reference",
-                 adaptation_lag=10000, adaptation_time=100):
+                 adaptation_lag=10000, adaptation_time=100, refocus_every=0, focus_fn=None):
+        """``refocus_every`` / ``focus_fn`` (no counterpart in the reference): every that many iterations the best point of
+        the cold chain is handed to ``focus_fn(point_row)`` -- by default ``posterior.like.focus(row, names, const)`` when the
+        likelihood has one (bajes_b200.GWLikelihood.focus: the focus table of DESIGN.md section 4.9).  It moves no random
+        number and changes no result beyond the likelihood's parity tolerance; 0 = never."""
         if nwalkers % 2 != 0:
             raise ValueError('The number of walkers must be even.')
         if rng not in ("reference", "vector"):
@@ -127,6 +131,12 @@ class PTEnsembleSampler(object):
         self.nprop_accepted = np.zeros((self.ntemps, self.nwalkers))
         self.n_batched_calls = 0
         self.n_points = 0
+        self.refocus_every = int(refocus_every)
+        self.n_refocus = 0
+        if focus_fn is None and self.refocus_every > 0 and hasattr(getattr(posterior, "like", None), "focus"):
+            prior = posterior.prior
+            focus_fn = lambda row: posterior.like.focus(row, names=list(prior.names), const=dict(getattr(prior, "const", {})))
+        self._focus_fn = focus_fn
 
     # ---- likelihood: ONE batched call per half-ensemble of all temperatures (ptmcmc.py:272-281) -----------------------
     def _evaluate(self, ps):
@@ -277,6 +287,11 @@ class PTEnsembleSampler(object):
                     self._acceptance_history.append(self.nprop_accepted / self.nprop)
                     self._tswap_acceptance_history.append(self.nswap_accepted / self.nswap)
             self._time += 1
+            if self.refocus_every > 0 and self._focus_fn is not None and self._time % self.refocus_every == 0:
+                cold = int(np.argmax(self._betas))                 # beta = 1
+                best = int(np.argmax(np.where(np.isfinite(logl[cold]), logl[cold], -np.inf)))
+                self._focus_fn(np.array(p[cold, best], dtype=np.float64))
+                self.n_refocus += 1
         self._p0, self._logposterior0, self._loglikelihood0 = p, logpost, logl
         return p, logpost, logl
 

@@ -176,3 +176,27 @@ def test_reference_chain_on_the_gpu_likelihood():
     assert same.mean() == 1.0, "chain departs from the reference's in %d of %d states" % ((~same).sum(), same.size)
     ref = gold["loglike_hist"]
     assert np.all(np.abs(s._loglikelihood_history - ref) <= 1e-6 * np.abs(ref) + 1e-4)
+
+
+def test_refocus_hook_hands_the_best_cold_point_to_the_likelihood_and_moves_no_random_number():
+    class _G(_Gauss):
+        def __init__(self):
+            self.focused = []
+
+        def focus(self, row, names=None, const=None):
+            assert list(names) == ["a", "b", "c"] and const == {}
+            self.focused.append(np.array(row))
+
+    prior = BoxPrior(["a", "b", "c"], [[-6, 6], [-6, 6], [-6, 6]], {})
+    p0 = np.random.default_rng(4).uniform(-1, 1, size=(3, 40, 3))
+    plain = PTEnsembleSampler(40, Posterior(_Gauss(), prior), ntemps=3, random=np.random.default_rng(3), rng="vector")
+    plain.sample(iterations=30, p0=p0.copy())
+    like = _G()
+    s = PTEnsembleSampler(40, Posterior(like, prior), ntemps=3, random=np.random.default_rng(3), rng="vector", refocus_every=10)
+    s.sample(iterations=30, p0=p0.copy())
+    assert s.n_refocus == 3 and len(like.focused) == 3
+    assert np.array_equal(s._chain_history, plain._chain_history)          # the hook draws nothing
+    # what it handed over is the best point of the cold chain at that iteration
+    for k, it in enumerate((9, 19, 29)):
+        j = int(np.argmax(s._loglikelihood_history[0, :, it]))
+        assert np.array_equal(like.focused[k], s._chain_history[0, j, it])
