@@ -823,11 +823,16 @@ def main():
 
     # ---- device-resident timing ---------------------------------------------------------------------------
     clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
+    clocks.start()                                 # every rank watches its own GPU (in-process NVML)
     barrier()
-    for _ in range(max(args.warmup, 3)):
+    # W warm-up steps as asked, and then as many more as it takes to keep the GPU busy for 0.3 s: a step is ~0.3 ms now,
+    # three of them do not bring an idle GPU up to its boost clock (seen as one rank of four at 1.7x the others' step)
+    n_warm, t_warm0 = 0, time.perf_counter()
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm0 < 0.3:
         step_device()
+        n_warm += 1
+        if n_warm % 16 == 0:
+            torch.cuda.synchronize(dev)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms, tile_ms = [], []
@@ -842,8 +847,7 @@ def main():
         b.synchronize()
         kern_ms.append(like.engine.last_kernel_ms()[1])
         tile_ms.append(like.engine.last_tile_ms())
-        if rank == 0:
-            clocks.sample()                        # between two timed steps
+        clocks.sample()                            # between two timed steps
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -1024,7 +1028,15 @@ def main():
         e2e_path = ("ShardedEvaluator.evaluate, no collective: host X -> ONE H2D copy into the sampler rank's HBM -> every rank's "
                     "prologue reads its rows, and every rank's epilogue stores its logL, over NVLink peer memory (flag-ordered) -> D2H") \
             if peer else "ShardedEvaluator.evaluate: host X -> H2D -> NCCL scatter -> per-rank kernels -> NCCL gather -> D2H (no peer access)"
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop()
+    if world > 1:
+        mine = torch.tensor([float(clk.get("sm_mhz") or 0.0)], dtype=torch.float64, device=dev)
+        allc = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allc, mine)
+        clk["per_rank_sm_mhz"] = allc.cpu().numpy().tolist()
+    clk["warmup_steps_run"] = n_warm
+    if rank != 0:
+        clk = None
 
     # ---- peaks and the secondary configs (collective: every rank takes part) -------------------------------------
     peaks = {"dfma": engine.measure_peak("dfma", local), "mufu": engine.measure_peak("mufu", local)}
